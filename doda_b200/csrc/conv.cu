@@ -1,0 +1,459 @@
+// conv.cu — output-stationary gather-GEMM for sparse convolution (fp32 CUDA-core path).
+//
+// Replaces spconv v1.2 `indice_conv` / `indice_conv_backward` (per offset: gather kernel -> cuBLAS SGEMM ->
+// scatter-add kernel).  One launch per conv instead of 1 + 26*3:
+//   * a CTA owns BM output rows x BN output channels and loops over the kernel offsets that have at
+//     least one neighbour in the tile; neighbour rows are gathered with 16-byte cp.async (zero-filled
+//     for missing neighbours) straight into a 3-stage shared-memory ring, W[k] chunks ride in the same ring;
+//   * every output row is written exactly once (float4 stores) -> no scatter atomics, no [P, C]
+//     gather/scatter buffers crossing HBM;
+//   * dgrad is the same kernel on the mirrored/transposed weights; wgrad walks the canonical pair lists.
+#include "common.cuh"
+#include <algorithm>
+
+namespace b200sp {
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem, int src_bytes) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+struct GGParams {
+    const float* in;
+    const float* W;       // [K][Cin][Cout]
+    const int* tab;       // TAB mode: [n_rows][K] input rows (or NULL with K==1: identity)
+    const int* pin;       // PAIRS mode: [K][pstride] input rows
+    const int* pout;      // PAIRS mode: [K][pstride] output rows
+    const int* pairnum;   // PAIRS mode: device [K]
+    float* out;
+    int64_t n_rows;       // TAB mode: number of output rows
+    int64_t pstride;
+    int Cin, Cout, K;
+    int accumulate;
+    int pairs_mode;
+};
+
+constexpr int GG_BK = 16;
+constexpr int GG_STAGES = 3;
+constexpr int GG_MAXK = 32;
+
+template <int BM, int BN, int TM, int TN>
+struct GGSmem {
+    float A[GG_STAGES][BM][GG_BK + 4];
+    float Wt[GG_STAGES][GG_BK][BN];
+    int idx[BM * GG_MAXK];  // TAB: [BM][K]; PAIRS: [BM]
+    int orow[BM];
+    int klist[GG_MAXK];
+    int kflag[GG_MAXK];
+    int nk;
+};
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN)) k_gather_gemm(GGParams p) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    constexpr int RT = BM / TM;  // row-threads
+    constexpr int CT = BN / TN;  // col-threads
+    static_assert(TN % 4 == 0, "TN must be a multiple of 4");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    GGSmem<BM, BN, TM, TN>& sm = *reinterpret_cast<GGSmem<BM, BN, TM, TN>*>(smem_raw);
+
+    const int tid = threadIdx.x;
+    const int tx = tid % CT, ty = tid / CT;
+    const int n0 = blockIdx.y * BN;
+    const int K = p.K;
+    int64_t row0 = (int64_t)blockIdx.x * BM;
+    int rows;
+    int kfixed = 0;
+    const int KT = p.pairs_mode ? 1 : K;  // idx columns held per row
+
+    if (p.pairs_mode) {
+        kfixed = blockIdx.z;
+        int n = p.pairnum[kfixed];
+        if (row0 >= n) return;
+        rows = (int)min((int64_t)BM, n - row0);
+        for (int r = tid; r < BM; r += NT) {
+            bool ok = r < rows;
+            sm.idx[r] = ok ? p.pin[(int64_t)kfixed * p.pstride + row0 + r] : -1;
+            sm.orow[r] = ok ? p.pout[(int64_t)kfixed * p.pstride + row0 + r] : -1;
+        }
+        if (tid == 0) {
+            sm.nk = 1;
+            sm.klist[0] = 0;
+        }
+    } else {
+        rows = (int)min((int64_t)BM, p.n_rows - row0);
+        if (tid < GG_MAXK) sm.kflag[tid] = 0;
+        __syncthreads();
+        if (p.tab) {
+            for (int i = tid; i < BM * K; i += NT) {
+                int v = (i < rows * K) ? p.tab[row0 * K + i] : -1;
+                sm.idx[i] = v;
+                if (v >= 0) sm.kflag[i % K] = 1;
+            }
+        } else {  // identity rows (1x1 conv / dense GEMM)
+            for (int r = tid; r < BM; r += NT) sm.idx[r] = r < rows ? (int)(row0 + r) : -1;
+            if (tid == 0) sm.kflag[0] = 1;
+        }
+        for (int r = tid; r < BM; r += NT) sm.orow[r] = r < rows ? (int)(row0 + r) : -1;
+        __syncthreads();
+        if (tid == 0) {
+            int nk = 0;
+            for (int k = 0; k < K; ++k)
+                if (sm.kflag[k]) sm.klist[nk++] = k;
+            sm.nk = nk;
+        }
+    }
+    __syncthreads();
+
+    const int nk = sm.nk;
+    const int Cin = p.Cin, Cout = p.Cout;
+    const int nck = (Cin + GG_BK - 1) / GG_BK;
+    const int nsteps = nk * nck;
+    const bool vecA = (Cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0);
+    const bool vecW = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.W) & 15) == 0);
+
+    auto load_step = [&](int step, int stage) {
+        int kk = step / nck;
+        int c0 = (step - kk * nck) * GG_BK;
+        int kcol = sm.klist[kk];             // column in idx
+        int kw = p.pairs_mode ? kfixed : kcol;  // weight slice
+        // A: BM rows x 4 chunks of 16 B
+        for (int i = tid; i < BM * (GG_BK / 4); i += NT) {
+            int r = i >> 2, c4 = i & 3;
+            int src = sm.idx[r * KT + kcol];
+            int col = c0 + c4 * 4;
+            float* dst = &sm.A[stage][r][c4 * 4];
+            if (vecA) {
+                bool ok = (src >= 0) && (col < Cin);
+                const float* g = ok ? p.in + (int64_t)src * Cin + col : p.in;
+                cp_async16(dst, g, ok ? 16 : 0);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    bool ok = (src >= 0) && (col + e < Cin);
+                    const float* g = ok ? p.in + (int64_t)src * Cin + col + e : p.in;
+                    cp_async4(dst + e, g, ok ? 4 : 0);
+                }
+            }
+        }
+        // W: BK rows x BN/4 chunks
+        const float* Wk = p.W + (int64_t)kw * Cin * Cout;
+        for (int i = tid; i < GG_BK * (BN / 4); i += NT) {
+            int r = i / (BN / 4), c4 = i % (BN / 4);
+            int ci = c0 + r, col = n0 + c4 * 4;
+            float* dst = &sm.Wt[stage][r][c4 * 4];
+            if (vecW) {
+                bool ok = (ci < Cin) && (col < Cout);
+                const float* g = ok ? Wk + (int64_t)ci * Cout + col : p.W;
+                cp_async16(dst, g, ok ? 16 : 0);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    bool ok = (ci < Cin) && (col + e < Cout);
+                    const float* g = ok ? Wk + (int64_t)ci * Cout + col + e : p.W;
+                    cp_async4(dst + e, g, ok ? 4 : 0);
+                }
+            }
+        }
+    };
+
+    float acc[TM][TN];
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+#pragma unroll
+    for (int s = 0; s < GG_STAGES - 1; ++s) {
+        if (s < nsteps) load_step(s, s);
+        cp_async_commit();
+    }
+
+    for (int step = 0; step < nsteps; ++step) {
+        cp_async_wait<GG_STAGES - 2>();
+        __syncthreads();
+        {
+            int nxt = step + GG_STAGES - 1;
+            if (nxt < nsteps) load_step(nxt, nxt % GG_STAGES);
+            cp_async_commit();
+        }
+        const int stage = step % GG_STAGES;
+#pragma unroll
+        for (int kk = 0; kk < GG_BK; kk += 4) {
+            float4 a[TM];
+#pragma unroll
+            for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(&sm.A[stage][ty + i * RT][kk]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float w[TN];
+#pragma unroll
+                for (int q = 0; q < TN / 4; ++q) {
+                    float4 w4 = *reinterpret_cast<const float4*>(&sm.Wt[stage][kk + r][tx * 4 + q * (CT * 4)]);
+                    w[q * 4 + 0] = w4.x;
+                    w[q * 4 + 1] = w4.y;
+                    w[q * 4 + 2] = w4.z;
+                    w[q * 4 + 3] = w4.w;
+                }
+#pragma unroll
+                for (int i = 0; i < TM; ++i) {
+                    float av = r == 0 ? a[i].x : r == 1 ? a[i].y : r == 2 ? a[i].z : a[i].w;
+#pragma unroll
+                    for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av, w[j], acc[i][j]);
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: thread owns rows ty + i*RT, column groups tx*4 + q*(CT*4)
+    const bool vecO = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        int orow = sm.orow[ty + i * RT];
+        if (orow < 0) continue;
+        float* o = p.out + (int64_t)orow * Cout;
+#pragma unroll
+        for (int q = 0; q < TN / 4; ++q) {
+            int col = n0 + tx * 4 + q * (CT * 4);
+            if (col >= Cout) continue;
+            if (vecO) {
+                float4 v = make_float4(acc[i][q * 4 + 0], acc[i][q * 4 + 1], acc[i][q * 4 + 2], acc[i][q * 4 + 3]);
+                if (p.accumulate) {
+                    float4 old = *reinterpret_cast<const float4*>(o + col);
+                    v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+                }
+                *reinterpret_cast<float4*>(o + col) = v;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (col + e < Cout) {
+                        float v = acc[i][q * 4 + e];
+                        if (p.accumulate) v += o[col + e];
+                        o[col + e] = v;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int BM, int BN, int TM, int TN>
+static int launch_gg(const GGParams& p, int64_t tiles_rows, int zdim, cudaStream_t st) {
+    constexpr int NT = (BM / TM) * (BN / TN);
+    size_t smem = sizeof(GGSmem<BM, BN, TM, TN>);
+    static bool attr_done = false;
+    if (!attr_done) {
+        B200SP_CUDA(cudaFuncSetAttribute(k_gather_gemm<BM, BN, TM, TN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)cdiv(tiles_rows, BM), (unsigned)cdiv(p.Cout, BN), (unsigned)zdim);
+    k_gather_gemm<BM, BN, TM, TN><<<grid, NT, smem, st>>>(p);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}
+
+static int dispatch_gg(const GGParams& p, int64_t tile_rows, int zdim, cudaStream_t st) {
+    // tile choice: wide row tiles when there are enough rows to fill 148 SMs, small tiles for the deep levels
+    const int64_t big_tiles = cdiv(tile_rows, 128) * cdiv(p.Cout, 64) * zdim;
+    if (p.Cout <= 16) {
+        if (tile_rows >= 128 * 148) return launch_gg<128, 16, 4, 4>(p, tile_rows, zdim, st);
+        return launch_gg<32, 16, 1, 4>(p, tile_rows, zdim, st);
+    }
+    if (p.Cout <= 32) {
+        if (tile_rows >= 128 * 148) return launch_gg<128, 32, 8, 4>(p, tile_rows, zdim, st);
+        return launch_gg<32, 32, 2, 4>(p, tile_rows, zdim, st);
+    }
+    if (big_tiles >= 148) return launch_gg<128, 64, 8, 4>(p, tile_rows, zdim, st);
+    return launch_gg<32, 32, 2, 4>(p, tile_rows, zdim, st);
+}
+
+// ---------------- wgrad over canonical pair lists ----------------
+struct WGParams {
+    const float* a;   // [*, Ca]
+    const float* b;   // [*, Cb]
+    const int* pa;    // [K][pstride] or NULL (identity)
+    const int* pb;
+    const int* pairnum;  // device [K] or NULL (identity: n_rows)
+    float* dW;        // [K][Ca][Cb]
+    int64_t pstride;
+    int64_t n_rows;
+    int Ca, Cb, K;
+    int ta, tb;       // tile extents (multiples of 4, <= 64)
+    int ppb;          // pairs per block
+};
+
+__global__ void __launch_bounds__(256) k_wgrad(WGParams p) {
+    __shared__ float s_red[256 * 16];
+    const int k = blockIdx.y;
+    const int64_t n = p.pairnum ? p.pairnum[k] : p.n_rows;
+    const int64_t p0 = (int64_t)blockIdx.x * p.ppb;
+    if (p0 >= n) return;
+    const int64_t p1 = min(n, p0 + p.ppb);
+    const int tilesB = (p.Cb + p.tb - 1) / p.tb;
+    const int a0 = (blockIdx.z / tilesB) * p.ta, b0 = (blockIdx.z % tilesB) * p.tb;
+    const int nB = p.tb / 4, RT = (p.ta / 4) * nB;
+    const int slices = 256 / RT;
+    const int tid = threadIdx.x;
+    const int slice = tid / RT, within = tid % RT;
+    const int ia = within / nB, ib = within % nB;
+    const int ca = a0 + ia * 4, cb = b0 + ib * 4;
+    const bool active = slice < slices;
+    const bool vecA = (p.Ca % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.a) & 15) == 0);
+    const bool vecB = (p.Cb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.b) & 15) == 0);
+    const int* pa = p.pa ? p.pa + (int64_t)k * p.pstride : nullptr;
+    const int* pb = p.pb ? p.pb + (int64_t)k * p.pstride : nullptr;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    auto ld4 = [](const float* base, int64_t row, int C, int c, bool vec) -> float4 {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* q = base + row * C + c;
+        if (vec) {
+            if (c < C) v = __ldg(reinterpret_cast<const float4*>(q));
+        } else {
+            if (c + 0 < C) v.x = __ldg(q + 0);
+            if (c + 1 < C) v.y = __ldg(q + 1);
+            if (c + 2 < C) v.z = __ldg(q + 2);
+            if (c + 3 < C) v.w = __ldg(q + 3);
+        }
+        return v;
+    };
+
+    if (active) {
+        constexpr int U = 4;
+        for (int64_t i = p0 + slice; i < p1; i += (int64_t)slices * U) {
+            float4 av[U], bv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                int64_t ii = i + (int64_t)u * slices;
+                if (ii < p1) {
+                    int64_t ra = pa ? pa[ii] : ii;
+                    int64_t rb = pb ? pb[ii] : ii;
+                    av[u] = ld4(p.a, ra, p.Ca, ca, vecA);
+                    bv[u] = ld4(p.b, rb, p.Cb, cb, vecB);
+                } else {
+                    av[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    bv[u] = av[u];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                float a4[4] = {av[u].x, av[u].y, av[u].z, av[u].w};
+                float b4[4] = {bv[u].x, bv[u].y, bv[u].z, bv[u].w};
+#pragma unroll
+                for (int x = 0; x < 4; ++x)
+#pragma unroll
+                    for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(a4[x], b4[y], acc[x][y]);
+            }
+        }
+    }
+    // cross-slice reduction through shared memory, then one atomic per element per block
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+        for (int y = 0; y < 4; ++y) s_red[(x * 4 + y) * 256 + tid] = active ? acc[x][y] : 0.f;
+    __syncthreads();
+    if (tid < RT) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x)
+#pragma unroll
+            for (int y = 0; y < 4; ++y) {
+                float s = 0.f;
+                for (int sl = 0; sl < slices; ++sl) s += s_red[(x * 4 + y) * 256 + sl * RT + tid];
+                if (ca + x < p.Ca && cb + y < p.Cb)
+                    atomicAdd(&p.dW[((int64_t)k * p.Ca + ca + x) * p.Cb + cb + y], s);
+            }
+    }
+}
+
+__global__ void k_weight_transpose(const float* __restrict__ W, int K, int Ci, int Co, int mirror,
+                                   float* __restrict__ out) {
+    // out[k'][co][ci] = W[k][ci][co], k' = mirror ? K-1-k : k
+    int64_t n = (int64_t)K * Ci * Co;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int ci = (int)(i % Ci);
+        int64_t t = i / Ci;
+        int co = (int)(t % Co);
+        int kp = (int)(t / Co);
+        int k = mirror ? K - 1 - kp : kp;
+        out[i] = W[((int64_t)k * Ci + ci) * Co + co];
+    }
+}
+
+}  // namespace b200sp
+
+using namespace b200sp;
+
+extern "C" int b200sp_gather_gemm(const float* in, int64_t n_in, int Cin, const float* W, const int32_t* tab, int K,
+                                  float* out, int64_t n_out, int Cout, int accumulate, void* stream) {
+    (void)n_in;
+    B200SP_CHECK_ARG(Cin >= 1 && Cout >= 1 && K >= 1, "gather_gemm: bad Cin/Cout/K");
+    B200SP_CHECK_ARG(K <= GG_MAXK, "gather_gemm: K=%d > %d not supported by this build", K, GG_MAXK);
+    B200SP_CHECK_ARG(tab || K == 1, "gather_gemm: tab==NULL requires K==1");
+    if (n_out == 0) return B200SP_OK;
+    GGParams p{};
+    p.in = in; p.W = W; p.tab = tab; p.out = out;
+    p.n_rows = n_out; p.Cin = Cin; p.Cout = Cout; p.K = K;
+    p.accumulate = accumulate; p.pairs_mode = 0;
+    return dispatch_gg(p, n_out, 1, (cudaStream_t)stream);
+}
+
+extern "C" int b200sp_gather_gemm_pairs(const float* in, int Cin, const float* W, const int32_t* pin,
+                                        const int32_t* pout, const int32_t* pairnum_dev, int64_t n_upper, int K,
+                                        int64_t pstride, float* out, int Cout, int accumulate, void* stream) {
+    B200SP_CHECK_ARG(Cin >= 1 && Cout >= 1 && K >= 1 && K <= GG_MAXK, "gather_gemm_pairs: bad Cin/Cout/K");
+    B200SP_CHECK_ARG(pin && pout && pairnum_dev, "gather_gemm_pairs: null pair lists");
+    if (n_upper <= 0) return B200SP_OK;
+    GGParams p{};
+    p.in = in; p.W = W; p.pin = pin; p.pout = pout; p.pairnum = pairnum_dev; p.out = out;
+    p.pstride = pstride; p.Cin = Cin; p.Cout = Cout; p.K = K;
+    p.accumulate = accumulate; p.pairs_mode = 1;
+    return dispatch_gg(p, n_upper, K, (cudaStream_t)stream);
+}
+
+extern "C" int b200sp_wgrad(const float* a, int Ca, const float* b, int Cb, const int32_t* pa, const int32_t* pb,
+                            const int32_t* pairnum_dev, int64_t n_upper, int K, int64_t pstride, float* dW,
+                            void* stream) {
+    B200SP_CHECK_ARG(Ca >= 1 && Cb >= 1 && K >= 1, "wgrad: bad Ca/Cb/K");
+    B200SP_CHECK_ARG(!(pa || pb) || pairnum_dev, "wgrad: pair lists need pairnum_dev");
+    const int64_t nmax = n_upper;
+    if (nmax <= 0) return B200SP_OK;
+    WGParams p{};
+    p.a = a; p.b = b; p.pa = pa; p.pb = pb; p.pairnum = (pa || pb) ? pairnum_dev : nullptr; p.dW = dW;
+    p.pstride = pstride; p.n_rows = n_upper; p.Ca = Ca; p.Cb = Cb; p.K = K;
+    auto tile = [](int C) { int t = (C + 3) / 4 * 4; return t > 64 ? 64 : t; };
+    p.ta = tile(Ca); p.tb = tile(Cb);
+    // enough blocks to fill the machine, few enough that the final atomics stay cheap
+    int tiles = (int)(cdiv(Ca, p.ta) * cdiv(Cb, p.tb));
+    int64_t ppb = 4096;
+    while (ppb > 256 && cdiv(nmax, ppb) * K * tiles < 2 * 148) ppb >>= 1;
+    p.ppb = (int)ppb;
+    dim3 grid((unsigned)cdiv(nmax, ppb), K, tiles);
+    k_wgrad<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}
+
+extern "C" int b200sp_weight_transpose(const float* W, int K, int Cin, int Cout, int mirror, float* out,
+                                       void* stream) {
+    B200SP_CHECK_ARG(K >= 1 && Cin >= 1 && Cout >= 1, "weight_transpose: bad sizes");
+    int64_t n = (int64_t)K * Cin * Cout;
+    k_weight_transpose<<<(unsigned)std::min<int64_t>(cdiv(n, 256), 2048), 256, 0, (cudaStream_t)stream>>>(W, K, Cin, Cout,
+                                                                                                   mirror, out);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}

@@ -1,0 +1,446 @@
+// elementwise.cu — HBM-bound row kernels: BatchNorm(+ReLU) on active sites, point<->voxel transfer,
+// row gather / scatter-add.  All are streaming kernels over [rows, C] fp32 with float4 accesses.
+//
+// Replaces nn.BatchNorm1d/DSNorm + nn.ReLU (model/unet.py:28,43; model/dsnorm.py:79-84),
+// voxelize_fp/bp (lib/pointgroup_ops/src/voxelize/voxelize.cu:10-52) and the devoxelize gather
+// (model/unet.py:62) of the reference.
+#include "common.cuh"
+
+namespace b200sp {
+
+constexpr int BN_THREADS = 256;
+constexpr int BN_MAXGRID = 592;  // 4 CTAs x 148 SMs
+
+// ---------------------------------------------------------------------------------------------
+// per-channel reduction of up to two quantities over rows.  Layout: thread (rl, cg) with cg the float4
+// column group; a block walks row chunks with a grid stride, then reduces over rl in shared memory and
+// writes one partial row per block: partial[block][q][C].
+// MODE 0: q0 = sum x, q1 = sum x^2                       (BN forward statistics)
+// MODE 1: q0 = sum g, q1 = sum g*xhat,  g = dy * relu'   (BN backward)
+// ---------------------------------------------------------------------------------------------
+template <int VEC, int MODE>
+__global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restrict__ x, const float* __restrict__ dy,
+                                                          int64_t M, int C, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift,
+                                                          const float* __restrict__ mean,
+                                                          const float* __restrict__ invstd, int relu,
+                                                          float* __restrict__ partial) {
+    extern __shared__ float s_part[];  // [2][rpb][C]
+    const int CG = C / VEC;
+    const int rpb = BN_THREADS / CG;
+    const int tid = threadIdx.x;
+    const int cg = tid % CG, rl = tid / CG;
+    const bool active = rl < rpb;
+    float a0[VEC], a1[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) a0[v] = a1[v] = 0.f;
+    float sc[VEC], sh[VEC], mu[VEC], is[VEC];
+    if (MODE == 1 && active) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            int c = cg * VEC + v;
+            sc[v] = scale[c];
+            sh[v] = shift[c];
+            mu[v] = mean[c];
+            is[v] = invstd[c];
+        }
+    }
+    if (active) {
+        for (int64_t r = (int64_t)blockIdx.x * rpb + rl; r < M; r += (int64_t)gridDim.x * rpb) {
+            float xv[VEC], gv[VEC];
+            if (VEC == 4) {
+                float4 t = __ldg(reinterpret_cast<const float4*>(x + r * C) + cg);
+                xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+                if (MODE == 1) {
+                    float4 g = __ldg(reinterpret_cast<const float4*>(dy + r * C) + cg);
+                    gv[0] = g.x; gv[1] = g.y; gv[2] = g.z; gv[3] = g.w;
+                }
+            } else {
+                xv[0] = __ldg(x + r * C + cg);
+                if (MODE == 1) gv[0] = __ldg(dy + r * C + cg);
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                if (MODE == 0) {
+                    a0[v] += xv[v];
+                    a1[v] = fmaf(xv[v], xv[v], a1[v]);
+                } else {
+                    float g = gv[v];
+                    if (relu && fmaf(xv[v], sc[v], sh[v]) <= 0.f) g = 0.f;
+                    a0[v] += g;
+                    a1[v] = fmaf(g, (xv[v] - mu[v]) * is[v], a1[v]);
+                }
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            s_part[rl * C + cg * VEC + v] = a0[v];
+            s_part[(rpb + rl) * C + cg * VEC + v] = a1[v];
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * C; i += BN_THREADS) {
+        int q = i / C, c = i % C;
+        float s = 0.f;
+        for (int r = 0; r < rpb; ++r) s += s_part[(q * rpb + r) * C + c];
+        partial[((int64_t)blockIdx.x * 2 + q) * C + c] = s;
+    }
+}
+
+// forward finalize: mean / invstd / unbiased var, and the fused scale/shift used by the apply pass
+__global__ void k_bn_finalize_fwd(const float* __restrict__ partial, int G, int64_t M, int C,
+                                  const float* __restrict__ w, const float* __restrict__ b, float eps,
+                                  float* __restrict__ mean, float* __restrict__ invstd,
+                                  float* __restrict__ running_mean, float* __restrict__ running_var,
+                                  float momentum, long long* __restrict__ num_batches_tracked,
+                                  float* __restrict__ scale, float* __restrict__ shift) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    if (c >= C) return;
+    double s = 0.0, ss = 0.0;
+    for (int g = 0; g < G; ++g) {
+        s += partial[((int64_t)g * 2 + 0) * C + c];
+        ss += partial[((int64_t)g * 2 + 1) * C + c];
+    }
+    double mu = s / (double)M;
+    double var = ss / (double)M - mu * mu;
+    if (var < 0.0) var = 0.0;
+    float is = (float)(1.0 / sqrt(var + (double)eps));
+    mean[c] = (float)mu;
+    invstd[c] = is;
+    // running statistics exactly as F.batch_norm: unbiased variance, exponential average
+    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+    if (running_var) {
+        float vu = (float)(M > 1 ? var * (double)M / (double)(M - 1) : var);
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * vu;
+    }
+    float wv = w ? w[c] : 1.f, bv = b ? b[c] : 0.f;
+    float sc = wv * is;
+    scale[c] = sc;
+    shift[c] = bv - (float)mu * sc;
+}
+
+__global__ void k_bn_scale_shift(const float* __restrict__ w, const float* __restrict__ b,
+                                 const float* __restrict__ mean, const float* __restrict__ invstd, int C,
+                                 float* __restrict__ scale, float* __restrict__ shift) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float wv = w ? w[c] : 1.f, bv = b ? b[c] : 0.f;
+    float sc = wv * invstd[c];
+    scale[c] = sc;
+    shift[c] = bv - mean[c] * sc;
+}
+
+// y = [relu](x*scale + shift)
+template <int VEC>
+__global__ void __launch_bounds__(256) k_affine_relu(const float* __restrict__ x, int64_t M, int C,
+                                                     const float* __restrict__ scale,
+                                                     const float* __restrict__ shift, int relu,
+                                                     float* __restrict__ y) {
+    const int CG = C / VEC;
+    const int64_t n = M * CG;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int cg = (int)(i % CG);
+        if (VEC == 4) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(x) + i);
+            float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + cg);
+            float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + cg);
+            float4 o;
+            o.x = fmaf(t.x, sc.x, sh.x); o.y = fmaf(t.y, sc.y, sh.y);
+            o.z = fmaf(t.z, sc.z, sh.z); o.w = fmaf(t.w, sc.w, sh.w);
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            reinterpret_cast<float4*>(y)[i] = o;
+        } else {
+            float o = fmaf(__ldg(x + i), scale[cg], shift[cg]);
+            y[i] = relu ? fmaxf(o, 0.f) : o;
+        }
+    }
+}
+
+// backward finalize: dw = sum g*xhat, db = sum g; coefficient rows for the apply pass
+__global__ void k_bn_finalize_bwd(const float* __restrict__ partial, int G, int64_t M, int C,
+                                  const float* __restrict__ w, const float* __restrict__ invstd,
+                                  float* __restrict__ dw, float* __restrict__ db, float* __restrict__ c_g,
+                                  float* __restrict__ c_mean_g, float* __restrict__ c_mean_gx) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double sg = 0.0, sgx = 0.0;
+    for (int g = 0; g < G; ++g) {
+        sg += partial[((int64_t)g * 2 + 0) * C + c];
+        sgx += partial[((int64_t)g * 2 + 1) * C + c];
+    }
+    if (dw) dw[c] = (float)sgx;
+    if (db) db[c] = (float)sg;
+    float wv = w ? w[c] : 1.f;
+    c_g[c] = wv * invstd[c];
+    c_mean_g[c] = (float)(sg / (double)M);
+    c_mean_gx[c] = (float)(sgx / (double)M);
+}
+
+// dx = w*invstd * (g - mean(g) - xhat*mean(g*xhat))
+template <int VEC>
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
+                                                      int64_t M, int C, const float* __restrict__ scale,
+                                                      const float* __restrict__ shift,
+                                                      const float* __restrict__ mean,
+                                                      const float* __restrict__ invstd,
+                                                      const float* __restrict__ c_g,
+                                                      const float* __restrict__ c_mean_g,
+                                                      const float* __restrict__ c_mean_gx, int relu,
+                                                      float* __restrict__ dx) {
+    const int CG = C / VEC;
+    const int64_t n = M * CG;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int cg = (int)(i % CG);
+        float xv[VEC], gv[VEC], o[VEC];
+        if (VEC == 4) {
+            float4 t = __ldg(reinterpret_cast<const float4*>(x) + i);
+            float4 g = __ldg(reinterpret_cast<const float4*>(dy) + i);
+            xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
+            gv[0] = g.x; gv[1] = g.y; gv[2] = g.z; gv[3] = g.w;
+        } else {
+            xv[0] = __ldg(x + i);
+            gv[0] = __ldg(dy + i);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            int c = cg * VEC + v;
+            float g = gv[v];
+            if (relu && fmaf(xv[v], scale[c], shift[c]) <= 0.f) g = 0.f;
+            float xhat = (xv[v] - mean[c]) * invstd[c];
+            o[v] = c_g[c] * (g - c_mean_g[c] - xhat * c_mean_gx[c]);
+        }
+        if (VEC == 4) reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
+        else dx[i] = o[0];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// point <-> voxel
+// ---------------------------------------------------------------------------------------------
+__global__ void k_voxelize_fp(const float* __restrict__ feats, float* __restrict__ out, const int* __restrict__ map,
+                              int average, int64_t M, int A, int C) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * C) return;
+    int64_t v = i / C;
+    int c = (int)(i - v * C);
+    const int* r = map + v * (A + 1);
+    int cnt = r[0];
+    float s = 0.f;
+    for (int j = 1; j <= cnt; ++j) s += __ldg(feats + (int64_t)r[j] * C + c);
+    float mult = (average && cnt > 0) ? 1.f / (float)cnt : 1.f;
+    out[i] += mult * s;
+}
+
+__global__ void k_voxelize_bp(const float* __restrict__ dout, float* __restrict__ dfeats,
+                              const int* __restrict__ map, int average, int64_t M, int A, int C) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * C) return;
+    int64_t v = i / C;
+    int c = (int)(i - v * C);
+    const int* r = map + v * (A + 1);
+    int cnt = r[0];
+    float mult = (average && cnt > 0) ? 1.f / (float)cnt : 1.f;
+    float g = mult * dout[i];
+    for (int j = 1; j <= cnt; ++j) atomicAdd(dfeats + (int64_t)r[j] * C + c, g);
+}
+
+template <typename IdxT, int VEC>
+__global__ void __launch_bounds__(256) k_gather_rows(const float* __restrict__ src, const IdxT* __restrict__ idx,
+                                                     int64_t n, int C, float* __restrict__ out) {
+    const int CG = C / VEC;
+    const int64_t total = n * CG;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / CG;
+        int cg = (int)(i - r * CG);
+        int64_t s = (int64_t)idx[r];
+        if (VEC == 4)
+            reinterpret_cast<float4*>(out)[i] = __ldg(reinterpret_cast<const float4*>(src + s * C) + cg);
+        else
+            out[i] = __ldg(src + s * C + cg);
+    }
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+template <typename IdxT, int VEC>
+__global__ void __launch_bounds__(256) k_scatter_add_rows(const float* __restrict__ src,
+                                                          const IdxT* __restrict__ idx, int64_t n, int C,
+                                                          float* __restrict__ dst) {
+    const int CG = C / VEC;
+    const int64_t total = n * CG;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / CG;
+        int cg = (int)(i - r * CG);
+        int64_t d = (int64_t)idx[r];
+        if (VEC == 4) red_add_v4(dst + d * C + cg * 4, __ldg(reinterpret_cast<const float4*>(src) + i));
+        else atomicAdd(dst + d * C + cg, __ldg(src + i));
+    }
+}
+
+static inline unsigned stream_grid(int64_t n_items, int threads) {
+    int64_t g = cdiv(n_items, threads);
+    int64_t cap = (int64_t)148 * 16;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+static inline bool vec4_ok(int C, const void* a, const void* b = nullptr, const void* c = nullptr) {
+    auto al = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return C % 4 == 0 && al(a) && al(b) && al(c);
+}
+
+}  // namespace b200sp
+
+using namespace b200sp;
+
+extern "C" int64_t b200sp_bn_ws_bytes(int64_t M, int C) {
+    (void)M;
+    return (int64_t)sizeof(float) * ((int64_t)BN_MAXGRID * 2 * C + 8 * (int64_t)C) + 1024;
+}
+
+static int bn_grid(int64_t M, int C, int VEC) {
+    int CG = C / VEC;
+    int rpb = BN_THREADS / CG;
+    int64_t g = cdiv(M, (int64_t)rpb * 4);
+    if (g < 1) g = 1;
+    if (g > BN_MAXGRID) g = BN_MAXGRID;
+    return (int)g;
+}
+
+extern "C" int b200sp_bn_fwd_train(const float* x, int64_t M, int C, const float* w, const float* b, float eps,
+                                   int relu, float* y, float* mean, float* invstd, float* running_mean,
+                                   float* running_var, float momentum, int64_t* num_batches_tracked, void* ws,
+                                   int64_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B200SP_CHECK_ARG(M >= 1 && C >= 1, "bn_fwd_train: need M>=1, C>=1");
+    B200SP_CHECK_ARG(ws_bytes >= b200sp_bn_ws_bytes(M, C), "bn_fwd_train: workspace too small");
+    const bool v4 = vec4_ok(C, x, y) && C / 4 <= BN_THREADS;
+    B200SP_CHECK_ARG(v4 || C <= BN_THREADS, "bn_fwd_train: C=%d unsupported", C);
+    float* partial = (float*)ws;
+    float* scale = partial + (int64_t)BN_MAXGRID * 2 * C;
+    float* shift = scale + C;
+    int VEC = v4 ? 4 : 1;
+    int G = bn_grid(M, C, VEC);
+    int rpb = BN_THREADS / (C / VEC);
+    size_t smem = sizeof(float) * 2 * rpb * C;
+    if (v4)
+        k_bn_reduce<4, 0><<<G, BN_THREADS, smem, st>>>(x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, partial);
+    else
+        k_bn_reduce<1, 0><<<G, BN_THREADS, smem, st>>>(x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, partial);
+    k_bn_finalize_fwd<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(partial, G, M, C, w, b, eps, mean, invstd, running_mean,
+                                                             running_var, momentum,
+                                                             (long long*)num_batches_tracked, scale, shift);
+    if (v4)
+        k_affine_relu<4><<<stream_grid(M * (C / 4), 256), 256, 0, st>>>(x, M, C, scale, shift, relu, y);
+    else
+        k_affine_relu<1><<<stream_grid(M * C, 256), 256, 0, st>>>(x, M, C, scale, shift, relu, y);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}
+
+extern "C" int b200sp_affine_relu(const float* x, int64_t M, int C, const float* scale, const float* shift, int relu,
+                                  float* y, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B200SP_CHECK_ARG(M >= 0 && C >= 1, "affine_relu: bad sizes");
+    if (M == 0) return B200SP_OK;
+    if (vec4_ok(C, x, y, scale) && vec4_ok(C, shift))
+        k_affine_relu<4><<<stream_grid(M * (C / 4), 256), 256, 0, st>>>(x, M, C, scale, shift, relu, y);
+    else
+        k_affine_relu<1><<<stream_grid(M * C, 256), 256, 0, st>>>(x, M, C, scale, shift, relu, y);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}
+
+extern "C" int b200sp_bn_bwd(const float* x, const float* dy, int64_t M, int C, const float* w, const float* b,
+                             const float* mean, const float* invstd, int relu, float* dx, float* dw, float* db,
+                             void* ws, int64_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B200SP_CHECK_ARG(M >= 1 && C >= 1, "bn_bwd: need M>=1, C>=1");
+    B200SP_CHECK_ARG(ws_bytes >= b200sp_bn_ws_bytes(M, C), "bn_bwd: workspace too small");
+    const bool v4 = vec4_ok(C, x, dy, dx) && C / 4 <= BN_THREADS;
+    B200SP_CHECK_ARG(v4 || C <= BN_THREADS, "bn_bwd: C=%d unsupported", C);
+    float* partial = (float*)ws;
+    float* scale = partial + (int64_t)BN_MAXGRID * 2 * C;
+    float* shift = scale + C;
+    float* c_g = shift + C;
+    float* c_mg = c_g + C;
+    float* c_mgx = c_mg + C;
+    int VEC = v4 ? 4 : 1;
+    int G = bn_grid(M, C, VEC);
+    int rpb = BN_THREADS / (C / VEC);
+    size_t smem = sizeof(float) * 2 * rpb * C;
+    k_bn_scale_shift<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(w, b, mean, invstd, C, scale, shift);
+    if (v4)
+        k_bn_reduce<4, 1><<<G, BN_THREADS, smem, st>>>(x, dy, M, C, scale, shift, mean, invstd, relu, partial);
+    else
+        k_bn_reduce<1, 1><<<G, BN_THREADS, smem, st>>>(x, dy, M, C, scale, shift, mean, invstd, relu, partial);
+    k_bn_finalize_bwd<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(partial, G, M, C, w, invstd, dw, db, c_g, c_mg, c_mgx);
+    if (v4)
+        k_bn_bwd_apply<4><<<stream_grid(M * (C / 4), 256), 256, 0, st>>>(x, dy, M, C, scale, shift, mean, invstd, c_g,
+                                                                        c_mg, c_mgx, relu, dx);
+    else
+        k_bn_bwd_apply<1><<<stream_grid(M * C, 256), 256, 0, st>>>(x, dy, M, C, scale, shift, mean, invstd, c_g, c_mg,
+                                                                  c_mgx, relu, dx);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}
+
+extern "C" int b200sp_voxelize_fp(const float* feats, float* out, const int32_t* map, int average, int64_t M, int A,
+                                  int C, void* stream) {
+    B200SP_CHECK_ARG(M >= 0 && A >= 0 && C >= 1, "voxelize_fp: bad sizes");
+    if (M == 0) return B200SP_OK;
+    k_voxelize_fp<<<(unsigned)cdiv(M * C, 256), 256, 0, (cudaStream_t)stream>>>(feats, out, map, average, M, A, C);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}
+
+extern "C" int b200sp_voxelize_bp(const float* dout, float* dfeats, const int32_t* map, int average, int64_t M,
+                                  int A, int C, void* stream) {
+    B200SP_CHECK_ARG(M >= 0 && A >= 0 && C >= 1, "voxelize_bp: bad sizes");
+    if (M == 0) return B200SP_OK;
+    k_voxelize_bp<<<(unsigned)cdiv(M * C, 256), 256, 0, (cudaStream_t)stream>>>(dout, dfeats, map, average, M, A, C);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}
+
+extern "C" int b200sp_gather_rows(const float* src, const void* idx, int idx_is_i64, int64_t n, int C, float* out,
+                                  void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B200SP_CHECK_ARG(n >= 0 && C >= 1, "gather_rows: bad sizes");
+    if (n == 0) return B200SP_OK;
+    bool v4 = vec4_ok(C, src, out);
+    unsigned grid = stream_grid(n * (v4 ? C / 4 : C), 256);
+    if (idx_is_i64) {
+        if (v4) k_gather_rows<int64_t, 4><<<grid, 256, 0, st>>>(src, (const int64_t*)idx, n, C, out);
+        else k_gather_rows<int64_t, 1><<<grid, 256, 0, st>>>(src, (const int64_t*)idx, n, C, out);
+    } else {
+        if (v4) k_gather_rows<int32_t, 4><<<grid, 256, 0, st>>>(src, (const int32_t*)idx, n, C, out);
+        else k_gather_rows<int32_t, 1><<<grid, 256, 0, st>>>(src, (const int32_t*)idx, n, C, out);
+    }
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}
+
+extern "C" int b200sp_scatter_add_rows(const float* src, const void* idx, int idx_is_i64, int64_t n, int C,
+                                       float* dst, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B200SP_CHECK_ARG(n >= 0 && C >= 1, "scatter_add_rows: bad sizes");
+    if (n == 0) return B200SP_OK;
+    bool v4 = vec4_ok(C, src, dst);
+    unsigned grid = stream_grid(n * (v4 ? C / 4 : C), 256);
+    if (idx_is_i64) {
+        if (v4) k_scatter_add_rows<int64_t, 4><<<grid, 256, 0, st>>>(src, (const int64_t*)idx, n, C, dst);
+        else k_scatter_add_rows<int64_t, 1><<<grid, 256, 0, st>>>(src, (const int64_t*)idx, n, C, dst);
+    } else {
+        if (v4) k_scatter_add_rows<int32_t, 4><<<grid, 256, 0, st>>>(src, (const int32_t*)idx, n, C, dst);
+        else k_scatter_add_rows<int32_t, 1><<<grid, 256, 0, st>>>(src, (const int32_t*)idx, n, C, dst);
+    }
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}

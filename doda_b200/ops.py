@@ -1,0 +1,459 @@
+"""Torch-level wrappers over the C ABI: device memory and streams come from torch, the work is done by
+libb200sparse.so.  Mirrors spconv v1.2 `spconv.ops` (get_indice_pairs / indice_conv / indice_conv_backward)
+and the autograd functions of `spconv.functional`.
+
+No CPU path: every function requires CUDA tensors and raises otherwise.
+"""
+import torch
+from torch.autograd import Function
+
+from ._lib import lib, check
+
+_I32 = torch.int32
+_F32 = torch.float32
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _req_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("doda_b200 ops need CUDA tensors (got a %s tensor): the sm_100a engine has no CPU "
+                               "fallback" % t.device.type)
+
+
+def _f32c(t):
+    if t.dtype != _F32:
+        raise TypeError("expected float32 features, got %s" % t.dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+_ws = {}
+
+
+def _workspace(nbytes, device, tag):
+    """Grow-only scratch buffer per (device, tag); safe because all launches are ordered on one stream."""
+    key = (device.index, tag, torch.cuda.current_stream().cuda_stream)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def _triple(v):
+    if isinstance(v, (list, tuple)):
+        assert len(v) == 3
+        return [int(x) for x in v]
+    return [int(v)] * 3
+
+
+def _carr(vals):
+    import ctypes
+    return (ctypes.c_int32 * len(vals))(*[int(v) for v in vals])
+
+
+# ------------------------------------------------------------------------------------------------
+# rulebook
+# ------------------------------------------------------------------------------------------------
+class Rulebook(object):
+    """What `indice_dict[key]` holds.  Iterates like the spconv v1.2 tuple
+    (outids, indices, indice_pairs, indice_pair_num, spatial_shape) and carries the engine's tables."""
+
+    __slots__ = ("kind", "outids", "indices", "pairs", "pairnum", "spatial_shape", "out_spatial_shape", "K",
+                 "ksize", "stride", "padding", "dilation", "nbr", "fwd", "bwd", "nonoverlap", "batch_size")
+
+    def __iter__(self):
+        return iter((self.outids, self.indices, self.pairs, self.pairnum, self.spatial_shape))
+
+    def __getitem__(self, i):
+        return tuple(self)[i]
+
+    def __len__(self):
+        return 5
+
+
+def conv_out_shape(shape, ksize, stride, padding, dilation):
+    return [(s + 2 * p - d * (k - 1) - 1) // st + 1 for s, k, st, p, d in zip(shape, ksize, stride, padding, dilation)]
+
+
+def build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding=0, dilation=1, subm=False,
+                   need_pairs=True):
+    """indices int32 [M,4] (batch, i0, i1, i2) on CUDA -> Rulebook."""
+    _req_cuda(indices)
+    if indices.dtype != _I32:
+        raise TypeError("indices must be int32 (spconv contract: voxel_coords.int(), model/unet.py:94)")
+    indices = indices.contiguous()
+    M = indices.shape[0]
+    dev = indices.device
+    ks, st, pd, dl = _triple(ksize), _triple(stride), _triple(padding), _triple(dilation)
+    shape = [int(s) for s in spatial_shape]
+    K = ks[0] * ks[1] * ks[2]
+    rb = Rulebook()
+    rb.K, rb.ksize, rb.stride, rb.padding, rb.dilation = K, ks, st, pd, dl
+    rb.indices, rb.spatial_shape, rb.batch_size = indices, shape, int(batch_size)
+    rb.nbr = rb.fwd = rb.bwd = None
+    rb.pairs = torch.empty((2, K, M), dtype=_I32, device=dev) if need_pairs else None
+    rb.pairnum = torch.empty((K,), dtype=_I32, device=dev) if need_pairs else None
+    pp = rb.pairs.data_ptr() if need_pairs else None
+    pn = rb.pairnum.data_ptr() if need_pairs else None
+    if subm:
+        rb.kind = "subm"
+        rb.out_spatial_shape = shape
+        rb.outids = indices
+        rb.nonoverlap = False
+        rb.nbr = torch.empty((M, K), dtype=_I32, device=dev)
+        wsb = lib.b200sp_rulebook_ws_bytes(M, K, 1)
+        ws = _workspace(wsb, dev, "rb")
+        check(lib.b200sp_rulebook_subm(indices.data_ptr(), M, int(batch_size), _carr(shape), _carr(ks), _carr(dl),
+                                       rb.nbr.data_ptr(), pp, pn, ws.data_ptr(), ws.numel(), _stream()),
+              "rulebook_subm")
+        return rb
+    rb.kind = "conv"
+    oshape = conv_out_shape(shape, ks, st, pd, dl)
+    if min(oshape) <= 0:
+        raise ValueError("sparse conv output shape %s is empty for input shape %s" % (oshape, shape))
+    rb.out_spatial_shape = oshape
+    # candidates (valid offsets) per input site: ceil(k/s) per axis when dilation is 1
+    cand = 1
+    for k, s, d in zip(ks, st, dl):
+        cand *= (-(-k // s)) if d == 1 else k
+    rb.nonoverlap = cand == 1
+    ub = max(M * cand, 1)
+    out_coords = torch.empty((ub, 4), dtype=_I32, device=dev)
+    rb.fwd = torch.empty((M, K), dtype=_I32, device=dev)
+    bwd = torch.empty((ub, K), dtype=_I32, device=dev)
+    wsb = lib.b200sp_rulebook_ws_bytes(M, K, cand)
+    ws = _workspace(wsb, dev, "rb")
+    import ctypes
+    n_out = ctypes.c_int64(0)
+    check(lib.b200sp_rulebook_conv(indices.data_ptr(), M, int(batch_size), _carr(shape), _carr(oshape), _carr(ks),
+                                   _carr(st), _carr(pd), _carr(dl), cand, out_coords.data_ptr(), rb.fwd.data_ptr(),
+                                   bwd.data_ptr(), pp, pn, ctypes.byref(n_out), ws.data_ptr(), ws.numel(),
+                                   _stream()), "rulebook_conv")
+    n = int(n_out.value)
+    rb.outids = out_coords[:n]
+    rb.bwd = bwd[:n]
+    return rb
+
+
+def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1, out_padding=0,
+                     subm=False, transpose=False, grid=None, use_hash=False):
+    """spconv v1.2 `ops.get_indice_pairs` -> (outids, indice_pairs[2,K,M], indice_pair_num[K]); pairs are in the
+    canonical order of SURVEY.md A.4 (ascending input row inside each offset, outputs in ascending flat index)."""
+    if transpose:
+        raise NotImplementedError("transposed sparse conv is not used by DODA (model/unet_block.py) and not built")
+    rb = build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, subm=subm)
+    return rb.outids, rb.pairs, rb.pairnum
+
+
+def pairs_to_table(pairs, pairnum, n_out, inverse=False):
+    K, M = pairs.shape[1], pairs.shape[2]
+    tab = torch.empty((n_out, K), dtype=_I32, device=pairs.device)
+    check(lib.b200sp_pairs_to_table(pairs.data_ptr(), pairnum.data_ptr(), K, M, 1 if inverse else 0, tab.data_ptr(),
+                                    n_out, _stream()), "pairs_to_table")
+    return tab
+
+
+# ------------------------------------------------------------------------------------------------
+# conv primitives
+# ------------------------------------------------------------------------------------------------
+def gather_gemm(feat, W3, tab, n_out, out=None, accumulate=False):
+    """out[r] = sum_k feat[tab[r,k]] @ W3[k];  W3 [K,Cin,Cout] contiguous; tab None -> dense GEMM (K==1)."""
+    K, Cin, Cout = W3.shape
+    if out is None:
+        out = torch.empty((n_out, Cout), dtype=_F32, device=feat.device)
+    check(lib.b200sp_gather_gemm(feat.data_ptr(), feat.shape[0], Cin, W3.data_ptr(),
+                                 tab.data_ptr() if tab is not None else None, K, out.data_ptr(), n_out, Cout,
+                                 1 if accumulate else 0, _stream()), "gather_gemm")
+    return out
+
+
+def gather_gemm_pairs(feat, W3, pin, pout, pairnum, n_upper, n_out):
+    """out[pout[k][i]] = feat[pin[k][i]] @ W3[k]; rows not covered stay zero."""
+    K, Cin, Cout = W3.shape
+    out = torch.zeros((n_out, Cout), dtype=_F32, device=feat.device)
+    check(lib.b200sp_gather_gemm_pairs(feat.data_ptr(), Cin, W3.data_ptr(), pin.data_ptr(), pout.data_ptr(),
+                                       pairnum.data_ptr(), n_upper, K, pin.stride(0), out.data_ptr(), Cout, 0,
+                                       _stream()), "gather_gemm_pairs")
+    return out
+
+
+def wgrad(a, b, pa, pb, pairnum, n_upper, K):
+    """dW[k] = sum_i a[pa[k][i]]^T b[pb[k][i]]  -> [K, Ca, Cb]"""
+    Ca, Cb = a.shape[1], b.shape[1]
+    dW = torch.zeros((K, Ca, Cb), dtype=_F32, device=a.device)
+    check(lib.b200sp_wgrad(a.data_ptr(), Ca, b.data_ptr(), Cb, pa.data_ptr() if pa is not None else None,
+                           pb.data_ptr() if pb is not None else None,
+                           pairnum.data_ptr() if pairnum is not None else None, n_upper, K,
+                           pa.stride(0) if pa is not None else 0, dW.data_ptr(), _stream()), "wgrad")
+    return dW
+
+
+def weight_transpose(W3, mirror):
+    K, Cin, Cout = W3.shape
+    out = torch.empty((K, Cout, Cin), dtype=_F32, device=W3.device)
+    check(lib.b200sp_weight_transpose(W3.data_ptr(), K, Cin, Cout, 1 if mirror else 0, out.data_ptr(), _stream()),
+          "weight_transpose")
+    return out
+
+
+def _w3(filters):
+    """[k,k,k,Cin,Cout] (or any leading kernel dims) -> contiguous [K,Cin,Cout] view"""
+    Cin, Cout = filters.shape[-2], filters.shape[-1]
+    f = filters if filters.is_contiguous() else filters.contiguous()
+    return f.view(-1, Cin, Cout)
+
+
+class SubMConvFunction(Function):
+    """spconv.functional.indice_subm_conv: out[q] = sum_k W[k] . in[q + k - centre] on the input's own sites."""
+
+    @staticmethod
+    def forward(ctx, features, filters, rb):
+        _req_cuda(features, filters)
+        features = _f32c(features)
+        W3 = _w3(filters)
+        ctx.rb = rb
+        ctx.save_for_backward(features, filters)
+        return gather_gemm(features, W3, rb.nbr, features.shape[0])
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        features, filters = ctx.saved_tensors
+        rb = ctx.rb
+        grad_out = _f32c(grad_out)  # the llijiang fork's `.contiguous()` (docs/INSTALL.md:25)
+        W3 = _w3(filters)
+        M = features.shape[0]
+        din = dW = None
+        if ctx.needs_input_grad[0]:
+            din = gather_gemm(grad_out, weight_transpose(W3, True), rb.nbr, M)
+        if ctx.needs_input_grad[1]:
+            dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K).view(filters.shape)
+        return din, dW, None
+
+
+class DenseConvFunction(Function):
+    """kernel_size == 1: features @ W.view(Cin, Cout) (spconv SparseConvolution.forward)."""
+
+    @staticmethod
+    def forward(ctx, features, filters):
+        _req_cuda(features, filters)
+        features = _f32c(features)
+        ctx.save_for_backward(features, filters)
+        return gather_gemm(features, _w3(filters), None, features.shape[0])
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        features, filters = ctx.saved_tensors
+        grad_out = _f32c(grad_out)
+        W3 = _w3(filters)
+        M = features.shape[0]
+        din = dW = None
+        if ctx.needs_input_grad[0]:
+            din = gather_gemm(grad_out, weight_transpose(W3, False), None, M)
+        if ctx.needs_input_grad[1]:
+            dW = wgrad(features, grad_out, None, None, None, M, 1).view(filters.shape)
+        return din, dW
+
+
+class SparseConvFunction(Function):
+    """spconv.functional.indice_conv (regular / strided sparse conv)."""
+
+    @staticmethod
+    def forward(ctx, features, filters, rb):
+        _req_cuda(features, filters)
+        features = _f32c(features)
+        ctx.rb = rb
+        ctx.save_for_backward(features, filters)
+        return gather_gemm(features, _w3(filters), rb.bwd, rb.outids.shape[0])
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        features, filters = ctx.saved_tensors
+        rb = ctx.rb
+        grad_out = _f32c(grad_out)
+        W3 = _w3(filters)
+        M_in = features.shape[0]
+        din = dW = None
+        if ctx.needs_input_grad[0]:
+            Wt = weight_transpose(W3, False)
+            if rb.nonoverlap:  # every input has at most one (output, offset): pair-grouped, no accumulation
+                din = gather_gemm_pairs(grad_out, Wt, rb.pairs[1], rb.pairs[0], rb.pairnum, M_in, M_in)
+            else:
+                din = gather_gemm(grad_out, Wt, rb.fwd, M_in)
+        if ctx.needs_input_grad[1]:
+            dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M_in, rb.K).view(filters.shape)
+        return din, dW, None
+
+
+class SparseInverseConvFunction(Function):
+    """spconv.functional.indice_inverse_conv: reuses the strided conv's rulebook with roles swapped."""
+
+    @staticmethod
+    def forward(ctx, features, filters, rb):
+        _req_cuda(features, filters)
+        features = _f32c(features)
+        ctx.rb = rb
+        ctx.save_for_backward(features, filters)
+        W3 = _w3(filters)
+        n_fine = rb.indices.shape[0]
+        if rb.nonoverlap:
+            return gather_gemm_pairs(features, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, n_fine)
+        return gather_gemm(features, W3, rb.fwd, n_fine)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        features, filters = ctx.saved_tensors
+        rb = ctx.rb
+        grad_out = _f32c(grad_out)
+        W3 = _w3(filters)
+        n_fine = rb.indices.shape[0]
+        din = dW = None
+        if ctx.needs_input_grad[0]:
+            din = gather_gemm(grad_out, weight_transpose(W3, False), rb.bwd, features.shape[0])
+        if ctx.needs_input_grad[1]:
+            dW = wgrad(features, grad_out, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, rb.K).view(filters.shape)
+        return din, dW, None
+
+
+def indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_out, inverse=False, subm=False):
+    """spconv v1.2 `ops.indice_conv` on a raw spconv-layout rulebook (any pair order)."""
+    _req_cuda(features, filters, indice_pairs)
+    features = _f32c(features)
+    tab = pairs_to_table(indice_pairs.contiguous(), indice_pair_num.contiguous(), int(num_activate_out), inverse)
+    return gather_gemm(features, _w3(filters), tab, int(num_activate_out))
+
+
+def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_num, inverse=False, subm=False):
+    """spconv v1.2 `ops.indice_conv_backward` -> (input_bp, filters_bp)."""
+    _req_cuda(features, filters, out_bp, indice_pairs)
+    features, out_bp = _f32c(features), _f32c(out_bp)
+    pairs, pairnum = indice_pairs.contiguous(), indice_pair_num.contiguous()
+    W3 = _w3(filters)
+    K = W3.shape[0]
+    n_in = features.shape[0]
+    tab = pairs_to_table(pairs, pairnum, n_in, not inverse)  # in-row -> out-row per offset
+    din = gather_gemm(out_bp, weight_transpose(W3, False), tab, n_in)
+    a_idx, b_idx = (pairs[1], pairs[0]) if inverse else (pairs[0], pairs[1])
+    dW = wgrad(features, out_bp, a_idx, b_idx, pairnum, pairs.shape[2], K).view(filters.shape)
+    return din, dW
+
+
+# ------------------------------------------------------------------------------------------------
+# BatchNorm(+ReLU) on active sites
+# ------------------------------------------------------------------------------------------------
+class BNReLUFunction(Function):
+    """Training-mode batch norm over the rows of [N_active, C] with optional fused ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, running_mean, running_var, nbt, momentum, eps, relu):
+        _req_cuda(x)
+        x = _f32c(x)
+        M, C = x.shape
+        dev = x.device
+        y = torch.empty_like(x)
+        stats = torch.empty((2, C), dtype=_F32, device=dev)
+        ws = _workspace(lib.b200sp_bn_ws_bytes(M, C), dev, "bn")
+        check(lib.b200sp_bn_fwd_train(x.data_ptr(), M, C, weight.data_ptr() if weight is not None else None,
+                                      bias.data_ptr() if bias is not None else None, float(eps), 1 if relu else 0,
+                                      y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+                                      running_mean.data_ptr() if running_mean is not None else None,
+                                      running_var.data_ptr() if running_var is not None else None, float(momentum),
+                                      nbt.data_ptr() if nbt is not None else None, ws.data_ptr(), ws.numel(),
+                                      _stream()), "bn_fwd_train")
+        ctx.save_for_backward(x, weight, bias, stats)
+        ctx.relu = relu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, stats = ctx.saved_tensors
+        dy = _f32c(dy)
+        M, C = x.shape
+        dev = x.device
+        dx = torch.empty_like(x)
+        dwb = torch.empty((2, C), dtype=_F32, device=dev)
+        ws = _workspace(lib.b200sp_bn_ws_bytes(M, C), dev, "bn")
+        check(lib.b200sp_bn_bwd(x.data_ptr(), dy.data_ptr(), M, C, weight.data_ptr() if weight is not None else None,
+                                bias.data_ptr() if bias is not None else None, stats[0].data_ptr(),
+                                stats[1].data_ptr(), 1 if ctx.relu else 0, dx.data_ptr(), dwb[0].data_ptr(),
+                                dwb[1].data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "bn_bwd")
+        dw = dwb[0] if weight is not None and ctx.needs_input_grad[1] else None
+        db = dwb[1] if bias is not None and ctx.needs_input_grad[2] else None
+        return dx, dw, db, None, None, None, None, None, None
+
+
+def affine_relu(x, scale, shift, relu=True):
+    _req_cuda(x)
+    x = _f32c(x)
+    y = torch.empty_like(x)
+    check(lib.b200sp_affine_relu(x.data_ptr(), x.shape[0], x.shape[1], scale.data_ptr(), shift.data_ptr(),
+                                 1 if relu else 0, y.data_ptr(), _stream()), "affine_relu")
+    return y
+
+
+def batch_norm_relu(x, bn, relu=True):
+    """Apply a torch BatchNorm-like module `bn` (nn.BatchNorm1d or DODA's DSNorm, model/dsnorm.py:63-84) to the
+    active-site matrix x [N, C], fused with ReLU, using the sm_100a kernels."""
+    if hasattr(bn, "domain_label") and hasattr(bn, "running_mean_source"):  # DSNorm: per-domain running stats
+        rm = bn.running_mean_target if bn.domain_label else bn.running_mean_source
+        rv = bn.running_var_target if bn.domain_label else bn.running_var_source
+    else:
+        rm, rv = bn.running_mean, bn.running_var
+    use_batch_stats = bn.training or not bn.track_running_stats or rm is None
+    if use_batch_stats:
+        nbt = None
+        momentum = 0.0 if bn.momentum is None else bn.momentum
+        if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+            nbt = bn.num_batches_tracked
+            if bn.momentum is None:  # cumulative moving average
+                momentum = 1.0 / float(int(nbt.item()) + 1)
+        upd = bn.training and bn.track_running_stats
+        return BNReLUFunction.apply(x, bn.weight, bn.bias, rm if upd else None, rv if upd else None, nbt, momentum,
+                                    bn.eps, relu)
+    if torch.is_grad_enabled() and (x.requires_grad or (bn.weight is not None and bn.weight.requires_grad)):
+        y = torch.nn.functional.batch_norm(x, rm, rv, bn.weight, bn.bias, False, 0.0, bn.eps)
+        return torch.relu(y) if relu else y
+    scale = torch.rsqrt(rv + bn.eps)
+    if bn.weight is not None:
+        scale = scale * bn.weight
+    shift = -rm * scale
+    if bn.bias is not None:
+        shift = shift + bn.bias
+    return affine_relu(x, scale.contiguous(), shift.contiguous(), relu)
+
+
+# ------------------------------------------------------------------------------------------------
+# row gather / scatter-add (devoxelize, model/unet.py:62)
+# ------------------------------------------------------------------------------------------------
+class GatherRowsFunction(Function):
+    @staticmethod
+    def forward(ctx, src, idx):
+        _req_cuda(src, idx)
+        src = _f32c(src)
+        idx = idx.contiguous()
+        if idx.dtype not in (torch.int32, torch.int64):
+            raise TypeError("index must be int32/int64")
+        n, C = idx.shape[0], src.shape[1]
+        out = torch.empty((n, C), dtype=_F32, device=src.device)
+        check(lib.b200sp_gather_rows(src.data_ptr(), idx.data_ptr(), 1 if idx.dtype == torch.int64 else 0, n, C,
+                                     out.data_ptr(), _stream()), "gather_rows")
+        ctx.save_for_backward(idx)
+        ctx.n_src = src.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        g = _f32c(g)
+        n, C = g.shape
+        d = torch.zeros((ctx.n_src, C), dtype=_F32, device=g.device)
+        check(lib.b200sp_scatter_add_rows(g.data_ptr(), idx.data_ptr(), 1 if idx.dtype == torch.int64 else 0, n, C,
+                                          d.data_ptr(), _stream()), "scatter_add_rows")
+        return d, None
+
+
+def gather_rows(src, idx):
+    return GatherRowsFunction.apply(src, idx)

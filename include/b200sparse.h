@@ -1,0 +1,203 @@
+/*
+ * b200sparse.h — C ABI of libb200sparse.so, the sm_100a sparse-3D-convolution engine that sits
+ * behind DODA's operator surface (spconv v1.2 / PG_OP / pointops2_cuda).
+ *
+ * Conventions
+ *   - every entry point returns int: 0 = ok, <0 = error (see B200SP_E*); the message is available
+ *     from b200sp_last_error() (thread-local).  Nothing here calls exit()/abort().
+ *   - pointers marked "dev" are CUDA device pointers, "host" are host pointers.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - the caller allocates every output (as the reference's Python wrappers do,
+ *     lib/pointgroup_ops/functions/pointgroup_ops.py:59,72,138-139,273).
+ *   - features are fp32 row-major [rows, C]; indices/rulebooks are int32; coords are
+ *     int32 [M,4] = (batch, i0, i1, i2) in the axis order of spatial_shape.
+ *
+ * Each block cites the reference interface it replaces.
+ */
+#ifndef B200SPARSE_H_
+#define B200SPARSE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SP_OK 0
+#define B200SP_EINVAL (-1)   /* bad argument */
+#define B200SP_ECUDA (-2)    /* CUDA runtime / launch error */
+#define B200SP_ENOMEM (-3)   /* workspace too small */
+#define B200SP_EUNSUP (-4)   /* configuration not supported by this build */
+
+const char* b200sp_last_error(void);
+int b200sp_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Rulebook builder.  Replaces spconv v1.2 `ops.get_indice_pairs` (called from
+ * SparseConvolution.forward; reference call sites model/unet.py:36, model/unet_block.py:26,29,70,78).
+ *
+ * Tables produced (all int32, -1 = none):
+ *   nbr  [M, K]           SubM: nbr[q,k] = input row at site(q) + (k - centre)   (out -> in view)
+ *   fwd  [M_in, K]        strided conv: fwd[j,k] = output row reached by input j through offset k
+ *   bwd  [M_out, K]       strided conv: bwd[o,k] = input row feeding output o through offset k
+ *   pairs [2, K, M_in]    spconv layout, canonical order (ascending input row inside each offset)
+ *   pairnum [K]
+ * ------------------------------------------------------------------------------------------ */
+
+/* bytes of device workspace needed by the two builders below for M_in rows and K offsets */
+int64_t b200sp_rulebook_ws_bytes(int64_t M_in, int K, int cand_per_input);
+
+/* SubM (stride 1, output sites == input sites). ksize/dil per axis; padding is k/2 as in spconv. */
+int b200sp_rulebook_subm(const int32_t* coords_dev, int64_t M, int batch, const int32_t* shape_host /*[3]*/,
+                         const int32_t* ksize_host /*[3]*/, const int32_t* dil_host /*[3]*/,
+                         int32_t* nbr_dev /*[M,K]*/, int32_t* pairs_dev /*[2,K,M] or NULL*/,
+                         int32_t* pairnum_dev /*[K] or NULL*/, void* ws_dev, int64_t ws_bytes, void* stream);
+
+/* Regular (strided) sparse conv.  Output sites are returned in ascending flattened index
+ * (the spconv-CUDA convention).  out_coords/bwd must be sized for the upper bound
+ * M_in * cand_per_input rows; *n_out_host receives the real count (this call synchronises the
+ * stream once to read it). */
+int b200sp_rulebook_conv(const int32_t* coords_dev, int64_t M_in, int batch, const int32_t* shape_host,
+                         const int32_t* out_shape_host, const int32_t* ksize_host, const int32_t* stride_host,
+                         const int32_t* pad_host, const int32_t* dil_host, int cand_per_input,
+                         int32_t* out_coords_dev /*[ub,4]*/, int32_t* fwd_dev /*[M_in,K]*/,
+                         int32_t* bwd_dev /*[ub,K]*/, int32_t* pairs_dev /*[2,K,M_in] or NULL*/,
+                         int32_t* pairnum_dev /*[K] or NULL*/, int64_t* n_out_host, void* ws_dev,
+                         int64_t ws_bytes, void* stream);
+
+/* pairs [2,K,M_in] (spconv layout) -> out-stationary table tab[n_out,K]; `inverse` swaps roles. */
+int b200sp_pairs_to_table(const int32_t* pairs_dev, const int32_t* pairnum_dev, int K, int64_t M_in,
+                          int inverse, int32_t* tab_dev /*[n_out,K]*/, int64_t n_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Convolution.  Replaces spconv v1.2 `ops.indice_conv` / `ops.indice_conv_backward`
+ * (gather -> SGEMM -> scatter-add per offset) with one output-stationary gather-GEMM launch.
+ *
+ *   out[r,:] (+)= sum_k  in[tab[r,k], :] @ W[k]          tab == NULL, K == 1  ->  plain GEMM (1x1 conv)
+ *
+ * W is [K][Cin][Cout] contiguous.  dgrad uses the same entry point on b200sp_weight_transpose(W)
+ * (mirrored offsets for SubM) and the out->in table of the adjoint.
+ * ------------------------------------------------------------------------------------------ */
+int b200sp_gather_gemm(const float* in_dev, int64_t n_in, int Cin, const float* W_dev, const int32_t* tab_dev, int K,
+                       float* out_dev, int64_t n_out, int Cout, int accumulate, void* stream);
+
+/* pair-grouped variant (each output row written by exactly one pair; used for the non-overlapping
+ * inverse conv forward and the strided conv dgrad):  out[po[k][i],:] = in[pi[k][i],:] @ W[k].
+ * pairnum stays on the device (no host sync): n_upper >= max_k pairnum[k] sizes the grid and CTAs past
+ * pairnum[k] exit immediately. */
+int b200sp_gather_gemm_pairs(const float* in_dev, int Cin, const float* W_dev, const int32_t* pairs_in_dev /*[K,stride]*/,
+                             const int32_t* pairs_out_dev, const int32_t* pairnum_dev, int64_t n_upper, int K,
+                             int64_t pair_stride, float* out_dev, int Cout, int accumulate, void* stream);
+
+/* weight gradient: dW[k][ci][co] += sum_i a[pa[k][i]][ci] * b[pb[k][i]][co].   pa/pb NULL -> identity
+ * rows (1x1 conv: n_upper rows, pairnum ignored).  dW must be zero-initialised by the caller. */
+int b200sp_wgrad(const float* a_dev, int Ca, const float* b_dev, int Cb, const int32_t* pa_dev, const int32_t* pb_dev,
+                 const int32_t* pairnum_dev, int64_t n_upper, int K, int64_t pair_stride, float* dW_dev /*[K,Ca,Cb]*/,
+                 void* stream);
+
+/* out[k'][co][ci] = W[k][ci][co], k' = mirror ? K-1-k : k   (weights for dgrad) */
+int b200sp_weight_transpose(const float* W_dev, int K, int Cin, int Cout, int mirror, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * BatchNorm(+ReLU) on active sites.  Replaces nn.BatchNorm1d(eps=1e-4, momentum=0.1) + nn.ReLU on the
+ * [N_active, C] feature matrix (model/unet.py:28,43; model/unet_block.py:24-28,46-47,68-69,76-77) and
+ * DSNorm's F.batch_norm call (model/dsnorm.py:79-84).
+ * ------------------------------------------------------------------------------------------ */
+int64_t b200sp_bn_ws_bytes(int64_t M, int C);
+/* training: batch statistics -> mean/invstd (saved for backward); y = [relu]((x-mean)*invstd*w + b).
+ * running_mean/var (nullable) are updated in place with `momentum` and the unbiased variance exactly as
+ * F.batch_norm does; num_batches_tracked (int64 on device, nullable) is incremented. */
+int b200sp_bn_fwd_train(const float* x_dev, int64_t M, int C, const float* w_dev, const float* b_dev, float eps,
+                        int relu, float* y_dev, float* mean_dev /*[C]*/, float* invstd_dev /*[C]*/,
+                        float* running_mean_dev, float* running_var_dev, float momentum,
+                        int64_t* num_batches_tracked_dev, void* ws_dev, int64_t ws_bytes, void* stream);
+/* inference / fixed statistics: y = [relu](x*scale + shift) */
+int b200sp_affine_relu(const float* x_dev, int64_t M, int C, const float* scale_dev, const float* shift_dev,
+                       int relu, float* y_dev, void* stream);
+int b200sp_bn_bwd(const float* x_dev, const float* dy_dev, int64_t M, int C, const float* w_dev, const float* b_dev,
+                  const float* mean_dev, const float* invstd_dev, int relu, float* dx_dev, float* dw_dev,
+                  float* db_dev, void* ws_dev, int64_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Point <-> voxel.  Replaces PG_OP.voxelize_idx (CPU, lib/pointgroup_ops/src/voxelize/voxelize.cpp:11-155),
+ * voxelize_fp / voxelize_bp / point_recover_fp / point_recover_bp (voxelize.cu:10-52, voxelize.cpp:185-205)
+ * and the devoxelize gather `features[p2v]` (model/unet.py:62) with its scatter-add backward.
+ * ------------------------------------------------------------------------------------------ */
+/* CPU, re-entrant, never touches CUDA (runs in forked DataLoader workers). Two-call protocol:
+ * pass out pointers NULL to obtain M and maxActive, then call again with buffers. */
+int b200sp_voxelize_idx_cpu(const int64_t* coords_host, int64_t N, int ncol /*3 or 4*/, int batch_size, int mode,
+                            int64_t* out_coords_host /*[M,ncol]*/, int32_t* input_map_host /*[N]*/,
+                            int32_t* output_map_host /*[M,1+maxActive]*/, int64_t* M_out, int32_t* max_active_out);
+/* out[v,:] (+)= mult * sum_i feats[map[v,1+i],:]   (mult = 1/count when average) ; no atomics */
+int b200sp_voxelize_fp(const float* feats_dev, float* out_dev, const int32_t* map_dev, int average, int64_t M,
+                       int max_active, int C, void* stream);
+/* d_feats[map[v,1+i],:] += mult * d_out[v,:] */
+int b200sp_voxelize_bp(const float* dout_dev, float* dfeats_dev, const int32_t* map_dev, int average, int64_t M,
+                       int max_active, int C, void* stream);
+/* out[i,:] = src[idx[i],:]   (idx int32 or int64) */
+int b200sp_gather_rows(const float* src_dev, const void* idx_dev, int idx_is_i64, int64_t n, int C, float* out_dev,
+                       void* stream);
+/* dst[idx[i],:] += src[i,:] */
+int b200sp_scatter_add_rows(const float* src_dev, const void* idx_dev, int idx_is_i64, int64_t n, int C,
+                            float* dst_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Remaining PG_OP kernels (lib/pointgroup_ops/src/pointgroup_ops_api.cpp:7-26).
+ * ------------------------------------------------------------------------------------------ */
+/* sec_mean.cu:12-109 — CSR-segment reductions, offsets int32 [P+1] */
+int b200sp_sec_mean(const float* inp_dev, const int32_t* offsets_dev, float* out_dev, int P, int C, void* stream);
+int b200sp_sec_mean_bp(const float* dout_dev, const int32_t* offsets_dev, float* dinp_dev, int P, int C, void* stream);
+int b200sp_sec_min(const float* inp_dev, const int32_t* offsets_dev, float* out_dev, int P, int C, void* stream);
+int b200sp_sec_max(const float* inp_dev, const int32_t* offsets_dev, float* out_dev, int P, int C, void* stream);
+/* bfs_cluster.cu:15-89 — radius neighbours inside the point's batch segment. Returns the total
+ * neighbour count in *n_active_host (may exceed n*mean_active: caller retries, as the reference does). */
+int64_t b200sp_ballquery_ws_bytes(int n);
+int b200sp_ballquery_batch_p(const float* xyz_dev, const int32_t* batch_idxs_dev, const int32_t* batch_offsets_dev,
+                             int32_t* idx_dev, int32_t* start_len_dev, int n, int mean_active, float radius,
+                             void* ws_dev, int64_t ws_bytes, int32_t* n_active_host, void* stream);
+/* bfs_cluster.cpp:28-111 — CPU BFS connected components. Two-call protocol like voxelize_idx. */
+int b200sp_bfs_cluster_cpu(const int32_t* sem_host, const int32_t* idx_host, const int32_t* start_len_host, int N,
+                           int threshold, int32_t* cluster_idxs_host /*[sum,2]*/, int32_t* cluster_offsets_host,
+                           int64_t* n_idx_out, int64_t* n_cluster_out);
+/* roipool.cu:12-49 */
+int b200sp_roipool_fp(const float* feats_dev, const int32_t* offsets_dev, float* out_dev, int32_t* maxidx_dev,
+                      int P, int C, void* stream);
+int b200sp_roipool_bp(const float* dout_dev, const int32_t* maxidx_dev, float* dfeats_dev, int P, int C, void* stream);
+/* get_iou.cu:12-29 */
+int b200sp_get_iou(const int32_t* proposals_idx_dev, const int32_t* proposals_offset_dev,
+                   const int64_t* instance_labels_dev, const int32_t* instance_pointnum_dev, float* iou_dev, int P,
+                   int I, void* stream);
+/* knn.cu:7-50 */
+int b200sp_knn_batch(const float* xyz_dev, const float* query_dev, const int32_t* batch_idxs_dev,
+                     const int32_t* query_offsets_dev, int32_t* idx_dev, int n, int m, int k, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * pointops2_cuda (lib/pointops2/src/pointops_api.cpp:13-23).  `offset` arguments are END offsets
+ * without the leading 0 (functions/pointops2.py:47,66).
+ * ------------------------------------------------------------------------------------------ */
+int b200sp_knnquery(int m, int nsample, const float* xyz_dev, const float* new_xyz_dev, const int32_t* offset_dev,
+                    const int32_t* new_offset_dev, int32_t* idx_dev, float* dist2_dev, void* stream);
+int b200sp_furthestsampling(int b, int n_max, int dim, const float* xyz_dev, const int32_t* offset_dev,
+                            const int32_t* new_offset_dev, float* tmp_dev, int32_t* idx_dev, void* stream);
+int b200sp_grouping_fwd(int m, int nsample, int c, const float* in_dev, const int32_t* idx_dev, float* out_dev,
+                        void* stream);
+int b200sp_grouping_bwd(int m, int nsample, int c, const float* dout_dev, const int32_t* idx_dev, float* din_dev,
+                        void* stream);
+int b200sp_interpolation_fwd(int n, int c, int k, const float* in_dev, const int32_t* idx_dev,
+                             const float* weight_dev, float* out_dev, void* stream);
+int b200sp_interpolation_bwd(int n, int c, int k, const float* dout_dev, const int32_t* idx_dev,
+                             const float* weight_dev, float* din_dev, void* stream);
+int b200sp_subtraction_fwd(int n, int nsample, int c, const float* in1_dev, const float* in2_dev,
+                           const int32_t* idx_dev, float* out_dev, void* stream);
+int b200sp_subtraction_bwd(int n, int nsample, int c, const int32_t* idx_dev, const float* dout_dev,
+                           float* din1_dev, float* din2_dev, void* stream);
+int b200sp_aggregation_fwd(int n, int nsample, int c, int w_c, const float* in_dev, const float* pos_dev,
+                           const float* w_dev, const int32_t* idx_dev, float* out_dev, void* stream);
+int b200sp_aggregation_bwd(int n, int nsample, int c, int w_c, const float* in_dev, const float* pos_dev,
+                           const float* w_dev, const int32_t* idx_dev, const float* dout_dev, float* din_dev,
+                           float* dpos_dev, float* dw_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SPARSE_H_ */
