@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py -- scenes/s forward+backward of DODA's sparse U-Net on synthetic ScanNet-shaped scenes
+(BASELINE.json configs[1]: 2 x 150k-voxel scenes, full unet.py fwd+bwd, bs=2 per GPU).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU, NCCL; whole scenes are sharded,
+                                                          gradients all-reduced by DDP: "scaling": "weak")
+
+Prints ONE JSON line (rank 0).  `value` = scenes/s with the collated batch already resident in HBM;
+`e2e` = the same step through the public API from pinned HOST buffers (H2D of the batch + D2H of the loss inside
+the timed region); `roofline` = the dominant kernel (k_gather_gemm, the sparse-conv gather-GEMM) timed live with
+CUDA events; `cpu_baseline` = the CPU oracle (restatement of spconv v1.2's native algorithm) on the host cores.
+`--impl reference` times that CPU implementation as the reference arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "scenes/sec fwd+bwd Sparse U-Net @150k voxels"
+UNIT = "scenes/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--voxels", type=int, default=150000)
+    ap.add_argument("--bs", type=int, default=2, help="scenes per GPU")
+    ap.add_argument("--mid", type=int, default=16, help="MODEL.BACKBONE.mid_channel (16 as shipped)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--detail", default="", help="write per-kernel detail JSON here")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt, self.proc = index, [], threading.Event(), None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self._stop_evt.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batch(rank, bs, voxels):
+    from doda_b200 import scenes
+    return scenes.collate([scenes.scene_with_voxels(1000 * rank + i, voxels) for i in range(bs)], seed=rank, dup_max=2)
+
+
+def conv_layer_bytes(rec):
+    """Algorithmic (compulsory) bytes of one gather-GEMM launch, SURVEY.md §8(d):
+    4*(M_in*Cin + M_out*Cout) + 4*K*Cin*Cout + 4*(table entries read)."""
+    return 4 * (rec["n_in"] * rec["Cin"] + rec["n_out"] * rec["Cout"]) + 4 * rec["K"] * rec["Cin"] * rec["Cout"] \
+        + 4 * rec["tab_entries"]
+
+
+def run_reference(args):
+    """Reference arm: the CPU restatement of the reference's (spconv v1.2 native) algorithm on the host cores."""
+    import torch
+    from doda_b200.unet import SparseConvNet
+    from oracle.unet_ref import model_step_ref
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    batch = make_batch(0, args.bs, args.voxels)
+    model = SparseConvNet(mid_channel=args.mid)
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        loss, _ = model_step_ref(sd, batch, training=True)
+        loss.backward()
+        return float(loss)
+
+    steps = max(1, min(args.steps, 5))  # each step is the FULL workload (~5 s of CPU work); bounded to stay in minutes
+    warm = max(1, min(args.warmup, 1))
+    for _ in range(warm):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    val = args.bs / dt
+    sample = "full step (bs=%d x %dk voxels, m=%d), %d timed steps" % (args.bs, args.voxels // 1000, args.mid, steps)
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+           "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "2x150k-voxel ScanNet-shape scenes, full SparseConvNet fwd+bwd, bs=%d, m=%d"
+                      % (args.bs, args.mid), "voxels_per_scene": args.voxels, "scenes_per_gpu": args.bs,
+                      "mid_channel": args.mid, "device": "host CPU (oracle port of spconv v1.2 native algorithm)"},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from doda_b200 import ops
+    from doda_b200._lib import lib
+    from doda_b200.unet import SparseConvNet, model_step
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the sm_100a path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib.load()  # fail loudly if the extension is missing
+
+    torch.manual_seed(0)
+    batch = make_batch(rank, args.bs, args.voxels)
+    model = SparseConvNet(mid_channel=args.mid).to(dev).train()
+    net = model
+    if world > 1:
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    criterion = torch.nn.CrossEntropyLoss(ignore_index=255)
+    tensor_keys = ["voxel_locs", "p2v_map", "v2p_map", "feats", "labels"]
+    host = dict(batch)
+    for k in tensor_keys:
+        host[k] = batch[k].pin_memory()
+    resident = dict(batch)
+    for k in tensor_keys:
+        resident[k] = batch[k].to(dev)
+    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in tensor_keys)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step(b):
+        for p in model.parameters():
+            p.grad = None
+        loss, _ = model_step(net, b, criterion=criterion, device=dev)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(b, nsteps, read_loss):
+        evs = []
+        barrier()
+        for _ in range(nsteps):
+            flush.zero_()  # L2 flush between timed iterations (not timed)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            loss = step(b)
+            if read_loss:
+                float(loss)  # device -> host read of the step's result
+            e.record()
+            evs.append((s, e))
+        barrier()
+        tot = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([tot], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    calls0 = ops.launch_count()
+    ms_total = timed(resident, args.steps, False)
+    launches = ops.launch_count() - calls0
+    ms_e2e = timed(host, args.steps, True)
+    if sampler:
+        sampler.stop()
+    scenes_per_step = args.bs * world
+    value = scenes_per_step * args.steps / (ms_total / 1e3)
+    e2e_val = scenes_per_step * args.steps / (ms_e2e / 1e3)
+
+    roof = None
+    detail = None
+    if rank == 0 and not args.no_roofline:
+        ops.profile_begin()
+        step(resident)
+        torch.cuda.synchronize()
+        recs = ops.profile_end()
+        gg = [r for r in recs if r["kernel"] == "k_gather_gemm"]
+        if gg:
+            tot_ms = sum(r["ms"] for r in gg)
+            tot_bytes = sum(conv_layer_bytes(r) for r in gg)
+            tot_flops = sum(2.0 * r["pairs_dense"] * r["Cin"] * r["Cout"] for r in gg)
+            all_ms = sum(r["ms"] for r in recs)
+            peak, how = peaks()
+            ach = tot_bytes / (tot_ms * 1e-3) / 1e9
+            top = max(gg, key=lambda r: r["ms"])
+            roof = {"bound": "hbm", "kernel": "k_gather_gemm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": None, "peak_source": how, "launches_per_step": len(gg),
+                    "avg_launch_ms": tot_ms / len(gg), "share_of_engine_kernel_time": tot_ms / max(all_ms, 1e-9),
+                    "dense_tflops": tot_flops / (tot_ms * 1e-3) / 1e12,
+                    "top_launch": {"ms": top["ms"], "n_out": top["n_out"], "Cin": top["Cin"], "Cout": top["Cout"],
+                                   "K": top["K"], "GBs": conv_layer_bytes(top) / (top["ms"] * 1e-3) / 1e9}}
+            detail = recs
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle.unet_ref import model_step_ref
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        sd = {k: v.detach().cpu().clone().requires_grad_(v.dtype.is_floating_point)
+              for k, v in model.state_dict().items()}
+        t0 = time.perf_counter()
+        loss_c, _ = model_step_ref(sd, batch, training=True)
+        loss_c.backward()
+        dt = time.perf_counter() - t0
+        cpu_base = {"value": args.bs / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                    "sample": "1 full step (bs=%d x %dk voxels, m=%d) of the CPU oracle, %.1f s"
+                              % (args.bs, args.voxels // 1000, args.mid, dt)}
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+               "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+               "config": {"workload": "2x150k-voxel ScanNet-shape scenes, full SparseConvNet fwd+bwd, bs=%d, m=%d"
+                          % (args.bs, args.mid), "voxels_per_scene": args.voxels, "scenes_per_gpu": args.bs,
+                          "mid_channel": args.mid, "parallelism": "dp%d (whole scenes per rank, DDP grad all-reduce)"
+                          % world, "l2": "256 MB flush between timed steps"},
+               "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                       "ms_per_step": ms_e2e / args.steps},
+               "gpu_launches": launches, "clocks": sampler.summary() if sampler else None}
+        if roof:
+            out["roofline"] = roof
+        if cpu_base:
+            out["cpu_baseline"] = cpu_base
+        print(json.dumps(out))
+        if args.detail and detail is not None:
+            with open(args.detail, "w") as f:
+                json.dump(detail, f)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

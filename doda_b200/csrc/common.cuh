@@ -27,7 +27,14 @@ void set_error(const char* fmt, ...);
         }                                                                                     \
     } while (0)
 
-#define B200SP_LAUNCH_CHECK() B200SP_CUDA(cudaGetLastError())
+// every kernel launch of this library is counted (bench.py reports it as gpu_launches)
+void add_launches(int n);
+#define B200SP_LAUNCH_CHECK_N(n)            \
+    do {                                    \
+        b200sp::add_launches(n);            \
+        B200SP_CUDA(cudaGetLastError());    \
+    } while (0)
+#define B200SP_LAUNCH_CHECK() B200SP_LAUNCH_CHECK_N(1)
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

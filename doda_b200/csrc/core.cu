@@ -6,6 +6,7 @@
 #include <unordered_map>
 #include <vector>
 #include <queue>
+#include <atomic>
 
 namespace b200sp {
 
@@ -17,6 +18,10 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void add_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long get_launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int num_sms() {
     static int n = 0;
@@ -49,6 +54,7 @@ using namespace b200sp;
 
 extern "C" const char* b200sp_last_error(void) { return g_err; }
 extern "C" int b200sp_version(void) { return 100; }
+extern "C" int64_t b200sp_launch_count(void) { return (int64_t)b200sp::get_launches(); }
 
 // Semantics follow lib/pointgroup_ops/src/voxelize/voxelize.cpp:62-155 (first-touch voxel ids while scanning
 // points in order; per-batch maps; output_map rows = [count, pt..., -1 pad]; coords of the first point) and

@@ -340,7 +340,7 @@ extern "C" int b200sp_bn_fwd_train(const float* x, int64_t M, int C, const float
         k_affine_relu<4><<<stream_grid(M * (C / 4), 256), 256, 0, st>>>(x, M, C, scale, shift, relu, y);
     else
         k_affine_relu<1><<<stream_grid(M * C, 256), 256, 0, st>>>(x, M, C, scale, shift, relu, y);
-    B200SP_LAUNCH_CHECK();
+    B200SP_LAUNCH_CHECK_N(3);
     return B200SP_OK;
 }
 
@@ -387,7 +387,7 @@ extern "C" int b200sp_bn_bwd(const float* x, const float* dy, int64_t M, int C, 
     else
         k_bn_bwd_apply<1><<<stream_grid(M * C, 256), 256, 0, st>>>(x, dy, M, C, scale, shift, mean, invstd, c_g, c_mg,
                                                                   c_mgx, relu, dx);
-    B200SP_LAUNCH_CHECK();
+    B200SP_LAUNCH_CHECK_N(4);
     return B200SP_OK;
 }
 

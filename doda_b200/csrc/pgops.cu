@@ -243,7 +243,7 @@ extern "C" int b200sp_ballquery_batch_p(const float* xyz, const int32_t* bidx, c
     B200SP_CUDA(cub::DeviceScan::ExclusiveSum(p, cub_bytes, counts, starts, n + 1, st));
     int64_t limit = (int64_t)n * mean_active;
     k_ballquery<true><<<grid, BQ_TILE, 0, st>>>(xyz, bidx, boff, n, r2, nullptr, starts, idx, start_len, limit);
-    B200SP_LAUNCH_CHECK();
+    B200SP_LAUNCH_CHECK_N(2 + 2 /* cub scan */);
     int total = 0;
     B200SP_CUDA(cudaMemcpyAsync(&total, starts + n, 4, cudaMemcpyDeviceToHost, st));
     B200SP_CUDA(cudaStreamSynchronize(st));

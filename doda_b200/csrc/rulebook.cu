@@ -236,7 +236,7 @@ static int emit_pairs(const int* tab, int64_t M, int K, int mirror, int* pairs, 
         k_pairs_scan<<<K, 256, 0, st>>>(blockcnt, nblk, pairnum);
         k_pairs_write<RB><<<nblk, 256, smem, st>>>(tab, M, K, mirror, nblk, blockcnt, pairs);
     }
-    B200SP_LAUNCH_CHECK();
+    B200SP_LAUNCH_CHECK_N(3);
     return B200SP_OK;
 }
 
@@ -333,7 +333,7 @@ extern "C" int b200sp_rulebook_subm(const int32_t* coords, int64_t M, int batch,
     B200SP_CUDA(cudaMemsetAsync(t.vals, 0x7F, cap * 4, st));
     k_hash_insert_coords<<<(unsigned)cdiv(M, 256), 256, 0, st>>>((const int4*)coords, M, g, t);
     k_subm_table<<<(unsigned)cdiv(M * g.K, 256), 256, 0, st>>>((const int4*)coords, M, g, t, nbr);
-    B200SP_LAUNCH_CHECK();
+    B200SP_LAUNCH_CHECK_N(2);
     if (pairs) {
         // pair (in=j, out=o) at offset k  <=>  in = o + (k - centre)  <=>  o = nbr[j, K-1-k]
         int rc = emit_pairs(nbr, M, g.K, /*mirror=*/1, pairs, pairnum, blockcnt, st);
@@ -402,7 +402,7 @@ extern "C" int b200sp_rulebook_conv(const int32_t* coords, int64_t M, int batch,
     k_conv_rank<<<(unsigned)cdiv(n_out, 256), 256, 0, st>>>(sorted, n_out, g, t, (int4*)out_coords);
     B200SP_CUDA(cudaMemsetAsync(bwd, 0xFF, sizeof(int) * (size_t)n_out * g.K, st));
     k_conv_tables<<<grid, 256, 0, st>>>((const int4*)coords, M, g, t, fwd, bwd);
-    B200SP_LAUNCH_CHECK();
+    B200SP_LAUNCH_CHECK_N(2 + 3 /* cub radix sort passes */);
     if (pairs) {
         int rc = emit_pairs(fwd, M, g.K, /*mirror=*/0, pairs, pairnum, blockcnt, st);
         if (rc) return rc;

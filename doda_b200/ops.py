@@ -30,6 +30,52 @@ def _f32c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def launch_count():
+    """CUDA kernels launched by libb200sparse in this process (bench.py: gpu_launches)."""
+    return int(lib.b200sp_launch_count())
+
+
+# optional per-call CUDA-event timing (bench.py roofline pass); off in normal operation
+_prof = None
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    global _prof
+    torch.cuda.synchronize()
+    recs = []
+    for info, s, e in _prof or []:
+        info = dict(info)
+        info["ms"] = s.elapsed_time(e)
+        recs.append(info)
+    _prof = None
+    return recs
+
+
+class _Timed(object):
+    __slots__ = ("info", "s")
+
+    def __init__(self, **info):
+        self.info = info
+
+    def __enter__(self):
+        if _prof is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *a):
+        if _prof is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            _prof.append((self.info, self.s, e))
+        return False
+
+
 _ws = {}
 
 
@@ -165,9 +211,11 @@ def gather_gemm(feat, W3, tab, n_out, out=None, accumulate=False):
     K, Cin, Cout = W3.shape
     if out is None:
         out = torch.empty((n_out, Cout), dtype=_F32, device=feat.device)
-    check(lib.b200sp_gather_gemm(feat.data_ptr(), feat.shape[0], Cin, W3.data_ptr(),
-                                 tab.data_ptr() if tab is not None else None, K, out.data_ptr(), n_out, Cout,
-                                 1 if accumulate else 0, _stream()), "gather_gemm")
+    with _Timed(kernel="k_gather_gemm", n_in=feat.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K,
+                tab_entries=n_out * K if tab is not None else 0, pairs_dense=n_out * K):
+        check(lib.b200sp_gather_gemm(feat.data_ptr(), feat.shape[0], Cin, W3.data_ptr(),
+                                     tab.data_ptr() if tab is not None else None, K, out.data_ptr(), n_out, Cout,
+                                     1 if accumulate else 0, _stream()), "gather_gemm")
     return out
 
 
@@ -175,9 +223,11 @@ def gather_gemm_pairs(feat, W3, pin, pout, pairnum, n_upper, n_out):
     """out[pout[k][i]] = feat[pin[k][i]] @ W3[k]; rows not covered stay zero."""
     K, Cin, Cout = W3.shape
     out = torch.zeros((n_out, Cout), dtype=_F32, device=feat.device)
-    check(lib.b200sp_gather_gemm_pairs(feat.data_ptr(), Cin, W3.data_ptr(), pin.data_ptr(), pout.data_ptr(),
-                                       pairnum.data_ptr(), n_upper, K, pin.stride(0), out.data_ptr(), Cout, 0,
-                                       _stream()), "gather_gemm_pairs")
+    with _Timed(kernel="k_gather_gemm", n_in=feat.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K,
+                tab_entries=2 * n_upper, pairs_dense=n_upper, pairs_mode=1):
+        check(lib.b200sp_gather_gemm_pairs(feat.data_ptr(), Cin, W3.data_ptr(), pin.data_ptr(), pout.data_ptr(),
+                                           pairnum.data_ptr(), n_upper, K, pin.stride(0), out.data_ptr(), Cout, 0,
+                                           _stream()), "gather_gemm_pairs")
     return out
 
 
@@ -185,10 +235,11 @@ def wgrad(a, b, pa, pb, pairnum, n_upper, K):
     """dW[k] = sum_i a[pa[k][i]]^T b[pb[k][i]]  -> [K, Ca, Cb]"""
     Ca, Cb = a.shape[1], b.shape[1]
     dW = torch.zeros((K, Ca, Cb), dtype=_F32, device=a.device)
-    check(lib.b200sp_wgrad(a.data_ptr(), Ca, b.data_ptr(), Cb, pa.data_ptr() if pa is not None else None,
-                           pb.data_ptr() if pb is not None else None,
-                           pairnum.data_ptr() if pairnum is not None else None, n_upper, K,
-                           pa.stride(0) if pa is not None else 0, dW.data_ptr(), _stream()), "wgrad")
+    with _Timed(kernel="k_wgrad", n_rows=a.shape[0], Ca=Ca, Cb=Cb, K=K, n_upper=n_upper):
+        check(lib.b200sp_wgrad(a.data_ptr(), Ca, b.data_ptr(), Cb, pa.data_ptr() if pa is not None else None,
+                               pb.data_ptr() if pb is not None else None,
+                               pairnum.data_ptr() if pairnum is not None else None, n_upper, K,
+                               pa.stride(0) if pa is not None else 0, dW.data_ptr(), _stream()), "wgrad")
     return dW
 
 

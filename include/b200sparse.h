@@ -31,6 +31,8 @@ extern "C" {
 
 const char* b200sp_last_error(void);
 int b200sp_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */
+int64_t b200sp_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Rulebook builder.  Replaces spconv v1.2 `ops.get_indice_pairs` (called from

@@ -1,0 +1,93 @@
+"""Functional CPU restatement of DODA's SparseConvNet forward (model/unet.py:58-69 with the blocks of
+model/unet_block.py:32-38 ResidualBlock, 87-100 UBlock) on top of the oracle rulebook/conv.  Parameters come from a
+state_dict with the reference's key names; gradients come from torch autograd, so one call gives the forward AND
+backward baseline (`loss.backward()`)."""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .rulebook import get_indice_pairs_ref
+from .conv import indice_conv_ref
+
+
+class _Sp(object):
+    def __init__(self, feats, idx, shape, bs, rbs):
+        self.f, self.idx, self.shape, self.bs, self.rbs = feats, idx, shape, bs, rbs
+
+
+def _bn_relu(sd, pre, x, training, eps=1e-4, momentum=0.1):
+    # nn.BatchNorm1d(eps=1e-4, momentum=0.1) + nn.ReLU (model/unet.py:28,43-44)
+    rm, rv = sd.get(pre + ".running_mean"), sd.get(pre + ".running_var")
+    y = F.batch_norm(x, None if training else rm, None if training else rv, sd[pre + ".weight"], sd[pre + ".bias"],
+                     training, momentum, eps)
+    return F.relu(y)
+
+
+def _subm3(sd, name, t, key):
+    if key not in t.rbs:
+        t.rbs[key] = get_indice_pairs_ref(t.idx, t.bs, t.shape, 3, 1, 1, 1, subm=True)
+    _, pairs, pairnum, _ = t.rbs[key]
+    return indice_conv_ref(t.f, sd[name], pairs, pairnum, t.f.shape[0], subm=True)
+
+
+def _residual(sd, pre, t, key, training):
+    # model/unet_block.py:32-38
+    x = t.f
+    w_skip = sd.get(pre + ".i_branch.0.weight")
+    skip = x if w_skip is None else x @ w_skip.reshape(w_skip.shape[-2], w_skip.shape[-1])  # 1x1 SubM == GEMM
+    h = _bn_relu(sd, pre + ".conv_branch.0", x, training)
+    h = _subm3(sd, pre + ".conv_branch.2.weight", _Sp(h, t.idx, t.shape, t.bs, t.rbs), key)
+    h = _bn_relu(sd, pre + ".conv_branch.3", h, training)
+    h = _subm3(sd, pre + ".conv_branch.5.weight", _Sp(h, t.idx, t.shape, t.bs, t.rbs), key)
+    return _Sp(h + skip, t.idx, t.shape, t.bs, t.rbs)
+
+
+def _ublock(sd, pre, t, level, nlevels, reps, training):
+    # model/unet_block.py:87-100
+    key = "subm%d" % level
+    for i in range(reps):
+        t = _residual(sd, "%s.blocks.block%d" % (pre, i), t, key, training)
+    if level < nlevels:
+        skip = t.f
+        h = _bn_relu(sd, pre + ".conv.0", t.f, training)
+        outids, pairs, pairnum, oshape = get_indice_pairs_ref(t.idx, t.bs, t.shape, 2, 2, 0, 1, subm=False)
+        d = indice_conv_ref(h, sd[pre + ".conv.2.weight"], pairs, pairnum, outids.shape[0])
+        child = _ublock(sd, pre + ".u", _Sp(d, outids, oshape, t.bs, t.rbs), level + 1, nlevels, reps, training)
+        h = _bn_relu(sd, pre + ".deconv.0", child.f, training)
+        up = indice_conv_ref(h, sd[pre + ".deconv.2.weight"], pairs, pairnum, t.f.shape[0], inverse=True)
+        t = _Sp(torch.cat((skip, up), dim=1), t.idx, t.shape, t.bs, t.rbs)
+        for i in range(reps):
+            t = _residual(sd, "%s.blocks_tail.block%d" % (pre, i), t, key, training)
+    return t
+
+
+def unet_forward_ref(sd, voxel_feats, voxel_coords, spatial_shape, batch_size, p2v, training=True, nlevels=7,
+                     reps=2):
+    """-> per-point scores [N, n_classes]  (model/unet.py:58-69)"""
+    idx = np.asarray(voxel_coords, dtype=np.int64)
+    t = _Sp(voxel_feats, idx, [int(s) for s in spatial_shape], batch_size, {})
+    t = _Sp(_subm3(sd, "input_conv.0.weight", t, "subm1"), idx, t.shape, batch_size, t.rbs)
+    t = _ublock(sd, "unet", t, 1, nlevels, reps, training)
+    h = _bn_relu(sd, "output_layer.0", t.f, training)
+    pts = h[torch.as_tensor(np.asarray(p2v), dtype=torch.int64)]
+    return pts @ sd["linear.weight"].t() + sd["linear.bias"]
+
+
+def voxelize_mean_ref(feats, v2p):
+    """mode-4 voxelization of point features (voxelize.cu:10-23): mean over the voxel's points."""
+    v2p = torch.as_tensor(np.asarray(v2p), dtype=torch.int64)
+    cnt = v2p[:, 0].clamp(min=1).to(feats.dtype)
+    out = torch.zeros((v2p.shape[0], feats.shape[1]), dtype=feats.dtype)
+    for j in range(1, v2p.shape[1]):
+        m = v2p[:, 0] >= j
+        out[m] += feats[v2p[m, j]]
+    return out / cnt[:, None]
+
+
+def model_step_ref(sd, batch, training=True):
+    """model_fn forward (model/unet.py:72-99,154-198): voxelize features, net, CE(ignore 255). -> (loss, scores)"""
+    vf = voxelize_mean_ref(batch["feats"], batch["v2p_map"])
+    scores = unet_forward_ref(sd, vf, batch["voxel_locs"].numpy(), batch["spatial_shape"],
+                              batch["offsets"].shape[0] - 1, batch["p2v_map"].numpy(), training)
+    loss = F.cross_entropy(scores, batch["labels"], ignore_index=255)
+    return loss, scores

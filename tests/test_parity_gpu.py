@@ -1,0 +1,259 @@
+"""GPU parity: the sm_100a path (through the C ABI) against the CPU oracle on identical seeded inputs.
+Integer / index results are compared bit-exactly; fp32 results with the SURVEY.md A.8 metric
+max|a-b| / max|b| <= 1e-4 (north_star's tolerance) against an fp64 evaluation of the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err, random_coords, surface_coords
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _rb_oracle(coords, batch, shape, ks, st, pd, dl, subm):
+    from oracle.rulebook import get_indice_pairs_ref
+    return get_indice_pairs_ref(coords, batch, shape, ks, st, pd, dl, subm=subm)
+
+
+def _check_rulebook(cuda_dev, coords, batch, shape, ks, st, pd, dl, subm):
+    from doda_b200 import ops
+    rb = ops.build_rulebook(torch.from_numpy(coords).to(cuda_dev), batch, shape, ks, st, pd, dl, subm=subm)
+    outids, pairs, pairnum, oshape = _rb_oracle(coords, batch, shape, ks, st, pd, dl, subm)
+    assert list(rb.out_spatial_shape) == list(oshape)
+    assert np.array_equal(rb.outids.cpu().numpy(), outids)
+    assert np.array_equal(rb.pairnum.cpu().numpy(), pairnum)
+    assert np.array_equal(rb.pairs.cpu().numpy(), pairs)  # includes the -1 padding
+    return rb, (outids, pairs, pairnum, oshape)
+
+
+@pytest.mark.parametrize("n,shape,batch", [(2000, (40, 37, 29), 2), (1, (5, 5, 5), 1), (300, (7, 7, 7), 3),
+                                           (20000, (128, 128, 128), 2)])
+def test_rulebook_subm_exact(cuda_dev, n, shape, batch):
+    coords = random_coords(1, n, batch, shape)
+    rb, (_, pairs, pairnum, _) = _check_rulebook(cuda_dev, coords, batch, list(shape), 3, 1, 1, 1, True)
+    # the engine's out->in table is consistent with the pairs: nbr[out, k] == in
+    nbr = rb.nbr.cpu().numpy()
+    K = 27
+    ref = np.full_like(nbr, -1)
+    for k in range(K):
+        n_k = pairnum[k]
+        ref[pairs[1, k, :n_k], k] = pairs[0, k, :n_k]
+    assert np.array_equal(nbr, ref)
+
+
+def test_rulebook_subm_surface_scene(cuda_dev):
+    coords, shape = surface_coords(0, 10000, 2)
+    _check_rulebook(cuda_dev, coords, 2, shape, 3, 1, 1, 1, True)
+
+
+@pytest.mark.parametrize("shape", [(40, 37, 29), (33, 33, 33), (8, 9, 2)])
+def test_rulebook_down_k2s2_exact(cuda_dev, shape):
+    # odd extents: voxels on the last odd plane are dropped (SURVEY.md §7.2 "odd spatial shapes")
+    coords = random_coords(2, min(3000, int(np.prod(shape)) // 3), 2, shape)
+    _check_rulebook(cuda_dev, coords, 2, list(shape), 2, 2, 0, 1, False)
+
+
+@pytest.mark.parametrize("ks,st,pd,dl", [(3, 2, 1, 1), (3, 1, 1, 1), (3, 1, 0, 1), ((3, 1, 2), (2, 1, 1), (1, 0, 0), 1),
+                                         (3, 1, 2, 2)])
+def test_rulebook_generic_conv_exact(cuda_dev, ks, st, pd, dl):
+    shape = (21, 18, 16)
+    coords = random_coords(3, 900, 2, shape)
+    _check_rulebook(cuda_dev, coords, 2, list(shape), ks, st, pd, dl, False)
+
+
+def test_rulebook_empty(cuda_dev):
+    from doda_b200 import ops
+    coords = torch.zeros((0, 4), dtype=torch.int32, device=cuda_dev)
+    rb = ops.build_rulebook(coords, 1, [8, 8, 8], 3, 1, 1, 1, subm=True)
+    assert rb.pairs.shape == (2, 27, 0) and int(rb.pairnum.sum()) == 0
+
+
+def _conv_case(cuda_dev, kind, Cin, Cout, seed=0, n=1500, shape=(24, 22, 20)):
+    from doda_b200 import ops
+    from oracle.conv import indice_conv_ref, indice_conv_backward_ref
+    torch.manual_seed(seed)
+    coords = random_coords(seed, n, 2, shape)
+    dev_coords = torch.from_numpy(coords).to(cuda_dev)
+    if kind == "subm":
+        rb = ops.build_rulebook(dev_coords, 2, list(shape), 3, 1, 1, 1, subm=True)
+        outids, pairs, pairnum, _ = _rb_oracle(coords, 2, list(shape), 3, 1, 1, 1, True)
+        kshape, fn, n_in, n_out, inv, subm = (3, 3, 3), ops.SubMConvFunction, coords.shape[0], coords.shape[0], False, True
+    else:
+        rb = ops.build_rulebook(dev_coords, 2, list(shape), 2, 2, 0, 1, subm=False)
+        outids, pairs, pairnum, _ = _rb_oracle(coords, 2, list(shape), 2, 2, 0, 1, False)
+        kshape = (2, 2, 2)
+        if kind == "down":
+            fn, n_in, n_out, inv, subm = ops.SparseConvFunction, coords.shape[0], outids.shape[0], False, False
+        else:
+            fn, n_in, n_out, inv, subm = ops.SparseInverseConvFunction, outids.shape[0], coords.shape[0], True, False
+    feats = torch.randn(n_in, Cin)
+    W = torch.randn(*kshape, Cin, Cout) * 0.2
+    gout = torch.randn(n_out, Cout)
+    ref = indice_conv_ref(feats.double(), W.double(), pairs, pairnum, n_out, inverse=inv, subm=subm)
+    din_ref, dW_ref = indice_conv_backward_ref(feats.double(), W.double(), gout.double(), pairs, pairnum, inv, subm)
+    f = feats.to(cuda_dev).requires_grad_(True)
+    w = W.to(cuda_dev).requires_grad_(True)
+    out = fn.apply(f, w, rb)
+    out.backward(gout.to(cuda_dev))
+    assert rel_err(out, ref) <= TOL, ("fwd", rel_err(out, ref))
+    assert rel_err(f.grad, din_ref) <= TOL, ("dgrad", rel_err(f.grad, din_ref))
+    assert rel_err(w.grad, dW_ref) <= TOL, ("wgrad", rel_err(w.grad, dW_ref))
+    # raw spconv-style entry points on the same rulebook
+    out2 = ops.indice_conv(f.detach(), w.detach(), rb.pairs, rb.pairnum, n_out, inverse=inv, subm=subm)
+    din2, dW2 = ops.indice_conv_backward(f.detach(), w.detach(), gout.to(cuda_dev), rb.pairs, rb.pairnum, inv, subm)
+    assert rel_err(out2, ref) <= TOL and rel_err(din2, din_ref) <= TOL and rel_err(dW2, dW_ref) <= TOL
+
+
+@pytest.mark.parametrize("Cin,Cout", [(16, 16), (3, 16), (32, 16), (32, 32), (48, 48), (64, 32), (112, 112), (5, 7),
+                                      (96, 48)])
+def test_subm_conv_fwd_bwd(cuda_dev, Cin, Cout):
+    _conv_case(cuda_dev, "subm", Cin, Cout)
+
+
+@pytest.mark.parametrize("Cin,Cout", [(16, 32), (32, 48), (96, 112), (6, 10)])
+def test_down_conv_fwd_bwd(cuda_dev, Cin, Cout):
+    _conv_case(cuda_dev, "down", Cin, Cout, shape=(25, 22, 21))
+
+
+@pytest.mark.parametrize("Cin,Cout", [(32, 16), (48, 32), (112, 96), (10, 6)])
+def test_inverse_conv_fwd_bwd(cuda_dev, Cin, Cout):
+    _conv_case(cuda_dev, "inverse", Cin, Cout, shape=(25, 22, 21))
+
+
+def test_subm_conv_large_tiles(cuda_dev):
+    # enough rows to take the 128-row tile path (>= 128*148 rows)
+    _conv_case(cuda_dev, "subm", 16, 16, n=12000, shape=(64, 64, 32))
+    _conv_case(cuda_dev, "subm", 32, 32, n=12000, shape=(64, 64, 32))
+    _conv_case(cuda_dev, "subm", 64, 64, n=12000, shape=(64, 64, 32))
+
+
+def test_conv1x1_fwd_bwd(cuda_dev):
+    from doda_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(3001, 64)
+    W = torch.randn(1, 1, 1, 64, 32) * 0.2
+    g = torch.randn(3001, 32)
+    xd, wd = x.to(cuda_dev).requires_grad_(True), W.to(cuda_dev).requires_grad_(True)
+    y = ops.DenseConvFunction.apply(xd, wd)
+    y.backward(g.to(cuda_dev))
+    W2 = W.view(64, 32).double()
+    assert rel_err(y, x.double() @ W2) <= TOL
+    assert rel_err(xd.grad, g.double() @ W2.t()) <= TOL
+    assert rel_err(wd.grad.view(64, 32), x.double().t() @ g.double()) <= TOL
+
+
+@pytest.mark.parametrize("M,C", [(5000, 16), (777, 48), (20000, 32), (64, 112), (3, 224), (1000, 10)])
+@pytest.mark.parametrize("relu", [True, False])
+def test_bn_relu_fwd_bwd(cuda_dev, M, C, relu):
+    from doda_b200 import ops
+    torch.manual_seed(M + C)
+    x = torch.randn(M, C) * 2 + 0.5
+    g = torch.randn(M, C)
+    bn_ref = torch.nn.BatchNorm1d(C, eps=1e-4, momentum=0.1).double()
+    with torch.no_grad():
+        bn_ref.weight.uniform_(0.5, 1.5)
+        bn_ref.bias.uniform_(-0.5, 0.5)
+    bn = torch.nn.BatchNorm1d(C, eps=1e-4, momentum=0.1).to(cuda_dev)
+    bn.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in bn_ref.state_dict().items()})
+    xr = x.double().requires_grad_(True)
+    yr = bn_ref(xr)
+    yr = torch.relu(yr) if relu else yr
+    yr.backward(g.double())
+    xd = x.to(cuda_dev).requires_grad_(True)
+    y = ops.batch_norm_relu(xd, bn, relu=relu)
+    y.backward(g.to(cuda_dev))
+    assert rel_err(y, yr) <= TOL
+    assert rel_err(xd.grad, xr.grad) <= 2e-4
+    assert rel_err(bn.weight.grad, bn_ref.weight.grad) <= TOL
+    assert rel_err(bn.bias.grad, bn_ref.bias.grad) <= TOL
+    assert rel_err(bn.running_mean, bn_ref.running_mean) <= TOL
+    assert rel_err(bn.running_var, bn_ref.running_var) <= TOL
+    assert int(bn.num_batches_tracked) == 1
+    # eval mode uses the running statistics
+    bn.eval(); bn_ref.eval()
+    with torch.no_grad():
+        ye = ops.batch_norm_relu(x.to(cuda_dev), bn, relu=relu)
+        yer = bn_ref(x.double())
+        yer = torch.relu(yer) if relu else yer
+    assert rel_err(ye, yer) <= TOL
+
+
+def test_voxelize_and_devoxelize(cuda_dev):
+    from doda_b200 import pointgroup_ops, ops
+    from oracle.unet_ref import voxelize_mean_ref
+    rng = np.random.RandomState(0)
+    pts = rng.randint(0, 12, size=(4000, 3))
+    locs = torch.from_numpy(np.concatenate([rng.randint(0, 2, size=(4000, 1)), pts], 1)).long().contiguous()
+    vl, p2v, v2p = pointgroup_ops.voxelization_idx(locs, 2, 4)
+    feats = torch.randn(4000, 3)
+    ref = voxelize_mean_ref(feats.double(), v2p.numpy())
+    fd = feats.to(cuda_dev).requires_grad_(True)
+    out = pointgroup_ops.voxelization(fd, v2p.to(cuda_dev), 4)
+    assert rel_err(out, ref) <= 1e-6
+    g = torch.randn_like(out)
+    out.backward(g)
+    fr = feats.double().requires_grad_(True)
+    voxelize_mean_ref(fr, v2p.numpy()).backward(g.double().cpu())
+    assert rel_err(fd.grad, fr.grad) <= 1e-6
+    # devoxelize gather + scatter-add backward (model/unet.py:62)
+    for C, dt in ((16, torch.int32), (16, torch.int64), (5, torch.int32)):
+        src = torch.randn(vl.shape[0], C, device=cuda_dev, requires_grad=True)
+        idx = p2v.to(cuda_dev).to(dt)
+        y = ops.gather_rows(src, idx)
+        assert torch.equal(y, src[idx.long()])
+        gy = torch.randn_like(y)
+        y.backward(gy)
+        ref_g = torch.zeros_like(src).index_add_(0, idx.long(), gy)
+        assert rel_err(src.grad, ref_g) <= 1e-5
+
+
+def _unet_parity(cuda_dev, target, mid, tol_scores, tol_grad):
+    from doda_b200 import scenes
+    from doda_b200.unet import SparseConvNet, model_step
+    from oracle.unet_ref import model_step_ref
+    torch.manual_seed(0)
+    batch = scenes.collate([scenes.scene_with_voxels(0, target), scenes.scene_with_voxels(1, target)], dup_max=2)
+    model = SparseConvNet(mid_channel=mid)
+    sd64 = {k: (v.detach().double().clone().requires_grad_(True) if v.is_floating_point() else v.clone())
+            for k, v in model.state_dict().items()}
+    b64 = dict(batch)
+    b64["feats"] = batch["feats"].double()
+    loss_ref, scores_ref = model_step_ref(sd64, b64, training=True)
+    loss_ref.backward()
+    model = model.to(cuda_dev).train()
+    loss, scores = model_step(model, batch, device=cuda_dev)
+    loss.backward()
+    assert rel_err(scores, scores_ref) <= tol_scores, ("scores", rel_err(scores, scores_ref))
+    assert abs(float(loss) - float(loss_ref)) <= tol_scores * max(1.0, abs(float(loss_ref)))
+    worst = 0.0
+    for name, p in model.named_parameters():
+        worst = max(worst, rel_err(p.grad, sd64[name].grad))
+    assert worst <= tol_grad, ("worst grad rel err", worst)
+
+
+def test_unet_fwd_bwd_small_scene(cuda_dev):
+    # whole-net check: 71 convs + 65 BN deep, so the per-op 1e-4 bound compounds; 1e-3 on logits / grads
+    _unet_parity(cuda_dev, 3000, 16, 1e-3, 5e-3)
+
+
+def test_unet_fwd_bwd_m32(cuda_dev):
+    _unet_parity(cuda_dev, 2000, 32, 1e-3, 5e-3)
+
+
+def test_spconv_surface_sequential_semantics(cuda_dev):
+    """SparseSequential mutates .features of the SAME object for dense modules."""
+    from doda_b200 import spconv
+    coords = torch.from_numpy(random_coords(0, 500, 1, (16, 16, 16))).to(cuda_dev)
+    x = spconv.SparseConvTensor(torch.randn(500, 8, device=cuda_dev), coords, [16, 16, 16], 1)
+    keep = x.features
+    seq = spconv.SparseSequential(torch.nn.BatchNorm1d(8, eps=1e-4, momentum=0.1), torch.nn.ReLU()).to(cuda_dev)
+    y = seq(x)
+    assert y is x and x.features is not keep and float(x.features.min()) >= 0.0
+    conv = spconv.SparseSequential(spconv.SubMConv3d(8, 4, 3, padding=1, bias=True, indice_key="k")).to(cuda_dev)
+    z = conv(x)
+    assert z is not x and z.indice_dict is x.indice_dict and "k" in x.indice_dict
+    assert z.features.shape == (500, 4)
+    d = z.dense()
+    assert d.shape == (1, 4, 16, 16, 16)
