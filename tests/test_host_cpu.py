@@ -1,0 +1,134 @@
+"""CPU: host-side logic of the drop-in surface -- module / parameter layout identical to the reference model
+(golden generated from /root/reference/model/unet.py), SparseSequential semantics, scene generator, and the
+world_size-2 data-parallel plumbing over gloo."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("m", [16, 32])
+def test_state_dict_layout_matches_reference_model(m):
+    from doda_b200.unet import SparseConvNet
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "unet_state_dict.json")))["m%d" % m]
+    sd = {k: list(v.shape) for k, v in SparseConvNet(mid_channel=m).state_dict().items()}
+    assert sd == gold
+    n_params = sum(int(np.prod(s)) for k, s in sd.items() if "running" not in k and "num_batches" not in k)
+    assert n_params == {16: 7531019, 32: 30104075}[m]
+
+
+def test_layer_census():
+    from doda_b200 import spconv
+    from doda_b200.unet import SparseConvNet
+    net = SparseConvNet(mid_channel=16)
+    convs = [mod for mod in net.modules() if isinstance(mod, spconv.SparseConvolution)]
+    k3 = [c for c in convs if c.subm and c.kernel_size == [3, 3, 3]]
+    k1 = [c for c in convs if c.subm and c.kernel_size == [1, 1, 1]]
+    down = [c for c in convs if not c.subm and not c.inverse]
+    inv = [c for c in convs if c.inverse]
+    assert (len(convs), len(k3), len(k1), len(down), len(inv)) == (71, 53, 6, 6, 6)
+    assert sum(isinstance(mod, torch.nn.BatchNorm1d) for mod in net.modules()) == 65
+    assert all(c.bias is None for c in convs)
+    assert net.input_conv[0].weight.shape == (3, 3, 3, 3, 16)
+
+
+def test_sparse_sequential_mutation_semantics_cpu():
+    """A.6: dense modules are applied to .features of the SAME object; OrderedDict / kwargs constructors"""
+    from collections import OrderedDict
+    from doda_b200 import spconv
+    x = spconv.SparseConvTensor(torch.randn(20, 4), torch.zeros(20, 4, dtype=torch.int32), [8, 8, 8], 1)
+    keep = x.features
+    seq = spconv.SparseSequential(OrderedDict([("a", torch.nn.ReLU()), ("b", torch.nn.Linear(4, 3))]))
+    y = seq(x)
+    assert y is x and x.features.shape == (20, 3) and x.features is not keep
+    assert len(seq) == 2 and isinstance(seq[0], torch.nn.ReLU) and isinstance(seq[-1], torch.nn.Linear)
+    seq2 = spconv.SparseSequential(torch.nn.ReLU(), tail=torch.nn.Identity())
+    assert list(dict(seq2.named_children())) == ["0", "tail"]
+    # an empty tensor skips dense modules
+    e = spconv.SparseConvTensor(torch.zeros(0, 4), torch.zeros(0, 4, dtype=torch.int32), [8, 8, 8], 1)
+    assert seq(e).features.shape == (0, 4)
+    d = spconv.SparseConvTensor(torch.ones(2, 3), torch.tensor([[0, 1, 2, 3], [1, 0, 0, 0]], dtype=torch.int32),
+                                [2, 3, 4], 2).dense()
+    assert d.shape == (2, 3, 2, 3, 4) and float(d.sum()) == 6.0 and float(d[0, :, 1, 2, 3].sum()) == 3.0
+
+
+def test_compat_modules_alias_the_engine():
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "import spconv, PG_OP, pointops2_cuda;"
+            "from spconv.modules import SparseModule;"
+            "import doda_b200.spconv as s;"
+            "assert spconv.SubMConv3d is s.SubMConv3d and SparseModule is s.SparseModule;"
+            "assert all(hasattr(PG_OP, n) for n in ['voxelize_idx','voxelize_fp','voxelize_bp','point_recover_fp',"
+            "'point_recover_bp','ballquery_batch_p','bfs_cluster','roipool_fp','roipool_bp','get_iou','sec_mean',"
+            "'sec_mean_bp','sec_min','sec_max','knn_batch']);"
+            "assert all(hasattr(pointops2_cuda, n) for n in ['knnquery_cuda','furthestsampling_cuda',"
+            "'furthestsampling_dim_cuda','grouping_forward_cuda','grouping_backward_cuda','interpolation_forward_cuda',"
+            "'interpolation_backward_cuda','subtraction_forward_cuda','subtraction_backward_cuda',"
+            "'aggregation_forward_cuda','aggregation_backward_cuda']); print('ok')"
+            % (os.path.join(ROOT, "compat"), ROOT))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr
+
+
+def test_scene_generator_is_seeded_and_sized():
+    from doda_b200 import scenes
+    a, b = scenes.scene_with_voxels(3, 5000), scenes.scene_with_voxels(3, 5000)
+    assert a.shape == (5000, 3) and np.array_equal(a, b)
+    assert len({tuple(r) for r in a.tolist()}) == 5000
+    assert not np.array_equal(a, scenes.scene_with_voxels(4, 5000))
+    batch = scenes.collate([a, scenes.scene_with_voxels(4, 4000)], dup_max=2)
+    assert batch["voxel_locs"].shape == (9000, 4) and batch["voxel_locs"].dtype == torch.int64
+    assert batch["p2v_map"].dtype == torch.int32 and batch["v2p_map"].dtype == torch.int32
+    assert int(batch["v2p_map"][:, 0].sum()) == batch["feats"].shape[0] == int(batch["offsets"][-1])
+    assert (np.asarray(batch["spatial_shape"]) >= 128).all()
+    u = scenes.uniform_scene(0, 1000, 0.02)
+    assert u.shape == (1000, 3) and len({tuple(r) for r in u.tolist()}) == 1000
+
+
+_DDP_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from doda_b200 import parallel
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+# scene sharding: disjoint, seeded, whole scenes per rank
+ids = parallel.scene_ids(rank, world, scenes_per_rank=2)
+allids = [None] * world
+dist.all_gather_object(allids, ids)
+flat = [i for l in allids for i in l]
+assert len(set(flat)) == len(flat) == 2 * world
+# flat-buffer gradient averaging == per-tensor all-reduce mean
+torch.manual_seed(rank)
+params = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(2, 2))]
+for p in params:
+    p.grad = torch.randn_like(p)
+params[2].grad = None  # a parameter that received no gradient
+ref = []
+for p in params[:2]:
+    g = p.grad.clone(); dist.all_reduce(g); ref.append(g / world)
+parallel.allreduce_grads(params, world)
+assert all(torch.allclose(p.grad, r, atol=1e-6) for p, r in zip(params[:2], ref))
+assert params[2].grad is None
+# max-over-ranks timing reduction
+t = parallel.max_over_ranks(float(rank + 1), torch.device("cpu"))
+assert t == float(world)
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_data_parallel_plumbing_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_DDP_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0 and "ok" in o, e
