@@ -10,6 +10,8 @@
 //   * dgrad is the same kernel on the mirrored/transposed weights; wgrad walks the canonical pair lists.
 #include "common.cuh"
 #include <algorithm>
+#include <stdlib.h>
+#include <string.h>
 
 namespace b200sp {
 
@@ -31,6 +33,7 @@ struct GGParams {
     const float* in;
     const float* W;       // [K][Cin][Cout]
     const int* tab;       // TAB mode: [n_rows][K] input rows (or NULL with K==1: identity)
+    const int* orow;      // TAB mode: output row of table row r (NULL: identity)
     const int* pin;       // PAIRS mode: [K][pstride] input rows
     const int* pout;      // PAIRS mode: [K][pstride] output rows
     const int* pairnum;   // PAIRS mode: device [K]
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__((BM / TM) * (BN / TN)) k_gather_gemm(GGParams 
             for (int r = tid; r < BM; r += NT) sm.idx[r] = r < rows ? (int)(row0 + r) : -1;
             if (tid == 0) sm.kflag[0] = 1;
         }
-        for (int r = tid; r < BM; r += NT) sm.orow[r] = r < rows ? (int)(row0 + r) : -1;
+        for (int r = tid; r < BM; r += NT) sm.orow[r] = r < rows ? (p.orow ? p.orow[row0 + r] : (int)(row0 + r)) : -1;
         __syncthreads();
         if (tid == 0) {
             int nk = 0;
@@ -398,31 +401,106 @@ __global__ void k_weight_transpose(const float* __restrict__ W, int K, int Ci, i
 
 using namespace b200sp;
 
-extern "C" int b200sp_gather_gemm(const float* in, int64_t n_in, int Cin, const float* W, const int32_t* tab, int K,
-                                  float* out, int64_t n_out, int Cout, int accumulate, void* stream) {
+namespace b200sp {
+int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, int wflags, const int* tab, const int* orow,
+                const int* pin,
+                const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out, int Cout,
+                int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st);
+int64_t conv_tc_ws_bytes(int K, int Cin, int Cout);
+
+// 0 = tensor-core path (tcgen05 3xTF32) whenever the shape is covered, 1 = fp32 CUDA-core kernel only
+static int g_conv_impl = -1;
+static int conv_impl() {
+    if (g_conv_impl < 0) {
+        const char* e = getenv("B200SP_CONV_IMPL");
+        g_conv_impl = (e && strcmp(e, "fp32") == 0) ? 1 : 0;
+    }
+    return g_conv_impl;
+}
+
+// fp32 kernel wants W as [K][Cin][Cout]; wflags bit0 = W is stored [K][Cout][Cin], bit1 = mirrored offsets
+static int fp32_weights(const float* W, int K, int Cin, int Cout, int wflags, void* ws, int64_t ws_bytes,
+                        cudaStream_t st, const float** Wuse) {
+    if (wflags == 0) {
+        *Wuse = W;
+        return B200SP_OK;
+    }
+    const int64_t need = (int64_t)K * Cin * Cout * 4;
+    if (!ws || ws_bytes < need) {
+        set_error("gather_gemm: workspace too small for the transposed weights (%lld < %lld)", (long long)ws_bytes,
+                  (long long)need);
+        return B200SP_ENOMEM;
+    }
+    B200SP_CHECK_ARG(wflags & 1, "gather_gemm: mirror without transpose is not used");
+    int64_t n = need / 4;
+    // stored [K][Cout][Cin] (Ci_w = Cout, Co_w = Cin) -> [K][Cin][Cout]
+    k_weight_transpose<<<(unsigned)std::min<int64_t>(cdiv(n, 256), 2048), 256, 0, st>>>(W, K, Cout, Cin, (wflags >> 1) & 1,
+                                                                                      static_cast<float*>(ws));
+    B200SP_LAUNCH_CHECK();
+    *Wuse = static_cast<const float*>(ws);
+    return B200SP_OK;
+}
+}  // namespace b200sp
+
+extern "C" int b200sp_set_conv_impl(int impl) {
+    B200SP_CHECK_ARG(impl == 0 || impl == 1, "set_conv_impl: 0 = tensor cores, 1 = fp32 CUDA cores");
+    b200sp::g_conv_impl = impl;
+    return B200SP_OK;
+}
+
+extern "C" int64_t b200sp_conv_ws_bytes(int K, int Cin, int Cout) {
+    int64_t a = b200sp::conv_tc_ws_bytes(K, Cin, Cout);
+    int64_t b = (int64_t)K * Cin * Cout * 4;
+    return align_up(a > b ? a : b, 256);
+}
+
+extern "C" int b200sp_gather_gemm(const float* in, int64_t n_in, int Cin, const float* W, int wflags, const int32_t* tab,
+                                  const int32_t* orow, int K, float* out, int64_t n_out, int Cout, int accumulate,
+                                  void* ws, int64_t ws_bytes, void* stream) {
     (void)n_in;
     B200SP_CHECK_ARG(Cin >= 1 && Cout >= 1 && K >= 1, "gather_gemm: bad Cin/Cout/K");
     B200SP_CHECK_ARG(K <= GG_MAXK, "gather_gemm: K=%d > %d not supported by this build", K, GG_MAXK);
     B200SP_CHECK_ARG(tab || K == 1, "gather_gemm: tab==NULL requires K==1");
     if (n_out == 0) return B200SP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (conv_impl() == 0) {
+        const int Ci_w = (wflags & 1) ? Cout : Cin, Co_w = (wflags & 1) ? Cin : Cout;
+        int rc = conv_tc_run(in, Cin, W, Ci_w, Co_w, wflags, tab, orow, nullptr, nullptr, nullptr, n_out, 0, K, out, Cout,
+                             accumulate, 0, ws, ws_bytes, st);
+        if (rc != B200SP_EUNSUP) return rc;
+    }
+    const float* Wuse = nullptr;
+    int rc = fp32_weights(W, K, Cin, Cout, wflags, ws, ws_bytes, st, &Wuse);
+    if (rc) return rc;
     GGParams p{};
-    p.in = in; p.W = W; p.tab = tab; p.out = out;
+    p.in = in; p.W = Wuse; p.tab = tab; p.orow = orow; p.out = out;
     p.n_rows = n_out; p.Cin = Cin; p.Cout = Cout; p.K = K;
     p.accumulate = accumulate; p.pairs_mode = 0;
-    return dispatch_gg(p, n_out, 1, (cudaStream_t)stream);
+    return dispatch_gg(p, n_out, 1, st);
 }
 
-extern "C" int b200sp_gather_gemm_pairs(const float* in, int Cin, const float* W, const int32_t* pin,
+extern "C" int b200sp_gather_gemm_pairs(const float* in, int Cin, const float* W, int wflags, const int32_t* pin,
                                         const int32_t* pout, const int32_t* pairnum_dev, int64_t n_upper, int K,
-                                        int64_t pstride, float* out, int Cout, int accumulate, void* stream) {
+                                        int64_t pstride, float* out, int Cout, int accumulate, void* ws,
+                                        int64_t ws_bytes, void* stream) {
     B200SP_CHECK_ARG(Cin >= 1 && Cout >= 1 && K >= 1 && K <= GG_MAXK, "gather_gemm_pairs: bad Cin/Cout/K");
     B200SP_CHECK_ARG(pin && pout && pairnum_dev, "gather_gemm_pairs: null pair lists");
     if (n_upper <= 0) return B200SP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (conv_impl() == 0) {
+        const int Ci_w = (wflags & 1) ? Cout : Cin, Co_w = (wflags & 1) ? Cin : Cout;
+        int rc = conv_tc_run(in, Cin, W, Ci_w, Co_w, wflags, nullptr, nullptr, pin, pout, pairnum_dev, n_upper, pstride, K,
+                             out, Cout, accumulate, 1, ws, ws_bytes, st);
+        if (rc != B200SP_EUNSUP) return rc;
+    }
+    const float* Wuse = nullptr;
+    int rc = fp32_weights(W, K, Cin, Cout, wflags, ws, ws_bytes, st, &Wuse);
+    if (rc) return rc;
     GGParams p{};
-    p.in = in; p.W = W; p.pin = pin; p.pout = pout; p.pairnum = pairnum_dev; p.out = out;
+    p.in = in; p.W = Wuse; p.pin = pin; p.pout = pout; p.pairnum = pairnum_dev; p.out = out;
     p.pstride = pstride; p.Cin = Cin; p.Cout = Cout; p.K = K;
     p.accumulate = accumulate; p.pairs_mode = 1;
-    return dispatch_gg(p, n_upper, K, (cudaStream_t)stream);
+    return dispatch_gg(p, n_upper, K, st);
 }
 
 extern "C" int b200sp_wgrad(const float* a, int Ca, const float* b, int Cb, const int32_t* pa, const int32_t* pb,

@@ -1,0 +1,479 @@
+// conv_tc.cu — sparse convolution forward / dgrad on the Blackwell tensor cores (tcgen05 + TMEM), fp32-accurate.
+//
+// Replaces spconv v1.2 `indice_conv` / the dgrad half of `indice_conv_backward` (per offset: gather kernel ->
+// cuBLAS SGEMM -> scatter-add).  One launch per conv, output-stationary:
+//
+//   out[r, :] = sum_k  in[tab[r,k], :] @ W[k]                 r in a 128-row tile owned by one CTA
+//
+//   * warps 8-11 (loaders, one thread per row): gather the neighbour rows of the tile for one (offset, channel-chunk)
+//     stage with 16-byte cp.async (zero-fill for missing neighbours) straight into shared memory in the un-swizzled
+//     canonical K-major UMMA layout (core matrix = 8 rows x 16 B); no registers, completion lands on an mbarrier,
+//     so up to `nslots` stages of gathers stay in flight per CTA;
+//   * warps 0-7 (transform): read the landed fp32 values back, write lo = v - tf32(v) into the twin tile (the tensor
+//     core itself uses tf32(v) = the top 19 bits of the raw copy as the high part);
+//   * warp 13: streams the matching pre-split weight block (prepared once per call by k_prep_weights, already in the
+//     canonical layout) with one cp.async.bulk per stage;
+//   * warp 12, one thread: issues tcgen05.mma kind::tf32 M=128 x N=Cout x K=8 — three products per K step
+//     (hi*hi + lo*hi + hi*lo, i.e. 3xTF32: fp32-level accuracy, |err| ~ 2^-21) accumulating in TMEM over ALL offsets
+//     and chunks, and releases each smem slot with tcgen05.commit;
+//   * epilogue (warps 0-7): tcgen05.ld the 128 x Cout accumulator and write every output row exactly once
+//     (no scatter atomics, no [P, C] gather/scatter buffers in HBM).
+//
+// dgrad is the same kernel on the transposed (SubM: mirrored) weights; the non-overlapping k2/s2 inverse conv and
+// strided dgrad use the pair-grouped mode (one offset per CTA, rows scattered through the pair list).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include <algorithm>
+#include <stdlib.h>
+#include <string.h>
+
+namespace b200sp {
+
+using namespace tc;
+
+constexpr int TC_BM = 128;
+constexpr int TC_MAXK = 32;
+constexpr int TC_XFORM = 256;   // warps 0-7 : transform (lo = v - tf32(v)) + epilogue
+constexpr int TC_LOADERS = 128; // warps 8-11: cp.async row gather straight into the canonical A layout
+constexpr int TC_WARP_MMA = 12;
+constexpr int TC_WARP_W = 13;
+constexpr int TC_THREADS = TC_XFORM + TC_LOADERS + 64;
+
+struct TCParams {
+    const float* in;
+    const float* Wp;     // prepared weights: [K][nchunks]{hi block, lo block}, block = canonical [KC/4][Cout_pad/8][8][4] fp32
+    const int* tab;      // [n_rows][K] or NULL (identity, K == 1)
+    const int* orow;     // output row of table row r (NULL: identity)
+    const int* pin;      // pairs mode: [K][pstride]
+    const int* pout;
+    const int* pairnum;  // device [K]
+    float* out;
+    int64_t n_rows;
+    int64_t pstride;
+    int Cin, Cout, K;
+    int nchunks, Cout_pad;
+    int accumulate, pairs_mode;
+    int nslots;
+    uint32_t stageB_bytes;  // 2 * Cout_pad * KC * 4
+    uint32_t tmem_cols;
+};
+
+template <int KC>
+struct TCLayout {
+    // K-adjacent core matrices of A are LBO bytes apart.  The pad (128/CPR bytes) staggers the banks so that the
+    // loaders' quarter-warps (8/CPR rows x CPR chunks of 16 B) write 128 distinct bytes' worth of banks.
+    static constexpr uint32_t CPR = KC / 4;                       // 16-byte chunks per row per stage
+    static constexpr uint32_t LBO = TC_BM * 16u + 128u / CPR;
+    static constexpr uint32_t A_BYTES = (CPR * LBO + 127u) & ~127u;  // one of {hi, lo}
+    __host__ __device__ static uint32_t offB(int nslots) { return (uint32_t)nslots * 2u * A_BYTES; }
+    __host__ __device__ static uint32_t offIdx(int nslots, uint32_t stageB) { return offB(nslots) + (uint32_t)nslots * stageB; }
+    __host__ __device__ static uint32_t offBars(int nslots, uint32_t stageB, int KT) {
+        uint32_t o = offIdx(nslots, stageB) + (uint32_t)(TC_BM * KT + TC_BM + 2 * TC_MAXK + 4) * 4u;
+        return (o + 15u) & ~15u;
+    }
+    __host__ __device__ static uint32_t total(int nslots, uint32_t stageB, int KT) {
+        return offBars(nslots, stageB, KT) + (uint32_t)(3 * nslots + 1) * 8u + 16u;
+    }
+};
+
+__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4_zfill(uint32_t smem_dst, const void* gsrc, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+// arrive on the mbarrier once every cp.async issued so far by this thread has landed (does not bump the pending count)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int KC>
+__global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
+    using L = TCLayout<KC>;
+    constexpr int NV = KC / 8;  // 16-byte chunks per transform thread per stage (two threads per row)
+    extern __shared__ __align__(128) unsigned char smem[];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = p.nslots;
+    const int K = p.K;
+    const int KT = p.pairs_mode ? 1 : K;
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + L::offB(S);
+    int* s_idx = reinterpret_cast<int*>(smem + L::offIdx(S, p.stageB_bytes));
+    int* s_orow = s_idx + TC_BM * KT;
+    int* s_klist = s_orow + TC_BM;
+    int* s_kflag = s_klist + TC_MAXK;
+    int* s_nk = s_kflag + TC_MAXK;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::offBars(S, p.stageB_bytes, KT));  // hi+lo+weights ready -> MMA
+    uint64_t* empty = full + S;                                                            // MMA done -> slot reusable
+    uint64_t* raw = empty + S;                                                             // gathered rows landed -> transform
+    uint64_t* accum = raw + S;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(accum + 1);
+
+    const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
+    int rows;
+    int kfixed = 0;
+    if (p.pairs_mode) {
+        kfixed = blockIdx.z;
+        const int n = p.pairnum[kfixed];
+        if (row0 >= n) return;  // whole CTA leaves before touching barriers / TMEM
+        rows = (int)min((int64_t)TC_BM, (int64_t)n - row0);
+        for (int r = tid; r < TC_BM; r += TC_THREADS) {
+            const bool ok = r < rows;
+            s_idx[r] = ok ? p.pin[(int64_t)kfixed * p.pstride + row0 + r] : -1;
+            s_orow[r] = ok ? p.pout[(int64_t)kfixed * p.pstride + row0 + r] : -1;
+        }
+        if (tid == 0) {
+            *s_nk = 1;
+            s_klist[0] = 0;
+        }
+    } else {
+        rows = (int)min((int64_t)TC_BM, p.n_rows - row0);
+        if (tid < TC_MAXK) s_kflag[tid] = 0;
+        __syncthreads();
+        if (p.tab) {
+            const int* t = p.tab + row0 * K;
+            for (int i = tid; i < TC_BM * K; i += TC_THREADS) {
+                const int v = (i < rows * K) ? __ldg(t + i) : -1;
+                s_idx[i] = v;
+                if (v >= 0) s_kflag[i % K] = 1;
+            }
+        } else {
+            for (int r = tid; r < TC_BM; r += TC_THREADS) s_idx[r] = r < rows ? (int)(row0 + r) : -1;
+            if (tid == 0) s_kflag[0] = 1;
+        }
+        for (int r = tid; r < TC_BM; r += TC_THREADS)
+            s_orow[r] = r < rows ? (p.orow ? __ldg(p.orow + row0 + r) : (int)(row0 + r)) : -1;
+        __syncthreads();
+        if (tid == 0) {
+            int nk = 0;
+            for (int k = 0; k < K; ++k)
+                if (s_kflag[k]) s_klist[nk++] = k;
+            *s_nk = nk;
+        }
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], TC_XFORM / 32 + 1);
+            mbar_init(&empty[s], 1);
+            mbar_init(&raw[s], TC_LOADERS);
+        }
+        mbar_init(accum, 1);
+        mbar_fence_init();
+    }
+    if (warp == TC_WARP_MMA) tmem_alloc(s_tmem, p.tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+
+    const uint32_t tmem = *s_tmem;
+    const int nk = *s_nk;
+    const int nchunks = p.nchunks;
+    const int nit = nk * nchunks;
+    const int Cin = p.Cin, Cout = p.Cout;
+
+    if (warp < TC_XFORM / 32) {
+        // ========== transform: lo = v - tf32(v) next to the raw rows (the tensor core reads tf32(v) from the raw copy) ==========
+        const int row = tid & (TC_BM - 1);
+        const int half = tid >> 7;
+        const uint32_t soff = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
+        int slot = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < nit; ++it) {
+            unsigned char* a_hi = sA + (size_t)slot * 2 * L::A_BYTES;
+            unsigned char* a_lo = a_hi + L::A_BYTES;
+            mbar_wait(&raw[slot], ph);
+#pragma unroll
+            for (int q = 0; q < NV; ++q) {
+                const uint32_t off = (uint32_t)(half * NV + q) * L::LBO + soff;
+                const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
+                float4 h, l;
+                split_tf32(v.x, h.x, l.x);
+                split_tf32(v.y, h.y, l.y);
+                split_tf32(v.z, h.z, l.z);
+                split_tf32(v.w, h.w, l.w);
+                *reinterpret_cast<float4*>(a_lo + off) = l;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[slot]);
+            if (++slot == S) {
+                slot = 0;
+                ph ^= 1u;
+            }
+        }
+
+        // ========== epilogue: TMEM -> registers -> global (each output row written once) ==========
+        const int q4 = warp & 3, hcol = warp >> 2;
+        const int orow = s_orow[q4 * 32 + lane];
+        const bool vecO = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+        if (nit > 0) {
+            mbar_wait(accum, 0);
+            tc_fence_after();
+        }
+        for (int ch = hcol; ch * 16 < p.Cout_pad; ch += 2) {
+            float v[16];
+            if (nit > 0) {
+                tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * 16), v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.f;
+            }
+            if (orow < 0) continue;
+            float* o = p.out + (int64_t)orow * Cout + ch * 16;
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) {
+                const int col = ch * 16 + g4 * 4;
+                if (col >= Cout) break;
+                if (vecO) {
+                    float4 w = make_float4(v[g4 * 4 + 0], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
+                    if (p.accumulate) {
+                        const float4 old = *reinterpret_cast<const float4*>(o + g4 * 4);
+                        w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+                    }
+                    *reinterpret_cast<float4*>(o + g4 * 4) = w;
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (col + e < Cout) {
+                            float w = v[g4 * 4 + e];
+                            if (p.accumulate) w += o[g4 * 4 + e];
+                            o[g4 * 4 + e] = w;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp < (TC_XFORM + TC_LOADERS) / 32) {
+        // ========== loaders: 16-byte cp.async (zero-fill for missing neighbours) straight into the canonical K-major
+        // layout.  Consecutive lanes take consecutive 16-byte chunks of the SAME row, so one warp instruction touches
+        // 32*16/(KC*4) rows = that many cache lines (not 32); completion is signalled on raw[slot] by the copy engine ==========
+        const int lt = tid - TC_XFORM;  // 0..127
+        constexpr int CPR = KC / 4;     // 16-byte chunks per row per stage
+        const bool vec = (Cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0);
+        int slot = 0, kk = 0, c = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < nit; ++it) {
+            const int kcol = p.pairs_mode ? 0 : s_klist[kk];
+            const int c0 = c * KC;
+            const uint32_t dst0 = smem_u32(sA + (size_t)slot * 2 * L::A_BYTES);
+            mbar_wait(&empty[slot], ph ^ 1u);
+            if (vec) {
+                // thread-constant: chunk j and row phase; q only advances the 8-row group
+                const int j = lt % CPR, rowb = lt / CPR;
+                constexpr int RPQ = TC_LOADERS / CPR;  // rows covered per pass (multiple of 8)
+                const bool colok = c0 + 4 * j < Cin;
+                const uint32_t dstb = dst0 + (uint32_t)j * L::LBO + (uint32_t)(rowb >> 3) * 128u + (uint32_t)(rowb & 7) * 16u;
+                const int* ip = s_idx + rowb * KT + kcol;
+#pragma unroll
+                for (int q = 0; q < CPR; ++q) {
+                    const int src = ip[q * RPQ * KT];
+                    const bool ok = (src >= 0) && colok;
+                    const float* g = p.in + ((int64_t)(ok ? src : 0) * Cin + (ok ? c0 + 4 * j : 0));
+                    cp_async16_zfill(dstb + (uint32_t)q * (RPQ / 8) * 128u, g, ok ? 16 : 0);
+                }
+            } else {
+#pragma unroll 4
+                for (int q = 0; q < KC; ++q) {
+                    const int i = q * TC_LOADERS + lt;
+                    const int row = i / KC, e = i % KC;
+                    const int src = s_idx[row * KT + kcol];
+                    const bool ok = (src >= 0) && (c0 + e < Cin);
+                    const float* g = p.in + (int64_t)(ok ? src : 0) * Cin + (ok ? c0 + e : 0);
+                    cp_async4_zfill(dst0 + (uint32_t)(e >> 2) * L::LBO + (uint32_t)(row >> 3) * 128u +
+                                        (uint32_t)(row & 7) * 16u + 4u * (uint32_t)(e & 3),
+                                    g, ok ? 4 : 0);
+                }
+            }
+            cp_async_arrive_noinc(&raw[slot]);
+            if (++c == nchunks) {
+                c = 0;
+                ++kk;
+            }
+            if (++slot == S) {
+                slot = 0;
+                ph ^= 1u;
+            }
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+    } else if (warp == TC_WARP_MMA) {
+        // ========== MMA issuer (one thread) ==========
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(TC_BM, p.Cout_pad, 0, 0);
+            const uint32_t lboA = L::LBO;                      // K-adjacent core matrices of A
+            const uint32_t lboB = (uint32_t)p.Cout_pad * 16u;  // K-adjacent core matrices of B
+            int slot = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < nit; ++it) {
+                mbar_wait(&full[slot], ph);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(sA + (size_t)slot * 2 * L::A_BYTES);
+                const uint32_t a_lo = a_hi + L::A_BYTES;
+                const uint32_t b_hi = smem_u32(sB + (size_t)slot * p.stageB_bytes);
+                const uint32_t b_lo = b_hi + p.stageB_bytes / 2;
+#pragma unroll
+                for (int j = 0; j < KC / 8; ++j) {
+                    const uint64_t dah = make_desc(a_hi + (uint32_t)j * 2u * lboA, lboA, 128u);
+                    const uint64_t dal = make_desc(a_lo + (uint32_t)j * 2u * lboA, lboA, 128u);
+                    const uint64_t dbh = make_desc(b_hi + (uint32_t)j * 2u * lboB, lboB, 128u);
+                    const uint64_t dbl = make_desc(b_lo + (uint32_t)j * 2u * lboB, lboB, 128u);
+                    mma_tf32_ss(tmem, dah, dbh, idesc, (it | j) != 0 ? 1u : 0u);
+                    mma_tf32_ss(tmem, dal, dbh, idesc, 1u);
+                    mma_tf32_ss(tmem, dah, dbl, idesc, 1u);
+                }
+                mma_commit(&empty[slot]);
+                if (++slot == S) {
+                    slot = 0;
+                    ph ^= 1u;
+                }
+            }
+            if (nit > 0) mma_commit(accum);
+        }
+    } else {
+        // ========== weight loader (one thread): one bulk copy per stage ==========
+        if (lane == 0) {
+            int slot = 0, kk = 0, c = 0;
+            uint32_t ph = 0;
+            for (int it = 0; it < nit; ++it) {
+                const int kw = p.pairs_mode ? kfixed : s_klist[kk];
+                mbar_wait(&empty[slot], ph ^ 1u);
+                mbar_arrive_expect_tx(&full[slot], p.stageB_bytes);
+                bulk_g2s(sB + (size_t)slot * p.stageB_bytes,
+                         reinterpret_cast<const unsigned char*>(p.Wp) + ((size_t)kw * nchunks + c) * p.stageB_bytes,
+                         p.stageB_bytes, &full[slot]);
+                if (++c == nchunks) {
+                    c = 0;
+                    ++kk;
+                }
+                if (++slot == S) {
+                    slot = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == TC_WARP_MMA) tmem_dealloc(tmem, p.tmem_cols);
+}
+
+// W [K][Ci_w][Co_w] fp32 -> per (offset, chunk) {hi, lo} blocks in the canonical K-major B layout.
+// transposed == 0: B_k[n][kin] = W[k][kin][n]        (forward: kin over Ci_w, n over Co_w)
+// transposed == 1: B_k[n][kin] = W[k][n][kin]        (dgrad:   kin over Co_w, n over Ci_w)
+// mirror: use W[K-1-k] for block k (SubM dgrad)
+__global__ void k_prep_weights(const float* __restrict__ W, int K, int Ci_w, int Co_w, int transposed, int mirror,
+                               int KC, int nchunks, int Cout_pad, float* __restrict__ Wp) {
+    const int Cin = transposed ? Co_w : Ci_w;
+    const int Cout = transposed ? Ci_w : Co_w;
+    const int64_t per_block = (int64_t)Cout_pad * KC;
+    const int64_t total = (int64_t)K * nchunks * per_block;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        // i enumerates (k, c, kin_local, n) with n fastest so that global reads of W are coalesced for the forward case
+        const int n = (int)(i % Cout_pad);
+        int64_t t = i / Cout_pad;
+        const int kl = (int)(t % KC);
+        t /= KC;
+        const int c = (int)(t % nchunks);
+        const int k = (int)(t / nchunks);
+        const int kin = c * KC + kl;
+        float v = 0.f;
+        if (kin < Cin && n < Cout) {
+            const int ks = mirror ? K - 1 - k : k;
+            v = transposed ? W[((int64_t)ks * Ci_w + n) * Co_w + kin] : W[((int64_t)ks * Ci_w + kin) * Co_w + n];
+        }
+        float hi, lo;
+        tc::split_tf32(v, hi, lo);
+        const int64_t base = ((int64_t)k * nchunks + c) * 2 * per_block;
+        const int64_t off = ((int64_t)(kl >> 2) * (Cout_pad >> 3) + (n >> 3)) * 32 + (n & 7) * 4 + (kl & 3);
+        Wp[base + off] = hi;
+        Wp[base + per_block + off] = lo;
+    }
+}
+
+struct TCPlan {
+    int KC, nchunks, Cout_pad, nslots;
+    uint32_t stageB, tmem_cols, smem;
+    int64_t wp_bytes;
+};
+
+static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
+    if (K < 1 || K > TC_MAXK || Cin < 1 || Cout < 1) return false;
+    const int Cin_pad = (Cin + 7) / 8 * 8;
+    pl.KC = (Cin_pad % 32 == 0) ? 32 : (Cin_pad % 16 == 0) ? 16 : 8;
+    pl.nchunks = Cin_pad / pl.KC;
+    pl.Cout_pad = (Cout + 15) / 16 * 16;
+    if (pl.Cout_pad > 256) return false;
+    pl.stageB = 2u * (uint32_t)pl.Cout_pad * pl.KC * 4u;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)pl.Cout_pad) cols <<= 1;
+    pl.tmem_cols = cols;
+    pl.wp_bytes = (int64_t)K * pl.nchunks * pl.stageB;
+    const uint32_t cpr = (uint32_t)pl.KC / 4u;
+    const uint32_t a_bytes = 2u * ((cpr * (TC_BM * 16u + 128u / cpr) + 127u) & ~127u);
+    // slots: aim for ~4-6 stages in flight, stay under ~100 KB so two CTAs can share an SM when the tile is small
+    int best = 0;
+    for (int s = 6; s >= 2; --s) {
+        uint32_t tot = (uint32_t)s * (a_bytes + pl.stageB) + (uint32_t)(TC_BM * KT + TC_BM + 2 * TC_MAXK + 4) * 4u + 64u +
+                       (uint32_t)(3 * s + 1) * 8u + 32u;
+        if (tot <= 100u * 1024u || (s <= 3 && tot <= 200u * 1024u)) {
+            best = s;
+            break;
+        }
+    }
+    if (best == 0) return false;
+    pl.nslots = best;
+    return true;
+}
+
+template <int KC>
+static int launch_tc(const TCParams& p, int KT, dim3 grid, cudaStream_t st) {
+    using L = TCLayout<KC>;
+    const uint32_t smem = L::total(p.nslots, p.stageB_bytes, KT);
+    static uint32_t attr_smem = 0;
+    if (smem > attr_smem) {
+        B200SP_CUDA(cudaFuncSetAttribute(k_conv_tc<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    k_conv_tc<KC><<<grid, TC_THREADS, smem, st>>>(p);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}
+
+// returns B200SP_EUNSUP when the shape is outside what the tensor path covers (caller falls back to the fp32 kernel)
+int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, int wflags, const int* tab, const int* orow,
+                const int* pin,
+                const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out, int Cout,
+                int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st) {
+    TCPlan pl;
+    const int KT = pairs_mode ? 1 : K;
+    if (!tc_plan(K, Cin, Cout, KT, pl)) return B200SP_EUNSUP;
+    if (!ws || ws_bytes < pl.wp_bytes) {
+        set_error("conv_tc: workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)pl.wp_bytes);
+        return B200SP_ENOMEM;
+    }
+    float* Wp = static_cast<float*>(ws);
+    {
+        const int64_t total = (int64_t)K * pl.nchunks * pl.Cout_pad * pl.KC;
+        const unsigned blocks = (unsigned)std::min<int64_t>(cdiv(total, 256), 4 * 148);
+        k_prep_weights<<<blocks, 256, 0, st>>>(W, K, Ci_w, Co_w, wflags & 1, (wflags >> 1) & 1, pl.KC, pl.nchunks,
+                                               pl.Cout_pad, Wp);
+        B200SP_LAUNCH_CHECK();
+    }
+    TCParams p{};
+    p.in = in; p.Wp = Wp; p.tab = tab; p.orow = orow; p.pin = pin; p.pout = pout; p.pairnum = pairnum; p.out = out;
+    p.n_rows = n_rows; p.pstride = pstride; p.Cin = Cin; p.Cout = Cout; p.K = K;
+    p.nchunks = pl.nchunks; p.Cout_pad = pl.Cout_pad; p.accumulate = accumulate; p.pairs_mode = pairs_mode;
+    p.nslots = pl.nslots; p.stageB_bytes = pl.stageB; p.tmem_cols = pl.tmem_cols;
+    dim3 grid((unsigned)cdiv(n_rows, TC_BM), 1, pairs_mode ? (unsigned)K : 1u);
+    if (pl.KC == 32) return launch_tc<32>(p, KT, grid, st);
+    if (pl.KC == 16) return launch_tc<16>(p, KT, grid, st);
+    return launch_tc<8>(p, KT, grid, st);
+}
+
+int64_t conv_tc_ws_bytes(int K, int Cin, int Cout) {
+    TCPlan pl;
+    if (!tc_plan(K, Cin, Cout, K, pl)) return 0;
+    return pl.wp_bytes;
+}
+
+}  // namespace b200sp

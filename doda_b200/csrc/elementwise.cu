@@ -94,14 +94,21 @@ __global__ void k_bn_finalize_fwd(const float* __restrict__ partial, int G, int6
                                   float* __restrict__ running_mean, float* __restrict__ running_var,
                                   float momentum, long long* __restrict__ num_batches_tracked,
                                   float* __restrict__ scale, float* __restrict__ shift) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
+    // one warp per channel: lanes stride over the G per-block partials, fp64 shuffle reduction
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c == 0 && lane == 0 && num_batches_tracked) *num_batches_tracked += 1;
     if (c >= C) return;
     double s = 0.0, ss = 0.0;
-    for (int g = 0; g < G; ++g) {
+    for (int g = lane; g < G; g += 32) {
         s += partial[((int64_t)g * 2 + 0) * C + c];
         ss += partial[((int64_t)g * 2 + 1) * C + c];
     }
+    for (int o = 16; o; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    if (lane != 0) return;
     double mu = s / (double)M;
     double var = ss / (double)M - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -162,13 +169,19 @@ __global__ void k_bn_finalize_bwd(const float* __restrict__ partial, int G, int6
                                   const float* __restrict__ w, const float* __restrict__ invstd,
                                   float* __restrict__ dw, float* __restrict__ db, float* __restrict__ c_g,
                                   float* __restrict__ c_mean_g, float* __restrict__ c_mean_gx) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (c >= C) return;
     double sg = 0.0, sgx = 0.0;
-    for (int g = 0; g < G; ++g) {
+    for (int g = lane; g < G; g += 32) {
         sg += partial[((int64_t)g * 2 + 0) * C + c];
         sgx += partial[((int64_t)g * 2 + 1) * C + c];
     }
+    for (int o = 16; o; o >>= 1) {
+        sg += __shfl_xor_sync(0xffffffffu, sg, o);
+        sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+    }
+    if (lane != 0) return;
     if (dw) dw[c] = (float)sgx;
     if (db) db[c] = (float)sg;
     float wv = w ? w[c] : 1.f;
@@ -333,7 +346,7 @@ extern "C" int b200sp_bn_fwd_train(const float* x, int64_t M, int C, const float
         k_bn_reduce<4, 0><<<G, BN_THREADS, smem, st>>>(x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, partial);
     else
         k_bn_reduce<1, 0><<<G, BN_THREADS, smem, st>>>(x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, partial);
-    k_bn_finalize_fwd<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(partial, G, M, C, w, b, eps, mean, invstd, running_mean,
+    k_bn_finalize_fwd<<<(unsigned)cdiv(C, 4), 128, 0, st>>>(partial, G, M, C, w, b, eps, mean, invstd, running_mean,
                                                              running_var, momentum,
                                                              (long long*)num_batches_tracked, scale, shift);
     if (v4)
@@ -380,7 +393,7 @@ extern "C" int b200sp_bn_bwd(const float* x, const float* dy, int64_t M, int C, 
         k_bn_reduce<4, 1><<<G, BN_THREADS, smem, st>>>(x, dy, M, C, scale, shift, mean, invstd, relu, partial);
     else
         k_bn_reduce<1, 1><<<G, BN_THREADS, smem, st>>>(x, dy, M, C, scale, shift, mean, invstd, relu, partial);
-    k_bn_finalize_bwd<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(partial, G, M, C, w, invstd, dw, db, c_g, c_mg, c_mgx);
+    k_bn_finalize_bwd<<<(unsigned)cdiv(C, 4), 128, 0, st>>>(partial, G, M, C, w, invstd, dw, db, c_g, c_mg, c_mgx);
     if (v4)
         k_bn_bwd_apply<4><<<stream_grid(M * (C / 4), 256), 256, 0, st>>>(x, dy, M, C, scale, shift, mean, invstd, c_g,
                                                                         c_mg, c_mgx, relu, dx);

@@ -30,6 +30,11 @@ def _f32c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+def set_conv_impl(name):
+    """'tc' (default): tcgen05 3xTF32 tensor-core kernels; 'fp32': CUDA-core kernels only (A/B testing)."""
+    check(lib.b200sp_set_conv_impl({"tc": 0, "fp32": 1}[name]), "set_conv_impl")
+
+
 def launch_count():
     """CUDA kernels launched by libb200sparse in this process (bench.py: gpu_launches)."""
     return int(lib.b200sp_launch_count())
@@ -109,7 +114,8 @@ class Rulebook(object):
     (outids, indices, indice_pairs, indice_pair_num, spatial_shape) and carries the engine's tables."""
 
     __slots__ = ("kind", "outids", "indices", "pairs", "pairnum", "spatial_shape", "out_spatial_shape", "K",
-                 "ksize", "stride", "padding", "dilation", "nbr", "fwd", "bwd", "nonoverlap", "batch_size")
+                 "ksize", "stride", "padding", "dilation", "nbr", "fwd", "bwd", "nonoverlap", "batch_size", "order",
+                 "nbr_perm")
 
     def __iter__(self):
         return iter((self.outids, self.indices, self.pairs, self.pairnum, self.spatial_shape))
@@ -123,6 +129,9 @@ class Rulebook(object):
 
 def conv_out_shape(shape, ksize, stride, padding, dilation):
     return [(s + 2 * p - d * (k - 1) - 1) // st + 1 for s, k, st, p, d in zip(shape, ksize, stride, padding, dilation)]
+
+
+mask_order = True  # SubM convs walk the rows sorted by neighbour bitmask (tiles share one set of present offsets)
 
 
 def build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding=0, dilation=1, subm=False,
@@ -140,7 +149,7 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding=
     rb = Rulebook()
     rb.K, rb.ksize, rb.stride, rb.padding, rb.dilation = K, ks, st, pd, dl
     rb.indices, rb.spatial_shape, rb.batch_size = indices, shape, int(batch_size)
-    rb.nbr = rb.fwd = rb.bwd = None
+    rb.nbr = rb.fwd = rb.bwd = rb.order = rb.nbr_perm = None
     rb.pairs = torch.empty((2, K, M), dtype=_I32, device=dev) if need_pairs else None
     rb.pairnum = torch.empty((K,), dtype=_I32, device=dev) if need_pairs else None
     pp = rb.pairs.data_ptr() if need_pairs else None
@@ -151,11 +160,16 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding=
         rb.outids = indices
         rb.nonoverlap = False
         rb.nbr = torch.empty((M, K), dtype=_I32, device=dev)
+        if mask_order:
+            rb.order = torch.empty((M,), dtype=_I32, device=dev)
+            rb.nbr_perm = torch.empty((M, K), dtype=_I32, device=dev)
         wsb = lib.b200sp_rulebook_ws_bytes(M, K, 1)
         ws = _workspace(wsb, dev, "rb")
         check(lib.b200sp_rulebook_subm(indices.data_ptr(), M, int(batch_size), _carr(shape), _carr(ks), _carr(dl),
-                                       rb.nbr.data_ptr(), pp, pn, ws.data_ptr(), ws.numel(), _stream()),
-              "rulebook_subm")
+                                       rb.nbr.data_ptr(), pp, pn,
+                                       rb.order.data_ptr() if mask_order else None,
+                                       rb.nbr_perm.data_ptr() if mask_order else None,
+                                       ws.data_ptr(), ws.numel(), _stream()), "rulebook_subm")
         return rb
     rb.kind = "conv"
     oshape = conv_out_shape(shape, ks, st, pd, dl)
@@ -206,28 +220,43 @@ def pairs_to_table(pairs, pairnum, n_out, inverse=False):
 # ------------------------------------------------------------------------------------------------
 # conv primitives
 # ------------------------------------------------------------------------------------------------
-def gather_gemm(feat, W3, tab, n_out, out=None, accumulate=False):
-    """out[r] = sum_k feat[tab[r,k]] @ W3[k];  W3 [K,Cin,Cout] contiguous; tab None -> dense GEMM (K==1)."""
-    K, Cin, Cout = W3.shape
+W_FWD, W_T, W_T_MIRROR = 0, 1, 3  # wflags of the C ABI: bit0 = use W[k]^T (dgrad), bit1 = mirrored offsets (SubM dgrad)
+
+
+def _conv_dims(W3, wflags):
+    K, Ci_w, Co_w = W3.shape
+    return (K, Co_w, Ci_w) if (wflags & 1) else (K, Ci_w, Co_w)
+
+
+def gather_gemm(feat, W3, tab, n_out, out=None, accumulate=False, wflags=W_FWD, orow=None):
+    """out[r] = sum_k feat[tab[r,k]] @ Wk;  W3 = the module weight viewed [K,Ci_w,Co_w]; Wk = W3[k] (wflags 0),
+    W3[k]^T (W_T) or W3[K-1-k]^T (W_T_MIRROR); tab None -> dense GEMM (K==1)."""
+    K, Cin, Cout = _conv_dims(W3, wflags)
+    assert feat.shape[1] == Cin
     if out is None:
         out = torch.empty((n_out, Cout), dtype=_F32, device=feat.device)
+    ws = _workspace(lib.b200sp_conv_ws_bytes(K, Cin, Cout), feat.device, "conv")
     with _Timed(kernel="k_gather_gemm", n_in=feat.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K,
                 tab_entries=n_out * K if tab is not None else 0, pairs_dense=n_out * K):
-        check(lib.b200sp_gather_gemm(feat.data_ptr(), feat.shape[0], Cin, W3.data_ptr(),
-                                     tab.data_ptr() if tab is not None else None, K, out.data_ptr(), n_out, Cout,
-                                     1 if accumulate else 0, _stream()), "gather_gemm")
+        check(lib.b200sp_gather_gemm(feat.data_ptr(), feat.shape[0], Cin, W3.data_ptr(), wflags,
+                                     tab.data_ptr() if tab is not None else None,
+                                     orow.data_ptr() if orow is not None else None, K, out.data_ptr(), n_out, Cout,
+                                     1 if accumulate else 0, ws.data_ptr(), ws.numel(), _stream()), "gather_gemm")
     return out
 
 
-def gather_gemm_pairs(feat, W3, pin, pout, pairnum, n_upper, n_out):
-    """out[pout[k][i]] = feat[pin[k][i]] @ W3[k]; rows not covered stay zero."""
-    K, Cin, Cout = W3.shape
+def gather_gemm_pairs(feat, W3, pin, pout, pairnum, n_upper, n_out, wflags=W_FWD):
+    """out[pout[k][i]] = feat[pin[k][i]] @ Wk; rows not covered stay zero."""
+    K, Cin, Cout = _conv_dims(W3, wflags)
+    assert feat.shape[1] == Cin
     out = torch.zeros((n_out, Cout), dtype=_F32, device=feat.device)
+    ws = _workspace(lib.b200sp_conv_ws_bytes(K, Cin, Cout), feat.device, "conv")
     with _Timed(kernel="k_gather_gemm", n_in=feat.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K,
                 tab_entries=2 * n_upper, pairs_dense=n_upper, pairs_mode=1):
-        check(lib.b200sp_gather_gemm_pairs(feat.data_ptr(), Cin, W3.data_ptr(), pin.data_ptr(), pout.data_ptr(),
-                                           pairnum.data_ptr(), n_upper, K, pin.stride(0), out.data_ptr(), Cout, 0,
-                                           _stream()), "gather_gemm_pairs")
+        check(lib.b200sp_gather_gemm_pairs(feat.data_ptr(), Cin, W3.data_ptr(), wflags, pin.data_ptr(),
+                                           pout.data_ptr(), pairnum.data_ptr(), n_upper, K, pin.stride(0),
+                                           out.data_ptr(), Cout, 0, ws.data_ptr(), ws.numel(), _stream()),
+              "gather_gemm_pairs")
     return out
 
 
@@ -268,7 +297,8 @@ class SubMConvFunction(Function):
         W3 = _w3(filters)
         ctx.rb = rb
         ctx.save_for_backward(features, filters)
-        return gather_gemm(features, W3, rb.nbr, features.shape[0])
+        tab, orow = (rb.nbr_perm, rb.order) if rb.nbr_perm is not None else (rb.nbr, None)
+        return gather_gemm(features, W3, tab, features.shape[0], orow=orow)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -279,7 +309,8 @@ class SubMConvFunction(Function):
         M = features.shape[0]
         din = dW = None
         if ctx.needs_input_grad[0]:
-            din = gather_gemm(grad_out, weight_transpose(W3, True), rb.nbr, M)
+            tab, orow = (rb.nbr_perm, rb.order) if rb.nbr_perm is not None else (rb.nbr, None)
+            din = gather_gemm(grad_out, W3, tab, M, wflags=W_T_MIRROR, orow=orow)
         if ctx.needs_input_grad[1]:
             dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K).view(filters.shape)
         return din, dW, None
@@ -303,7 +334,7 @@ class DenseConvFunction(Function):
         M = features.shape[0]
         din = dW = None
         if ctx.needs_input_grad[0]:
-            din = gather_gemm(grad_out, weight_transpose(W3, False), None, M)
+            din = gather_gemm(grad_out, W3, None, M, wflags=W_T)
         if ctx.needs_input_grad[1]:
             dW = wgrad(features, grad_out, None, None, None, M, 1).view(filters.shape)
         return din, dW
@@ -329,11 +360,10 @@ class SparseConvFunction(Function):
         M_in = features.shape[0]
         din = dW = None
         if ctx.needs_input_grad[0]:
-            Wt = weight_transpose(W3, False)
             if rb.nonoverlap:  # every input has at most one (output, offset): pair-grouped, no accumulation
-                din = gather_gemm_pairs(grad_out, Wt, rb.pairs[1], rb.pairs[0], rb.pairnum, M_in, M_in)
+                din = gather_gemm_pairs(grad_out, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, M_in, M_in, wflags=W_T)
             else:
-                din = gather_gemm(grad_out, Wt, rb.fwd, M_in)
+                din = gather_gemm(grad_out, W3, rb.fwd, M_in, wflags=W_T)
         if ctx.needs_input_grad[1]:
             dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M_in, rb.K).view(filters.shape)
         return din, dW, None
@@ -363,7 +393,7 @@ class SparseInverseConvFunction(Function):
         n_fine = rb.indices.shape[0]
         din = dW = None
         if ctx.needs_input_grad[0]:
-            din = gather_gemm(grad_out, weight_transpose(W3, False), rb.bwd, features.shape[0])
+            din = gather_gemm(grad_out, W3, rb.bwd, features.shape[0], wflags=W_T)
         if ctx.needs_input_grad[1]:
             dW = wgrad(features, grad_out, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, rb.K).view(filters.shape)
         return din, dW, None
@@ -386,7 +416,7 @@ def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_nu
     K = W3.shape[0]
     n_in = features.shape[0]
     tab = pairs_to_table(pairs, pairnum, n_in, not inverse)  # in-row -> out-row per offset
-    din = gather_gemm(out_bp, weight_transpose(W3, False), tab, n_in)
+    din = gather_gemm(out_bp, W3, tab, n_in, wflags=W_T)
     a_idx, b_idx = (pairs[1], pairs[0]) if inverse else (pairs[0], pairs[1])
     dW = wgrad(features, out_bp, a_idx, b_idx, pairnum, pairs.shape[2], K).view(filters.shape)
     return din, dW

@@ -40,6 +40,10 @@ int64_t b200sp_launch_count(void);
  *
  * Tables produced (all int32, -1 = none):
  *   nbr  [M, K]           SubM: nbr[q,k] = input row at site(q) + (k - centre)   (out -> in view)
+ *   order [M]             SubM: the engine's processing order = rows stably sorted by their neighbour bitmask
+ *                         (bit k set <=> nbr[q,k] >= 0);
+ *   nbr_perm [M, K]       nbr_perm[i,k] = nbr[order[i],k].  The 128 rows of a tile then share (nearly) one set of
+ *                         present offsets: absent offsets drop out per tile and most gathered rows are real
  *   fwd  [M_in, K]        strided conv: fwd[j,k] = output row reached by input j through offset k
  *   bwd  [M_out, K]       strided conv: bwd[o,k] = input row feeding output o through offset k
  *   pairs [2, K, M_in]    spconv layout, canonical order (ascending input row inside each offset)
@@ -52,8 +56,9 @@ int64_t b200sp_rulebook_ws_bytes(int64_t M_in, int K, int cand_per_input);
 /* SubM (stride 1, output sites == input sites). ksize/dil per axis; padding is k/2 as in spconv. */
 int b200sp_rulebook_subm(const int32_t* coords_dev, int64_t M, int batch, const int32_t* shape_host /*[3]*/,
                          const int32_t* ksize_host /*[3]*/, const int32_t* dil_host /*[3]*/,
-                         int32_t* nbr_dev /*[M,K]*/, int32_t* pairs_dev /*[2,K,M] or NULL*/,
-                         int32_t* pairnum_dev /*[K] or NULL*/, void* ws_dev, int64_t ws_bytes, void* stream);
+                         int32_t* nbr_dev /*[M,K] or NULL*/, int32_t* pairs_dev /*[2,K,M] or NULL*/,
+                         int32_t* pairnum_dev /*[K] or NULL*/, int32_t* order_dev /*[M] or NULL*/,
+                         int32_t* nbr_perm_dev /*[M,K] or NULL*/, void* ws_dev, int64_t ws_bytes, void* stream);
 
 /* Regular (strided) sparse conv.  Output sites are returned in ascending flattened index
  * (the spconv-CUDA convention).  out_coords/bwd must be sized for the upper bound
@@ -75,21 +80,31 @@ int b200sp_pairs_to_table(const int32_t* pairs_dev, const int32_t* pairnum_dev, 
  * Convolution.  Replaces spconv v1.2 `ops.indice_conv` / `ops.indice_conv_backward`
  * (gather -> SGEMM -> scatter-add per offset) with one output-stationary gather-GEMM launch.
  *
- *   out[r,:] (+)= sum_k  in[tab[r,k], :] @ W[k]          tab == NULL, K == 1  ->  plain GEMM (1x1 conv)
+ *   out[orow[r],:] (+)= sum_k  in[tab[r,k], :] @ W[k]    tab == NULL, K == 1  ->  plain GEMM (1x1 conv)
+ *                                                         orow == NULL -> identity (table row r is output row r)
  *
- * W is [K][Cin][Cout] contiguous.  dgrad uses the same entry point on b200sp_weight_transpose(W)
- * (mirrored offsets for SubM) and the out->in table of the adjoint.
+ * W is the module's weight viewed as [K][Ci_w][Co_w] contiguous.  wflags = 0: forward (Cin = Ci_w, Cout = Co_w).
+ * wflags bit0: use W[k]^T (dgrad: Cin = Co_w, Cout = Ci_w); bit1: mirrored offsets W[K-1-k] (SubM dgrad), with
+ * the out->in table of the adjoint.
  * ------------------------------------------------------------------------------------------ */
-int b200sp_gather_gemm(const float* in_dev, int64_t n_in, int Cin, const float* W_dev, const int32_t* tab_dev, int K,
-                       float* out_dev, int64_t n_out, int Cout, int accumulate, void* stream);
+int b200sp_gather_gemm(const float* in_dev, int64_t n_in, int Cin, const float* W_dev, int wflags,
+                       const int32_t* tab_dev, const int32_t* orow_dev, int K, float* out_dev, int64_t n_out, int Cout,
+                       int accumulate, void* ws_dev, int64_t ws_bytes, void* stream);
 
 /* pair-grouped variant (each output row written by exactly one pair; used for the non-overlapping
  * inverse conv forward and the strided conv dgrad):  out[po[k][i],:] = in[pi[k][i],:] @ W[k].
  * pairnum stays on the device (no host sync): n_upper >= max_k pairnum[k] sizes the grid and CTAs past
  * pairnum[k] exit immediately. */
-int b200sp_gather_gemm_pairs(const float* in_dev, int Cin, const float* W_dev, const int32_t* pairs_in_dev /*[K,stride]*/,
-                             const int32_t* pairs_out_dev, const int32_t* pairnum_dev, int64_t n_upper, int K,
-                             int64_t pair_stride, float* out_dev, int Cout, int accumulate, void* stream);
+int b200sp_gather_gemm_pairs(const float* in_dev, int Cin, const float* W_dev, int wflags,
+                             const int32_t* pairs_in_dev /*[K,stride]*/, const int32_t* pairs_out_dev,
+                             const int32_t* pairnum_dev, int64_t n_upper, int K, int64_t pair_stride, float* out_dev,
+                             int Cout, int accumulate, void* ws_dev, int64_t ws_bytes, void* stream);
+
+/* device workspace both calls above need (pre-split tensor-core weight image / transposed weights) */
+int64_t b200sp_conv_ws_bytes(int K, int Cin, int Cout);
+/* 0 (default) = tcgen05 tensor-core path (3xTF32, fp32-accurate) wherever the shape is covered;
+ * 1 = fp32 CUDA-core kernel only.  Also selectable with the environment variable B200SP_CONV_IMPL=fp32. */
+int b200sp_set_conv_impl(int impl);
 
 /* weight gradient: dW[k][ci][co] += sum_i a[pa[k][i]][ci] * b[pb[k][i]][co].   pa/pb NULL -> identity
  * rows (1x1 conv: n_upper rows, pairnum ignored).  dW must be zero-initialised by the caller. */
