@@ -407,6 +407,8 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
                 const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out, int Cout,
                 int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st);
 int64_t conv_tc_ws_bytes(int K, int Cin, int Cout);
+int wgrad_tc_run(const float* a, int Ca, const float* b, int Cb, const int* pa, const int* pb, const int* pairnum,
+                 int64_t n_upper, int K, int64_t pstride, float* dW, cudaStream_t st);
 
 // 0 = tensor-core path (tcgen05 3xTF32) whenever the shape is covered, 1 = fp32 CUDA-core kernel only
 static int g_conv_impl = -1;
@@ -510,6 +512,10 @@ extern "C" int b200sp_wgrad(const float* a, int Ca, const float* b, int Cb, cons
     B200SP_CHECK_ARG(!(pa || pb) || pairnum_dev, "wgrad: pair lists need pairnum_dev");
     const int64_t nmax = n_upper;
     if (nmax <= 0) return B200SP_OK;
+    if (conv_impl() == 0) {
+        int rc = wgrad_tc_run(a, Ca, b, Cb, pa, pb, pairnum_dev, n_upper, K, pstride, dW, (cudaStream_t)stream);
+        if (rc != B200SP_EUNSUP) return rc;
+    }
     WGParams p{};
     p.a = a; p.b = b; p.pa = pa; p.pb = pb; p.pairnum = (pa || pb) ? pairnum_dev : nullptr; p.dW = dW;
     p.pstride = pstride; p.n_rows = n_upper; p.Ca = Ca; p.Cb = Cb; p.K = K;

@@ -35,9 +35,10 @@ constexpr int TC_BM = 128;
 constexpr int TC_MAXK = 32;
 constexpr int TC_XFORM = 256;   // warps 0-7 : transform (lo = v - tf32(v)) + epilogue
 constexpr int TC_LOADERS = 128; // warps 8-11: cp.async row gather straight into the canonical A layout
-constexpr int TC_WARP_MMA = 12;
-constexpr int TC_WARP_W = 13;
-constexpr int TC_THREADS = TC_XFORM + TC_LOADERS + 64;
+constexpr int TC_WARP_MMA = 12;   // warps 12..15: MMA issuers.  One thread sustains only ~1 tcgen05.mma per ~215 cycles
+constexpr int TC_MAX_ISSUERS = 4;  // whatever its shape (tools/mma_bench), but issuers run concurrently: the MMAs of a
+constexpr int TC_WARP_W = 16;      // tile are dealt round-robin to NI warps, each with its own TMEM accumulator
+constexpr int TC_THREADS = TC_XFORM + TC_LOADERS + 32 * TC_MAX_ISSUERS + 32;
 
 struct TCParams {
     const float* in;
@@ -56,6 +57,7 @@ struct TCParams {
     int nslots;
     uint32_t stageB_bytes;  // 2 * Cout_pad * KC * 4
     uint32_t tmem_cols;
+    int ni;  // MMA issuer warps in use (accumulators)
 };
 
 template <int KC>
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             mbar_init(&empty[s], 1);
             mbar_init(&raw[s], TC_LOADERS);
         }
-        mbar_init(accum, 1);
+        mbar_init(accum, p.ni);
         mbar_fence_init();
     }
     if (warp == TC_WARP_MMA) tmem_alloc(s_tmem, p.tmem_cols);
@@ -207,6 +209,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
         const int q4 = warp & 3, hcol = warp >> 2;
         const int orow = s_orow[q4 * 32 + lane];
         const bool vecO = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+        const int nacc_used = min(p.ni, nit);
         if (nit > 0) {
             mbar_wait(accum, 0);
             tc_fence_after();
@@ -215,6 +218,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             float v[16];
             if (nit > 0) {
                 tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * 16), v);
+                for (int ac = 1; ac < nacc_used; ++ac) {
+                    float w[16];
+                    tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ac * p.Cout_pad + ch * 16), w);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] += w[i];
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0.f;
@@ -296,38 +305,47 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             }
         }
         asm volatile("cp.async.wait_all;\n" ::: "memory");
-    } else if (warp == TC_WARP_MMA) {
-        // ========== MMA issuer (one thread) ==========
-        if (lane == 0) {
+    } else if (warp < TC_WARP_MMA + TC_MAX_ISSUERS) {
+        // ========== MMA issuers: warp w owns the stages it = w, w+ni, ... and accumulator w.  The whole warp walks
+        // the loop (uniform control flow), one elected lane issues; descriptors are advanced by constant adds ==========
+        const int w = warp - TC_WARP_MMA;
+        if (w < p.ni) {
             const uint32_t idesc = make_idesc_tf32(TC_BM, p.Cout_pad, 0, 0);
-            const uint32_t lboA = L::LBO;                      // K-adjacent core matrices of A
             const uint32_t lboB = (uint32_t)p.Cout_pad * 16u;  // K-adjacent core matrices of B
-            int slot = 0;
-            uint32_t ph = 0;
-            for (int it = 0; it < nit; ++it) {
+            const uint32_t dcol = tmem + (uint32_t)(w * p.Cout_pad);
+            // descriptors of slot 0 (hi tiles); lo tiles / other slots / K steps are constant offsets in 16-byte units
+            const uint64_t dA0 = make_desc(smem_u32(sA), L::LBO, 128u);
+            const uint64_t dB0 = make_desc(smem_u32(sB), lboB, 128u);
+            const uint32_t slotA16 = (2u * L::A_BYTES) >> 4, loA16 = L::A_BYTES >> 4, kA16 = (2u * L::LBO) >> 4;
+            const uint32_t slotB16 = p.stageB_bytes >> 4, loB16 = p.stageB_bytes >> 5, kB16 = (2u * lboB) >> 4;
+            int slot = w % S;
+            uint32_t ph = (uint32_t)(w / S) & 1u;
+            uint32_t acc = 0;
+            for (int it = w; it < nit; it += p.ni) {
                 mbar_wait(&full[slot], ph);
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(sA + (size_t)slot * 2 * L::A_BYTES);
-                const uint32_t a_lo = a_hi + L::A_BYTES;
-                const uint32_t b_hi = smem_u32(sB + (size_t)slot * p.stageB_bytes);
-                const uint32_t b_lo = b_hi + p.stageB_bytes / 2;
+                const uint64_t da = dA0 + (uint64_t)((uint32_t)slot * slotA16);
+                const uint64_t db = dB0 + (uint64_t)((uint32_t)slot * slotB16);
+                if (elect_one()) {
 #pragma unroll
-                for (int j = 0; j < KC / 8; ++j) {
-                    const uint64_t dah = make_desc(a_hi + (uint32_t)j * 2u * lboA, lboA, 128u);
-                    const uint64_t dal = make_desc(a_lo + (uint32_t)j * 2u * lboA, lboA, 128u);
-                    const uint64_t dbh = make_desc(b_hi + (uint32_t)j * 2u * lboB, lboB, 128u);
-                    const uint64_t dbl = make_desc(b_lo + (uint32_t)j * 2u * lboB, lboB, 128u);
-                    mma_tf32_ss(tmem, dah, dbh, idesc, (it | j) != 0 ? 1u : 0u);
-                    mma_tf32_ss(tmem, dal, dbh, idesc, 1u);
-                    mma_tf32_ss(tmem, dah, dbl, idesc, 1u);
+                    for (int j = 0; j < KC / 8; ++j) {
+                        mma_tf32_ss(dcol, da + j * kA16, db + j * kB16, idesc, acc);
+                        mma_tf32_ss(dcol, da + loA16 + j * kA16, db + j * kB16, idesc, 1u);
+                        mma_tf32_ss(dcol, da + j * kA16, db + loB16 + j * kB16, idesc, 1u);
+                        acc = 1u;
+                    }
+                    mma_commit(&empty[slot]);
                 }
-                mma_commit(&empty[slot]);
-                if (++slot == S) {
-                    slot = 0;
+                acc = 1u;
+                __syncwarp();
+                slot += p.ni;
+                while (slot >= S) {
+                    slot -= S;
                     ph ^= 1u;
                 }
             }
-            if (nit > 0) mma_commit(accum);
+            if (nit > 0 && elect_one()) mma_commit(accum);
+            __syncwarp();
         }
     } else {
         // ========== weight loader (one thread): one bulk copy per stage ==========
@@ -391,7 +409,7 @@ __global__ void k_prep_weights(const float* __restrict__ W, int K, int Ci_w, int
 }
 
 struct TCPlan {
-    int KC, nchunks, Cout_pad, nslots;
+    int KC, nchunks, Cout_pad, nslots, ni;
     uint32_t stageB, tmem_cols, smem;
     int64_t wp_bytes;
 };
@@ -404,8 +422,7 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
     pl.Cout_pad = (Cout + 15) / 16 * 16;
     if (pl.Cout_pad > 256) return false;
     pl.stageB = 2u * (uint32_t)pl.Cout_pad * pl.KC * 4u;
-    uint32_t cols = 32;
-    while (cols < (uint32_t)pl.Cout_pad) cols <<= 1;
+    uint32_t cols = 32;  // refined below once the issuer count is known
     pl.tmem_cols = cols;
     pl.wp_bytes = (int64_t)K * pl.nchunks * pl.stageB;
     const uint32_t cpr = (uint32_t)pl.KC / 4u;
@@ -422,6 +439,21 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
     }
     if (best == 0) return false;
     pl.nslots = best;
+    // issuer warps: each smem slot must belong to exactly ONE issuer (its mbarrier waits are parity waits, an issuer
+    // running a fill ahead of a slot it shares would alias phases), so ni divides nslots; one accumulator per issuer
+    {
+        const char* e = getenv("B200SP_TC_ISSUERS");
+        const int want = std::max(1, std::min(e ? atoi(e) : TC_MAX_ISSUERS, TC_MAX_ISSUERS));
+        pl.ni = 1;
+        for (int ni = want; ni >= 1; --ni)
+            if (best % ni == 0 && ni * pl.Cout_pad <= 512) {
+                pl.ni = ni;
+                break;
+            }
+    }
+    cols = 32;
+    while (cols < (uint32_t)(pl.ni * pl.Cout_pad)) cols <<= 1;
+    pl.tmem_cols = cols;
     return true;
 }
 
@@ -463,7 +495,7 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
     p.in = in; p.Wp = Wp; p.tab = tab; p.orow = orow; p.pin = pin; p.pout = pout; p.pairnum = pairnum; p.out = out;
     p.n_rows = n_rows; p.pstride = pstride; p.Cin = Cin; p.Cout = Cout; p.K = K;
     p.nchunks = pl.nchunks; p.Cout_pad = pl.Cout_pad; p.accumulate = accumulate; p.pairs_mode = pairs_mode;
-    p.nslots = pl.nslots; p.stageB_bytes = pl.stageB; p.tmem_cols = pl.tmem_cols;
+    p.nslots = pl.nslots; p.stageB_bytes = pl.stageB; p.tmem_cols = pl.tmem_cols; p.ni = pl.ni;
     dim3 grid((unsigned)cdiv(n_rows, TC_BM), 1, pairs_mode ? (unsigned)K : 1u);
     if (pl.KC == 32) return launch_tc<32>(p, KT, grid, st);
     if (pl.KC == 16) return launch_tc<16>(p, KT, grid, st);
