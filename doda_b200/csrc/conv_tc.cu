@@ -33,12 +33,19 @@ using namespace tc;
 
 constexpr int TC_BM = 128;
 constexpr int TC_MAXK = 32;
-constexpr int TC_XFORM = 256;   // warps 0-7 : transform (lo = v - tf32(v)) + epilogue
-constexpr int TC_LOADERS = 128; // warps 8-11: cp.async row gather straight into the canonical A layout
-constexpr int TC_WARP_MMA = 12;   // warps 12..15: MMA issuers.  One thread sustains only ~1 tcgen05.mma per ~215 cycles
-constexpr int TC_MAX_ISSUERS = 4;  // whatever its shape (tools/mma_bench), but issuers run concurrently: the MMAs of a
-constexpr int TC_WARP_W = 16;      // tile are dealt round-robin to NI warps, each with its own TMEM accumulator
-constexpr int TC_THREADS = TC_XFORM + TC_LOADERS + 32 * TC_MAX_ISSUERS + 32;
+// warp roles of the persistent CTA (18 warps)
+constexpr int TC_W_XFORM = 0;     // warps 0-3  : transform (lo = v - tf32(v)), thread <-> row
+constexpr int TC_W_EPI = 4;       // warps 4-7  : epilogue, warp (4+q) reads TMEM lane quarter q
+constexpr int TC_W_LOAD = 8;      // warps 8-11 : cp.async row gather straight into the canonical A layout
+constexpr int TC_W_MMA = 12;      // warps 12-15: MMA issuers.  One thread sustains only ~1 tcgen05.mma per ~215 cycles
+constexpr int TC_MAX_ISSUERS = 4; //   whatever its shape (tools/mma_bench) but issuers run concurrently: stages are dealt
+                                  //   round-robin to ni warps, each with its own TMEM accumulator
+constexpr int TC_W_WEIGHT = 16;   // warp 16    : weight blocks, one cp.async.bulk per stage
+constexpr int TC_W_TILE = 17;     // warp 17    : tile prefetcher (table rows, active-offset list) one tile ahead
+constexpr int TC_THREADS = 18 * 32;
+constexpr int TC_XFORM_THREADS = 128;
+constexpr int TC_LOADERS = 128;
+constexpr int TC_NBUF = 2;        // tile-metadata buffers and TMEM accumulator sets
 
 struct TCParams {
     const float* in;
@@ -57,7 +64,9 @@ struct TCParams {
     int nslots;
     uint32_t stageB_bytes;  // 2 * Cout_pad * KC * 4
     uint32_t tmem_cols;
-    int ni;  // MMA issuer warps in use (accumulators)
+    int ni;                 // MMA issuer warps in use (accumulators per set)
+    int row_tiles;          // ceil(n_rows / 128)
+    int total_tiles;        // row_tiles * (pairs_mode ? K : 1)
 };
 
 template <int KC>
@@ -67,14 +76,15 @@ struct TCLayout {
     static constexpr uint32_t CPR = KC / 4;                       // 16-byte chunks per row per stage
     static constexpr uint32_t LBO = TC_BM * 16u + 128u / CPR;
     static constexpr uint32_t A_BYTES = (CPR * LBO + 127u) & ~127u;  // one of {hi, lo}
+    __host__ __device__ static uint32_t meta_ints(int KT) { return (uint32_t)(TC_BM * KT + TC_BM + TC_MAXK + 4); }
     __host__ __device__ static uint32_t offB(int nslots) { return (uint32_t)nslots * 2u * A_BYTES; }
-    __host__ __device__ static uint32_t offIdx(int nslots, uint32_t stageB) { return offB(nslots) + (uint32_t)nslots * stageB; }
+    __host__ __device__ static uint32_t offMeta(int nslots, uint32_t stageB) { return offB(nslots) + (uint32_t)nslots * stageB; }
     __host__ __device__ static uint32_t offBars(int nslots, uint32_t stageB, int KT) {
-        uint32_t o = offIdx(nslots, stageB) + (uint32_t)(TC_BM * KT + TC_BM + 2 * TC_MAXK + 4) * 4u;
+        uint32_t o = offMeta(nslots, stageB) + TC_NBUF * meta_ints(KT) * 4u;
         return (o + 15u) & ~15u;
     }
     __host__ __device__ static uint32_t total(int nslots, uint32_t stageB, int KT) {
-        return offBars(nslots, stageB, KT) + (uint32_t)(3 * nslots + 1) * 8u + 16u;
+        return offBars(nslots, stageB, KT) + (uint32_t)(3 * nslots + 4 * TC_NBUF) * 8u + 16u;
     }
 };
 
@@ -89,290 +99,373 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Persistent CTA: walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  Every role keeps its own running counters
+// (tile sequence number i, global stage number g); the smem stage ring and the two TMEM accumulator sets run
+// seamlessly across tiles, so gathers of tile t+1 are in flight while tile t is multiplied and tile t-1 is stored.
 template <int KC>
 __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
     using L = TCLayout<KC>;
-    constexpr int NV = KC / 8;  // 16-byte chunks per transform thread per stage (two threads per row)
+    constexpr int NV = KC / 4;  // 16-byte chunks per row per stage
     extern __shared__ __align__(128) unsigned char smem[];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = p.nslots;
     const int K = p.K;
     const int KT = p.pairs_mode ? 1 : K;
+    const int ni = p.ni;
     unsigned char* sA = smem;
     unsigned char* sB = smem + L::offB(S);
-    int* s_idx = reinterpret_cast<int*>(smem + L::offIdx(S, p.stageB_bytes));
-    int* s_orow = s_idx + TC_BM * KT;
-    int* s_klist = s_orow + TC_BM;
-    int* s_kflag = s_klist + TC_MAXK;
-    int* s_nk = s_kflag + TC_MAXK;
+    int* s_meta = reinterpret_cast<int*>(smem + L::offMeta(S, p.stageB_bytes));
+    const int meta_ints = (int)L::meta_ints(KT);
+    // per buffer: idx[128*KT] | orow[128] | klist[32] | nk | kfixed | pad
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::offBars(S, p.stageB_bytes, KT));  // hi+lo+weights ready -> MMA
     uint64_t* empty = full + S;                                                            // MMA done -> slot reusable
     uint64_t* raw = empty + S;                                                             // gathered rows landed -> transform
-    uint64_t* accum = raw + S;
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(accum + 1);
+    uint64_t* tready = raw + S;           // [NBUF] tile metadata published
+    uint64_t* tfree = tready + TC_NBUF;   // [NBUF] every reader is done with the tile metadata
+    uint64_t* accf = tfree + TC_NBUF;     // [NBUF] accumulator set complete -> epilogue
+    uint64_t* acce = accf + TC_NBUF;      // [NBUF] accumulator set drained -> issuers
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acce + TC_NBUF);
 
-    const int64_t row0 = (int64_t)blockIdx.x * TC_BM;
-    int rows;
-    int kfixed = 0;
-    if (p.pairs_mode) {
-        kfixed = blockIdx.z;
-        const int n = p.pairnum[kfixed];
-        if (row0 >= n) return;  // whole CTA leaves before touching barriers / TMEM
-        rows = (int)min((int64_t)TC_BM, (int64_t)n - row0);
-        for (int r = tid; r < TC_BM; r += TC_THREADS) {
-            const bool ok = r < rows;
-            s_idx[r] = ok ? p.pin[(int64_t)kfixed * p.pstride + row0 + r] : -1;
-            s_orow[r] = ok ? p.pout[(int64_t)kfixed * p.pstride + row0 + r] : -1;
-        }
-        if (tid == 0) {
-            *s_nk = 1;
-            s_klist[0] = 0;
-        }
-    } else {
-        rows = (int)min((int64_t)TC_BM, p.n_rows - row0);
-        if (tid < TC_MAXK) s_kflag[tid] = 0;
-        __syncthreads();
-        if (p.tab) {
-            const int* t = p.tab + row0 * K;
-            for (int i = tid; i < TC_BM * K; i += TC_THREADS) {
-                const int v = (i < rows * K) ? __ldg(t + i) : -1;
-                s_idx[i] = v;
-                if (v >= 0) s_kflag[i % K] = 1;
-            }
-        } else {
-            for (int r = tid; r < TC_BM; r += TC_THREADS) s_idx[r] = r < rows ? (int)(row0 + r) : -1;
-            if (tid == 0) s_kflag[0] = 1;
-        }
-        for (int r = tid; r < TC_BM; r += TC_THREADS)
-            s_orow[r] = r < rows ? (p.orow ? __ldg(p.orow + row0 + r) : (int)(row0 + r)) : -1;
-        __syncthreads();
-        if (tid == 0) {
-            int nk = 0;
-            for (int k = 0; k < K; ++k)
-                if (s_kflag[k]) s_klist[nk++] = k;
-            *s_nk = nk;
-        }
-    }
+    const int ntiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], TC_XFORM / 32 + 1);
+            mbar_init(&full[s], TC_XFORM_THREADS / 32 + 1);
             mbar_init(&empty[s], 1);
             mbar_init(&raw[s], TC_LOADERS);
         }
-        mbar_init(accum, p.ni);
+        for (int b = 0; b < TC_NBUF; ++b) {
+            mbar_init(&tready[b], 1);
+            mbar_init(&tfree[b], TC_LOADERS + 4 /*xform warps*/ + 4 /*epilogue warps*/ + ni + 1 /*weights*/);
+            mbar_init(&accf[b], ni);
+            mbar_init(&acce[b], 4);
+        }
         mbar_fence_init();
     }
-    if (warp == TC_WARP_MMA) tmem_alloc(s_tmem, p.tmem_cols);
+    if (warp == TC_W_MMA) tmem_alloc(s_tmem, p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
 
     const uint32_t tmem = *s_tmem;
-    const int nk = *s_nk;
     const int nchunks = p.nchunks;
-    const int nit = nk * nchunks;
     const int Cin = p.Cin, Cout = p.Cout;
 
-    if (warp < TC_XFORM / 32) {
-        // ========== transform: lo = v - tf32(v) next to the raw rows (the tensor core reads tf32(v) from the raw copy) ==========
-        const int row = tid & (TC_BM - 1);
-        const int half = tid >> 7;
-        const uint32_t soff = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
-        int slot = 0;
-        uint32_t ph = 0;
-        for (int it = 0; it < nit; ++it) {
-            unsigned char* a_hi = sA + (size_t)slot * 2 * L::A_BYTES;
-            unsigned char* a_lo = a_hi + L::A_BYTES;
-            mbar_wait(&raw[slot], ph);
-#pragma unroll
-            for (int q = 0; q < NV; ++q) {
-                const uint32_t off = (uint32_t)(half * NV + q) * L::LBO + soff;
-                const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
-                float4 h, l;
-                split_tf32(v.x, h.x, l.x);
-                split_tf32(v.y, h.y, l.y);
-                split_tf32(v.z, h.z, l.z);
-                split_tf32(v.w, h.w, l.w);
-                *reinterpret_cast<float4*>(a_lo + off) = l;
-            }
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[slot]);
-            if (++slot == S) {
-                slot = 0;
-                ph ^= 1u;
-            }
-        }
+#define TC_META(b) (s_meta + (b) * meta_ints)
+#define TC_IDX(b) (TC_META(b))
+#define TC_OROW(b) (TC_META(b) + TC_BM * KT)
+#define TC_KLIST(b) (TC_META(b) + TC_BM * KT + TC_BM)
+#define TC_NK(b) (TC_META(b)[TC_BM * KT + TC_BM + TC_MAXK])
+#define TC_KFIX(b) (TC_META(b)[TC_BM * KT + TC_BM + TC_MAXK + 1])
 
-        // ========== epilogue: TMEM -> registers -> global (each output row written once) ==========
-        const int q4 = warp & 3, hcol = warp >> 2;
-        const int orow = s_orow[q4 * 32 + lane];
-        const bool vecO = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
-        const int nacc_used = min(p.ni, nit);
-        if (nit > 0) {
-            mbar_wait(accum, 0);
-            tc_fence_after();
-        }
-        for (int ch = hcol; ch * 16 < p.Cout_pad; ch += 2) {
-            float v[16];
-            if (nit > 0) {
-                tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ch * 16), v);
-                for (int ac = 1; ac < nacc_used; ++ac) {
-                    float w[16];
-                    tmem_ld16(tmem + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(ac * p.Cout_pad + ch * 16), w);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] += w[i];
+    if (warp == TC_W_TILE) {
+        // ========== tile prefetcher ==========
+        for (int i = 0; i < ntiles; ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            mbar_wait(&tfree[b], ph ^ 1u);
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            int* idx = TC_IDX(b);
+            int* orow = TC_OROW(b);
+            int* klist = TC_KLIST(b);
+            if (p.pairs_mode) {
+                const int kf = tile / p.row_tiles;
+                const int64_t row0 = (int64_t)(tile - kf * p.row_tiles) * TC_BM;
+                const int n = __ldg(p.pairnum + kf);
+                const int rows = (int)max((int64_t)0, min((int64_t)TC_BM, (int64_t)n - row0));
+                for (int r = lane; r < TC_BM; r += 32) {
+                    const bool ok = r < rows;
+                    idx[r] = ok ? __ldg(p.pin + (int64_t)kf * p.pstride + row0 + r) : -1;
+                    orow[r] = ok ? __ldg(p.pout + (int64_t)kf * p.pstride + row0 + r) : -1;
+                }
+                if (lane == 0) {
+                    klist[0] = 0;
+                    TC_NK(b) = rows > 0 ? 1 : 0;
+                    TC_KFIX(b) = kf;
                 }
             } else {
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = 0.f;
-            }
-            if (orow < 0) continue;
-            float* o = p.out + (int64_t)orow * Cout + ch * 16;
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) {
-                const int col = ch * 16 + g4 * 4;
-                if (col >= Cout) break;
-                if (vecO) {
-                    float4 w = make_float4(v[g4 * 4 + 0], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
-                    if (p.accumulate) {
-                        const float4 old = *reinterpret_cast<const float4*>(o + g4 * 4);
-                        w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w;
+                const int64_t row0 = (int64_t)tile * TC_BM;
+                const int rows = (int)min((int64_t)TC_BM, p.n_rows - row0);
+                unsigned mask = 0;
+                if (p.tab) {
+                    const int* t = p.tab + row0 * K;
+                    const int tot = rows * K;
+                    int kk = lane % K;  // column of element i = lane, lane+32, ...
+                    const int step = 32 % K;
+                    for (int e = lane; e < TC_BM * K; e += 32) {
+                        const int v = e < tot ? __ldg(t + e) : -1;
+                        idx[e] = v;
+                        if (v >= 0) mask |= 1u << kk;
+                        kk += step;
+                        if (kk >= K) kk -= K;
                     }
-                    *reinterpret_cast<float4*>(o + g4 * 4) = w;
                 } else {
+                    for (int r = lane; r < TC_BM; r += 32) idx[r] = r < rows ? (int)(row0 + r) : -1;
+                    mask = rows > 0 ? 1u : 0u;
+                }
+                for (int r = lane; r < TC_BM; r += 32)
+                    orow[r] = r < rows ? (p.orow ? __ldg(p.orow + row0 + r) : (int)(row0 + r)) : -1;
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        if (col + e < Cout) {
-                            float w = v[g4 * 4 + e];
-                            if (p.accumulate) w += o[g4 * 4 + e];
-                            o[g4 * 4 + e] = w;
+                for (int o = 16; o; o >>= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
+                if (lane == 0) {
+                    int nk = 0;
+                    for (int k = 0; k < K; ++k)
+                        if (mask >> k & 1u) klist[nk++] = k;
+                    TC_NK(b) = nk;
+                    TC_KFIX(b) = 0;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tready[b]);
+        }
+    } else if (warp >= TC_W_LOAD && warp < TC_W_LOAD + 4) {
+        // ========== loaders: 16-byte cp.async (zero-fill for missing neighbours) straight into the canonical K-major
+        // layout.  Consecutive lanes take consecutive 16-byte chunks of the SAME row, so one warp instruction touches
+        // 32*16/(KC*4) rows = that many cache lines (not 32); completion is signalled on raw[slot] by the copy engine ==========
+        const int lt = tid - TC_W_LOAD * 32;  // 0..127
+        constexpr int CPR = KC / 4;
+        const bool vec = (Cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0);
+        int slot = 0;
+        uint32_t sph = 0;
+        for (int i = 0; i < ntiles; ++i) {
+            const int b = i & 1;
+            mbar_wait(&tready[b], (uint32_t)(i >> 1) & 1u);
+            const int* idx = TC_IDX(b);
+            const int* klist = TC_KLIST(b);
+            const int nk = TC_NK(b);
+            for (int kk = 0; kk < nk; ++kk) {
+                const int kcol = p.pairs_mode ? 0 : klist[kk];
+                for (int c = 0; c < nchunks; ++c) {
+                    const int c0 = c * KC;
+                    const uint32_t dst0 = smem_u32(sA + (size_t)slot * 2 * L::A_BYTES);
+                    mbar_wait(&empty[slot], sph ^ 1u);
+                    if (vec) {
+                        // thread-constant: chunk j and row phase; q only advances the 8-row group
+                        const int j = lt % CPR, rowb = lt / CPR;
+                        constexpr int RPQ = TC_LOADERS / CPR;  // rows covered per pass (multiple of 8)
+                        const bool colok = c0 + 4 * j < Cin;
+                        const uint32_t dstb = dst0 + (uint32_t)j * L::LBO + (uint32_t)(rowb >> 3) * 128u + (uint32_t)(rowb & 7) * 16u;
+                        const int* ip = idx + rowb * KT + kcol;
+#pragma unroll
+                        for (int q = 0; q < CPR; ++q) {
+                            const int src = ip[q * RPQ * KT];
+                            const bool ok = (src >= 0) && colok;
+                            const float* g = p.in + ((int64_t)(ok ? src : 0) * Cin + (ok ? c0 + 4 * j : 0));
+                            cp_async16_zfill(dstb + (uint32_t)q * (RPQ / 8) * 128u, g, ok ? 16 : 0);
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int q = 0; q < KC; ++q) {
+                            const int e0 = q * TC_LOADERS + lt;
+                            const int row = e0 / KC, e = e0 % KC;
+                            const int src = idx[row * KT + kcol];
+                            const bool ok = (src >= 0) && (c0 + e < Cin);
+                            const float* g = p.in + (int64_t)(ok ? src : 0) * Cin + (ok ? c0 + e : 0);
+                            cp_async4_zfill(dst0 + (uint32_t)(e >> 2) * L::LBO + (uint32_t)(row >> 3) * 128u +
+                                                (uint32_t)(row & 7) * 16u + 4u * (uint32_t)(e & 3),
+                                            g, ok ? 4 : 0);
+                        }
+                    }
+                    cp_async_arrive_noinc(&raw[slot]);
+                    if (++slot == S) {
+                        slot = 0;
+                        sph ^= 1u;
+                    }
+                }
+            }
+            mbar_arrive(&tfree[b]);
+        }
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+    } else if (warp < TC_W_XFORM + 4) {
+        // ========== transform: lo = v - tf32(v) next to the raw rows (the tensor core reads tf32(v) from the raw copy) ==========
+        const int row = tid;  // 0..127
+        const uint32_t soff = (uint32_t)(row >> 3) * 128u + (uint32_t)(row & 7) * 16u;
+        int slot = 0;
+        uint32_t sph = 0;
+        for (int i = 0; i < ntiles; ++i) {
+            const int b = i & 1;
+            mbar_wait(&tready[b], (uint32_t)(i >> 1) & 1u);
+            const int nit = TC_NK(b) * nchunks;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tfree[b]);
+            for (int it = 0; it < nit; ++it) {
+                unsigned char* a_hi = sA + (size_t)slot * 2 * L::A_BYTES;
+                unsigned char* a_lo = a_hi + L::A_BYTES;
+                mbar_wait(&raw[slot], sph);
+#pragma unroll
+                for (int q = 0; q < NV; ++q) {
+                    const uint32_t off = (uint32_t)q * L::LBO + soff;
+                    const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
+                    float4 h, l;
+                    split_tf32(v.x, h.x, l.x);
+                    split_tf32(v.y, h.y, l.y);
+                    split_tf32(v.z, h.z, l.z);
+                    split_tf32(v.w, h.w, l.w);
+                    *reinterpret_cast<float4*>(a_lo + off) = l;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[slot]);
+                if (++slot == S) {
+                    slot = 0;
+                    sph ^= 1u;
+                }
+            }
+        }
+    } else if (warp >= TC_W_EPI && warp < TC_W_EPI + 4) {
+        // ========== epilogue: TMEM -> registers -> global (each output row written once) ==========
+        const int q4 = warp - TC_W_EPI;
+        const bool vecO = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+        int g0 = 0;  // global stage number of the tile's first stage
+        for (int i = 0; i < ntiles; ++i) {
+            const int b = i & 1;
+            const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+            mbar_wait(&tready[b], ph);
+            const int nit = TC_NK(b) * nchunks;
+            const int orow = TC_OROW(b)[q4 * 32 + lane];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tfree[b]);
+            if (nit > 0) {
+                mbar_wait(&accf[b], ph);
+                tc_fence_after();
+            }
+            const int nused = min(ni, nit);
+            const uint32_t set_col = tmem + (uint32_t)(b * ni * p.Cout_pad);
+            for (int ch = 0; ch * 16 < p.Cout_pad; ++ch) {
+                float v[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = 0.f;
+                for (int u = 0; u < nused; ++u) {
+                    const int w = (g0 + u) % ni;  // issuers that received a stage of this tile
+                    float t[16];
+                    tmem_ld16(set_col + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(w * p.Cout_pad + ch * 16), t);
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) v[e] += t[e];
+                }
+                if (orow < 0) continue;
+                float* o = p.out + (int64_t)orow * Cout + ch * 16;
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    const int col = ch * 16 + g4 * 4;
+                    if (col >= Cout) break;
+                    if (vecO) {
+                        float4 wv = make_float4(v[g4 * 4 + 0], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
+                        if (p.accumulate) {
+                            const float4 old = *reinterpret_cast<const float4*>(o + g4 * 4);
+                            wv.x += old.x; wv.y += old.y; wv.z += old.z; wv.w += old.w;
+                        }
+                        *reinterpret_cast<float4*>(o + g4 * 4) = wv;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            if (col + e < Cout) {
+                                float wv = v[g4 * 4 + e];
+                                if (p.accumulate) wv += o[g4 * 4 + e];
+                                o[g4 * 4 + e] = wv;
+                            }
                         }
                     }
                 }
             }
+            if (nit > 0) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acce[b]);
+            }
+            g0 += nit;
         }
-    } else if (warp < (TC_XFORM + TC_LOADERS) / 32) {
-        // ========== loaders: 16-byte cp.async (zero-fill for missing neighbours) straight into the canonical K-major
-        // layout.  Consecutive lanes take consecutive 16-byte chunks of the SAME row, so one warp instruction touches
-        // 32*16/(KC*4) rows = that many cache lines (not 32); completion is signalled on raw[slot] by the copy engine ==========
-        const int lt = tid - TC_XFORM;  // 0..127
-        constexpr int CPR = KC / 4;     // 16-byte chunks per row per stage
-        const bool vec = (Cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0);
-        int slot = 0, kk = 0, c = 0;
-        uint32_t ph = 0;
-        for (int it = 0; it < nit; ++it) {
-            const int kcol = p.pairs_mode ? 0 : s_klist[kk];
-            const int c0 = c * KC;
-            const uint32_t dst0 = smem_u32(sA + (size_t)slot * 2 * L::A_BYTES);
-            mbar_wait(&empty[slot], ph ^ 1u);
-            if (vec) {
-                // thread-constant: chunk j and row phase; q only advances the 8-row group
-                const int j = lt % CPR, rowb = lt / CPR;
-                constexpr int RPQ = TC_LOADERS / CPR;  // rows covered per pass (multiple of 8)
-                const bool colok = c0 + 4 * j < Cin;
-                const uint32_t dstb = dst0 + (uint32_t)j * L::LBO + (uint32_t)(rowb >> 3) * 128u + (uint32_t)(rowb & 7) * 16u;
-                const int* ip = s_idx + rowb * KT + kcol;
-#pragma unroll
-                for (int q = 0; q < CPR; ++q) {
-                    const int src = ip[q * RPQ * KT];
-                    const bool ok = (src >= 0) && colok;
-                    const float* g = p.in + ((int64_t)(ok ? src : 0) * Cin + (ok ? c0 + 4 * j : 0));
-                    cp_async16_zfill(dstb + (uint32_t)q * (RPQ / 8) * 128u, g, ok ? 16 : 0);
-                }
-            } else {
-#pragma unroll 4
-                for (int q = 0; q < KC; ++q) {
-                    const int i = q * TC_LOADERS + lt;
-                    const int row = i / KC, e = i % KC;
-                    const int src = s_idx[row * KT + kcol];
-                    const bool ok = (src >= 0) && (c0 + e < Cin);
-                    const float* g = p.in + (int64_t)(ok ? src : 0) * Cin + (ok ? c0 + e : 0);
-                    cp_async4_zfill(dst0 + (uint32_t)(e >> 2) * L::LBO + (uint32_t)(row >> 3) * 128u +
-                                        (uint32_t)(row & 7) * 16u + 4u * (uint32_t)(e & 3),
-                                    g, ok ? 4 : 0);
-                }
-            }
-            cp_async_arrive_noinc(&raw[slot]);
-            if (++c == nchunks) {
-                c = 0;
-                ++kk;
-            }
-            if (++slot == S) {
-                slot = 0;
-                ph ^= 1u;
-            }
-        }
-        asm volatile("cp.async.wait_all;\n" ::: "memory");
-    } else if (warp < TC_WARP_MMA + TC_MAX_ISSUERS) {
-        // ========== MMA issuers: warp w owns the stages it = w, w+ni, ... and accumulator w.  The whole warp walks
-        // the loop (uniform control flow), one elected lane issues; descriptors are advanced by constant adds ==========
-        const int w = warp - TC_WARP_MMA;
-        if (w < p.ni) {
+    } else if (warp >= TC_W_MMA && warp < TC_W_MMA + TC_MAX_ISSUERS) {
+        // ========== MMA issuers: warp w owns the global stages g = w (mod ni) and accumulator w of each set.  The whole
+        // warp walks the loops (uniform control flow), one elected lane issues; descriptors advance by constant adds ==========
+        const int w = warp - TC_W_MMA;
+        if (w < ni) {
             const uint32_t idesc = make_idesc_tf32(TC_BM, p.Cout_pad, 0, 0);
             const uint32_t lboB = (uint32_t)p.Cout_pad * 16u;  // K-adjacent core matrices of B
-            const uint32_t dcol = tmem + (uint32_t)(w * p.Cout_pad);
             // descriptors of slot 0 (hi tiles); lo tiles / other slots / K steps are constant offsets in 16-byte units
             const uint64_t dA0 = make_desc(smem_u32(sA), L::LBO, 128u);
             const uint64_t dB0 = make_desc(smem_u32(sB), lboB, 128u);
             const uint32_t slotA16 = (2u * L::A_BYTES) >> 4, loA16 = L::A_BYTES >> 4, kA16 = (2u * L::LBO) >> 4;
             const uint32_t slotB16 = p.stageB_bytes >> 4, loB16 = p.stageB_bytes >> 5, kB16 = (2u * lboB) >> 4;
-            int slot = w % S;
-            uint32_t ph = (uint32_t)(w / S) & 1u;
-            uint32_t acc = 0;
-            for (int it = w; it < nit; it += p.ni) {
-                mbar_wait(&full[slot], ph);
-                tc_fence_after();
-                const uint64_t da = dA0 + (uint64_t)((uint32_t)slot * slotA16);
-                const uint64_t db = dB0 + (uint64_t)((uint32_t)slot * slotB16);
-                if (elect_one()) {
-#pragma unroll
-                    for (int j = 0; j < KC / 8; ++j) {
-                        mma_tf32_ss(dcol, da + j * kA16, db + j * kB16, idesc, acc);
-                        mma_tf32_ss(dcol, da + loA16 + j * kA16, db + j * kB16, idesc, 1u);
-                        mma_tf32_ss(dcol, da + j * kA16, db + loB16 + j * kB16, idesc, 1u);
-                        acc = 1u;
-                    }
-                    mma_commit(&empty[slot]);
-                }
-                acc = 1u;
+            int g0 = 0;
+            for (int i = 0; i < ntiles; ++i) {
+                const int b = i & 1;
+                const uint32_t ph = (uint32_t)(i >> 1) & 1u;
+                mbar_wait(&tready[b], ph);
+                const int nit = TC_NK(b) * nchunks;
                 __syncwarp();
-                slot += p.ni;
-                while (slot >= S) {
-                    slot -= S;
-                    ph ^= 1u;
+                if (lane == 0) mbar_arrive(&tfree[b]);
+                if (nit > 0) {
+                    mbar_wait(&acce[b], ph ^ 1u);  // the epilogue drained this accumulator set
+                    tc_fence_after();
+                    const uint32_t dcol = tmem + (uint32_t)((b * ni + w) * p.Cout_pad);
+                    uint32_t acc = 0;
+                    // first global stage >= g0 owned by this issuer
+                    int g = g0 + ((w - g0 % ni) + ni) % ni;
+                    for (; g < g0 + nit; g += ni) {
+                        const int slot = g % S;
+                        const uint32_t sph = (uint32_t)(g / S) & 1u;
+                        mbar_wait(&full[slot], sph);
+                        tc_fence_after();
+                        const uint64_t da = dA0 + (uint64_t)((uint32_t)slot * slotA16);
+                        const uint64_t db = dB0 + (uint64_t)((uint32_t)slot * slotB16);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int j = 0; j < KC / 8; ++j) {
+                                mma_tf32_ss(dcol, da + j * kA16, db + j * kB16, idesc, acc);
+                                mma_tf32_ss(dcol, da + loA16 + j * kA16, db + j * kB16, idesc, 1u);
+                                mma_tf32_ss(dcol, da + j * kA16, db + loB16 + j * kB16, idesc, 1u);
+                                acc = 1u;
+                            }
+                            mma_commit(&empty[slot]);
+                        }
+                        acc = 1u;
+                        __syncwarp();
+                    }
+                    if (elect_one()) mma_commit(&accf[b]);
+                    __syncwarp();
                 }
+                g0 += nit;
             }
-            if (nit > 0 && elect_one()) mma_commit(accum);
-            __syncwarp();
         }
-    } else {
+    } else if (warp == TC_W_WEIGHT) {
         // ========== weight loader (one thread): one bulk copy per stage ==========
         if (lane == 0) {
-            int slot = 0, kk = 0, c = 0;
-            uint32_t ph = 0;
-            for (int it = 0; it < nit; ++it) {
-                const int kw = p.pairs_mode ? kfixed : s_klist[kk];
-                mbar_wait(&empty[slot], ph ^ 1u);
-                mbar_arrive_expect_tx(&full[slot], p.stageB_bytes);
-                bulk_g2s(sB + (size_t)slot * p.stageB_bytes,
-                         reinterpret_cast<const unsigned char*>(p.Wp) + ((size_t)kw * nchunks + c) * p.stageB_bytes,
-                         p.stageB_bytes, &full[slot]);
-                if (++c == nchunks) {
-                    c = 0;
-                    ++kk;
+            int slot = 0;
+            uint32_t sph = 0;
+            for (int i = 0; i < ntiles; ++i) {
+                const int b = i & 1;
+                mbar_wait(&tready[b], (uint32_t)(i >> 1) & 1u);
+                const int nk = TC_NK(b);
+                const int kfixed = TC_KFIX(b);
+                const int* klist = TC_KLIST(b);
+                for (int kk = 0; kk < nk; ++kk) {
+                    const int kw = p.pairs_mode ? kfixed : klist[kk];
+                    for (int c = 0; c < nchunks; ++c) {
+                        mbar_wait(&empty[slot], sph ^ 1u);
+                        mbar_arrive_expect_tx(&full[slot], p.stageB_bytes);
+                        bulk_g2s(sB + (size_t)slot * p.stageB_bytes,
+                                 reinterpret_cast<const unsigned char*>(p.Wp) + ((size_t)kw * nchunks + c) * p.stageB_bytes,
+                                 p.stageB_bytes, &full[slot]);
+                        if (++slot == S) {
+                            slot = 0;
+                            sph ^= 1u;
+                        }
+                    }
                 }
-                if (++slot == S) {
-                    slot = 0;
-                    ph ^= 1u;
-                }
+                mbar_arrive(&tfree[b]);
             }
         }
     }
+#undef TC_META
+#undef TC_IDX
+#undef TC_OROW
+#undef TC_KLIST
+#undef TC_NK
+#undef TC_KFIX
     tc_fence_before();
     __syncthreads();
-    if (warp == TC_WARP_MMA) tmem_dealloc(tmem, p.tmem_cols);
+    if (warp == TC_W_MMA) tmem_dealloc(tmem, p.tmem_cols);
 }
 
 // W [K][Ci_w][Co_w] fp32 -> per (offset, chunk) {hi, lo} blocks in the canonical K-major B layout.
@@ -422,17 +515,15 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
     pl.Cout_pad = (Cout + 15) / 16 * 16;
     if (pl.Cout_pad > 256) return false;
     pl.stageB = 2u * (uint32_t)pl.Cout_pad * pl.KC * 4u;
-    uint32_t cols = 32;  // refined below once the issuer count is known
-    pl.tmem_cols = cols;
     pl.wp_bytes = (int64_t)K * pl.nchunks * pl.stageB;
     const uint32_t cpr = (uint32_t)pl.KC / 4u;
     const uint32_t a_bytes = 2u * ((cpr * (TC_BM * 16u + 128u / cpr) + 127u) & ~127u);
-    // slots: aim for ~4-6 stages in flight, stay under ~100 KB so two CTAs can share an SM when the tile is small
+    const uint32_t fixed = TC_NBUF * (uint32_t)(TC_BM * KT + TC_BM + TC_MAXK + 4) * 4u + 512u;
+    // slots: 4 under ~110 KB lets two CTAs share an SM; big stages fall back to fewer slots / one CTA per SM
     int best = 0;
-    for (int s = 6; s >= 2; --s) {
-        uint32_t tot = (uint32_t)s * (a_bytes + pl.stageB) + (uint32_t)(TC_BM * KT + TC_BM + 2 * TC_MAXK + 4) * 4u + 64u +
-                       (uint32_t)(3 * s + 1) * 8u + 32u;
-        if (tot <= 100u * 1024u || (s <= 3 && tot <= 200u * 1024u)) {
+    for (int s = 4; s >= 2; --s) {
+        const uint32_t tot = (uint32_t)s * (a_bytes + pl.stageB) + fixed;
+        if (tot <= 110u * 1024u || (s <= 3 && tot <= 220u * 1024u)) {
             best = s;
             break;
         }
@@ -440,25 +531,26 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
     if (best == 0) return false;
     pl.nslots = best;
     // issuer warps: each smem slot must belong to exactly ONE issuer (its mbarrier waits are parity waits, an issuer
-    // running a fill ahead of a slot it shares would alias phases), so ni divides nslots; one accumulator per issuer
+    // running a fill ahead of a slot it shares would alias phases), so ni divides nslots; two accumulator sets
     {
         const char* e = getenv("B200SP_TC_ISSUERS");
         const int want = std::max(1, std::min(e ? atoi(e) : TC_MAX_ISSUERS, TC_MAX_ISSUERS));
-        pl.ni = 1;
+        pl.ni = 0;
         for (int ni = want; ni >= 1; --ni)
-            if (best % ni == 0 && ni * pl.Cout_pad <= 512) {
+            if (best % ni == 0 && TC_NBUF * ni * pl.Cout_pad <= 512) {
                 pl.ni = ni;
                 break;
             }
+        if (pl.ni == 0) return false;
     }
-    cols = 32;
-    while (cols < (uint32_t)(pl.ni * pl.Cout_pad)) cols <<= 1;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(TC_NBUF * pl.ni * pl.Cout_pad)) cols <<= 1;
     pl.tmem_cols = cols;
     return true;
 }
 
 template <int KC>
-static int launch_tc(const TCParams& p, int KT, dim3 grid, cudaStream_t st) {
+static int launch_tc(const TCParams& p, int KT, cudaStream_t st) {
     using L = TCLayout<KC>;
     const uint32_t smem = L::total(p.nslots, p.stageB_bytes, KT);
     static uint32_t attr_smem = 0;
@@ -466,6 +558,10 @@ static int launch_tc(const TCParams& p, int KT, dim3 grid, cudaStream_t st) {
         B200SP_CUDA(cudaFuncSetAttribute(k_conv_tc<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
+    // persistent grid: as many CTAs as fit on the machine (TMEM: 512 columns per SM), never more than tiles
+    int occ = smem <= 110u * 1024u ? 2 : 1;
+    while (occ > 1 && (uint32_t)occ * p.tmem_cols > 512u) --occ;
+    const int grid = std::min(p.total_tiles, num_sms() * occ);
     k_conv_tc<KC><<<grid, TC_THREADS, smem, st>>>(p);
     B200SP_LAUNCH_CHECK();
     return B200SP_OK;
@@ -473,9 +569,8 @@ static int launch_tc(const TCParams& p, int KT, dim3 grid, cudaStream_t st) {
 
 // returns B200SP_EUNSUP when the shape is outside what the tensor path covers (caller falls back to the fp32 kernel)
 int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, int wflags, const int* tab, const int* orow,
-                const int* pin,
-                const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out, int Cout,
-                int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                const int* pin, const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out,
+                int Cout, int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st) {
     TCPlan pl;
     const int KT = pairs_mode ? 1 : K;
     if (!tc_plan(K, Cin, Cout, KT, pl)) return B200SP_EUNSUP;
@@ -483,6 +578,7 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
         set_error("conv_tc: workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)pl.wp_bytes);
         return B200SP_ENOMEM;
     }
+    if (cdiv(n_rows, TC_BM) * (pairs_mode ? K : 1) > (int64_t)1 << 30) return B200SP_EUNSUP;
     float* Wp = static_cast<float*>(ws);
     {
         const int64_t total = (int64_t)K * pl.nchunks * pl.Cout_pad * pl.KC;
@@ -496,10 +592,11 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
     p.n_rows = n_rows; p.pstride = pstride; p.Cin = Cin; p.Cout = Cout; p.K = K;
     p.nchunks = pl.nchunks; p.Cout_pad = pl.Cout_pad; p.accumulate = accumulate; p.pairs_mode = pairs_mode;
     p.nslots = pl.nslots; p.stageB_bytes = pl.stageB; p.tmem_cols = pl.tmem_cols; p.ni = pl.ni;
-    dim3 grid((unsigned)cdiv(n_rows, TC_BM), 1, pairs_mode ? (unsigned)K : 1u);
-    if (pl.KC == 32) return launch_tc<32>(p, KT, grid, st);
-    if (pl.KC == 16) return launch_tc<16>(p, KT, grid, st);
-    return launch_tc<8>(p, KT, grid, st);
+    p.row_tiles = (int)cdiv(n_rows, TC_BM);
+    p.total_tiles = p.row_tiles * (pairs_mode ? K : 1);
+    if (pl.KC == 32) return launch_tc<32>(p, KT, st);
+    if (pl.KC == 16) return launch_tc<16>(p, KT, st);
+    return launch_tc<8>(p, KT, st);
 }
 
 int64_t conv_tc_ws_bytes(int K, int Cin, int Cout) {
