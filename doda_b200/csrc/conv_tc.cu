@@ -67,6 +67,7 @@ struct TCParams {
     int ni;                 // MMA issuer warps in use (accumulators per set)
     int row_tiles;          // ceil(n_rows / 128)
     int total_tiles;        // row_tiles * (pairs_mode ? K : 1)
+    int dbg;                // dev only: 1 = skip the MMAs, 2 = skip the gathers, 4 = skip the transform
 };
 
 template <int KC>
@@ -84,7 +85,7 @@ struct TCLayout {
         return (o + 15u) & ~15u;
     }
     __host__ __device__ static uint32_t total(int nslots, uint32_t stageB, int KT) {
-        return offBars(nslots, stageB, KT) + (uint32_t)(3 * nslots + 4 * TC_NBUF) * 8u + 16u;
+        return offBars(nslots, stageB, KT) + (uint32_t)(3 * nslots + 5 * TC_NBUF) * 8u + 16u;
     }
 };
 
@@ -125,7 +126,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
     uint64_t* tfree = tready + TC_NBUF;   // [NBUF] every reader is done with the tile metadata
     uint64_t* accf = tfree + TC_NBUF;     // [NBUF] accumulator set complete -> epilogue
     uint64_t* acce = accf + TC_NBUF;      // [NBUF] accumulator set drained -> issuers
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acce + TC_NBUF);
+    uint64_t* tload = acce + TC_NBUF;     // [NBUF] bulk copy of the tile's table rows landed (prefetcher only)
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tload + TC_NBUF);
 
     const int ntiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             mbar_init(&tfree[b], TC_LOADERS + 4 /*xform warps*/ + 4 /*epilogue warps*/ + ni + 1 /*weights*/);
             mbar_init(&accf[b], ni);
             mbar_init(&acce[b], 4);
+            mbar_init(&tload[b], 1);
         }
         mbar_fence_init();
     }
@@ -188,15 +191,36 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                 const int64_t row0 = (int64_t)tile * TC_BM;
                 const int rows = (int)min((int64_t)TC_BM, p.n_rows - row0);
                 unsigned mask = 0;
+                {
+                    int ov[TC_BM / 32];
+#pragma unroll
+                    for (int q = 0; q < TC_BM / 32; ++q) {
+                        const int r = lane + 32 * q;
+                        ov[q] = r < rows ? (p.orow ? __ldg(p.orow + row0 + r) : (int)(row0 + r)) : -1;
+                    }
+#pragma unroll
+                    for (int q = 0; q < TC_BM / 32; ++q) orow[lane + 32 * q] = ov[q];
+                }
                 if (p.tab) {
                     const int* t = p.tab + row0 * K;
                     const int tot = rows * K;
-                    int kk = lane % K;  // column of element i = lane, lane+32, ...
+                    const uint32_t bytes = (uint32_t)tot * 4u;
+                    if (rows == TC_BM && (bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(t) & 15) == 0)) {
+                        // full tile: one bulk copy of the 128 x K table rows, then the offset mask from shared memory
+                        if (lane == 0) {
+                            mbar_arrive_expect_tx(&tload[b], bytes);
+                            bulk_g2s(idx, t, bytes, &tload[b]);
+                        }
+                        mbar_wait(&tload[b], ph);
+                    } else {
+                        for (int e = lane; e < TC_BM * K; e += 32) idx[e] = e < tot ? __ldg(t + e) : -1;
+                        if (lane == 0) mbar_arrive(&tload[b]);  // keep the phase of this buffer's barrier in step
+                        __syncwarp();
+                    }
+                    int kk = lane % K;  // column of element e = lane, lane+32, ...
                     const int step = 32 % K;
                     for (int e = lane; e < TC_BM * K; e += 32) {
-                        const int v = e < tot ? __ldg(t + e) : -1;
-                        idx[e] = v;
-                        if (v >= 0) mask |= 1u << kk;
+                        if (idx[e] >= 0) mask |= 1u << kk;
                         kk += step;
                         if (kk >= K) kk -= K;
                     }
@@ -204,8 +228,6 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                     for (int r = lane; r < TC_BM; r += 32) idx[r] = r < rows ? (int)(row0 + r) : -1;
                     mask = rows > 0 ? 1u : 0u;
                 }
-                for (int r = lane; r < TC_BM; r += 32)
-                    orow[r] = r < rows ? (p.orow ? __ldg(p.orow + row0 + r) : (int)(row0 + r)) : -1;
 #pragma unroll
                 for (int o = 16; o; o >>= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
                 if (lane == 0) {
@@ -240,7 +262,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                     const int c0 = c * KC;
                     const uint32_t dst0 = smem_u32(sA + (size_t)slot * 2 * L::A_BYTES);
                     mbar_wait(&empty[slot], sph ^ 1u);
-                    if (vec) {
+                    if (p.dbg & 2) {
+                    } else if (vec) {
                         // thread-constant: chunk j and row phase; q only advances the 8-row group
                         const int j = lt % CPR, rowb = lt / CPR;
                         constexpr int RPQ = TC_LOADERS / CPR;  // rows covered per pass (multiple of 8)
@@ -294,7 +317,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                 unsigned char* a_lo = a_hi + L::A_BYTES;
                 mbar_wait(&raw[slot], sph);
 #pragma unroll
-                for (int q = 0; q < NV; ++q) {
+                for (int q = 0; q < ((p.dbg & 4) ? 0 : NV); ++q) {
                     const uint32_t off = (uint32_t)q * L::LBO + soff;
                     const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
                     float4 h, l;
@@ -318,6 +341,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
         const int q4 = warp - TC_W_EPI;
         const bool vecO = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
         int g0 = 0;  // global stage number of the tile's first stage
+        uint32_t aph[TC_NBUF] = {0, 0};  // phase of each accumulator set = number of NON-EMPTY tiles it served (mod 2)
         for (int i = 0; i < ntiles; ++i) {
             const int b = i & 1;
             const uint32_t ph = (uint32_t)(i >> 1) & 1u;
@@ -327,7 +351,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&tfree[b]);
             if (nit > 0) {
-                mbar_wait(&accf[b], ph);
+                mbar_wait(&accf[b], aph[b]);
+                aph[b] ^= 1u;
                 tc_fence_after();
             }
             const int nused = min(ni, nit);
@@ -388,6 +413,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             const uint32_t slotA16 = (2u * L::A_BYTES) >> 4, loA16 = L::A_BYTES >> 4, kA16 = (2u * L::LBO) >> 4;
             const uint32_t slotB16 = p.stageB_bytes >> 4, loB16 = p.stageB_bytes >> 5, kB16 = (2u * lboB) >> 4;
             int g0 = 0;
+            uint32_t aph[TC_NBUF] = {0, 0};  // as in the epilogue: empty tiles do not touch the accumulator barriers
             for (int i = 0; i < ntiles; ++i) {
                 const int b = i & 1;
                 const uint32_t ph = (uint32_t)(i >> 1) & 1u;
@@ -396,7 +422,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tfree[b]);
                 if (nit > 0) {
-                    mbar_wait(&acce[b], ph ^ 1u);  // the epilogue drained this accumulator set
+                    mbar_wait(&acce[b], aph[b] ^ 1u);  // the epilogue drained this accumulator set
+                    aph[b] ^= 1u;
                     tc_fence_after();
                     const uint32_t dcol = tmem + (uint32_t)((b * ni + w) * p.Cout_pad);
                     uint32_t acc = 0;
@@ -411,7 +438,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                         const uint64_t db = dB0 + (uint64_t)((uint32_t)slot * slotB16);
                         if (elect_one()) {
 #pragma unroll
-                            for (int j = 0; j < KC / 8; ++j) {
+                            for (int j = 0; j < ((p.dbg & 1) ? 0 : KC / 8); ++j) {
                                 mma_tf32_ss(dcol, da + j * kA16, db + j * kB16, idesc, acc);
                                 mma_tf32_ss(dcol, da + loA16 + j * kA16, db + j * kB16, idesc, 1u);
                                 mma_tf32_ss(dcol, da + j * kA16, db + loB16 + j * kB16, idesc, 1u);
@@ -592,6 +619,10 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
     p.n_rows = n_rows; p.pstride = pstride; p.Cin = Cin; p.Cout = Cout; p.K = K;
     p.nchunks = pl.nchunks; p.Cout_pad = pl.Cout_pad; p.accumulate = accumulate; p.pairs_mode = pairs_mode;
     p.nslots = pl.nslots; p.stageB_bytes = pl.stageB; p.tmem_cols = pl.tmem_cols; p.ni = pl.ni;
+    {
+        const char* e = getenv("B200SP_TC_DEBUG");
+        p.dbg = e ? atoi(e) : 0;
+    }
     p.row_tiles = (int)cdiv(n_rows, TC_BM);
     p.total_tiles = p.row_tiles * (pairs_mode ? K : 1);
     if (pl.KC == 32) return launch_tc<32>(p, KT, st);

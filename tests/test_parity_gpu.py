@@ -129,6 +129,13 @@ def test_subm_conv_large_tiles(cuda_dev):
     _conv_case(cuda_dev, "subm", 64, 64, n=12000, shape=(64, 64, 32))
 
 
+@pytest.mark.parametrize("kind,Cin,Cout", [("subm", 16, 16), ("subm", 32, 48), ("down", 16, 32), ("inverse", 32, 16)])
+def test_conv_many_tiles_per_cta(cuda_dev, kind, Cin, Cout):
+    """> 2 x 148 x 128 rows: the persistent conv kernel walks several tiles per CTA (cross-tile pipelining, both
+    accumulator sets, empty tiles in the pair-grouped mode); checked against the fp64 oracle"""
+    _conv_case(cuda_dev, kind, Cin, Cout, seed=7, n=45000, shape=(96, 96, 64))
+
+
 def test_conv1x1_fwd_bwd(cuda_dev):
     from doda_b200 import ops
     torch.manual_seed(0)
