@@ -67,6 +67,7 @@ struct TCParams {
     int ni;                 // MMA issuer warps in use (accumulators per set)
     int row_tiles;          // ceil(n_rows / 128)
     int total_tiles;        // row_tiles * (pairs_mode ? K : 1)
+    int nsplit;             // table mode: the active offsets of a row tile are dealt to nsplit CTAs (atomic epilogue)
     int dbg;                // dev only: 1 = skip the MMAs, 2 = skip the gathers, 4 = skip the transform
 };
 
@@ -188,7 +189,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                     TC_KFIX(b) = kf;
                 }
             } else {
-                const int64_t row0 = (int64_t)tile * TC_BM;
+                const int rt = tile / p.nsplit, split = tile - rt * p.nsplit;
+                const int64_t row0 = (int64_t)rt * TC_BM;
                 const int rows = (int)min((int64_t)TC_BM, p.n_rows - row0);
                 unsigned mask = 0;
                 {
@@ -231,9 +233,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
 #pragma unroll
                 for (int o = 16; o; o >>= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
                 if (lane == 0) {
-                    int nk = 0;
+                    int nk = 0, pos = 0;
                     for (int k = 0; k < K; ++k)
-                        if (mask >> k & 1u) klist[nk++] = k;
+                        if (mask >> k & 1u) {
+                            if (pos % p.nsplit == split) klist[nk++] = k;  // this CTA's share of the active offsets
+                            ++pos;
+                        }
                     TC_NK(b) = nk;
                     TC_KFIX(b) = 0;
                 }
@@ -357,7 +362,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             }
             const int nused = min(ni, nit);
             const uint32_t set_col = tmem + (uint32_t)(b * ni * p.Cout_pad);
-            for (int ch = 0; ch * 16 < p.Cout_pad; ++ch) {
+            const bool split_mode = p.nsplit > 1;
+            for (int ch = 0; ch * 16 < ((split_mode && nit == 0) ? 0 : p.Cout_pad); ++ch) {
                 float v[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) v[e] = 0.f;
@@ -374,7 +380,16 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                 for (int g4 = 0; g4 < 4; ++g4) {
                     const int col = ch * 16 + g4 * 4;
                     if (col >= Cout) break;
-                    if (vecO) {
+                    if (split_mode) {
+                        if (vecO) {
+                            atomicAdd(reinterpret_cast<float4*>(o + g4 * 4),
+                                      make_float4(v[g4 * 4 + 0], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]));
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                if (col + e < Cout) atomicAdd(o + g4 * 4 + e, v[g4 * 4 + e]);
+                        }
+                    } else if (vecO) {
                         float4 wv = make_float4(v[g4 * 4 + 0], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
                         if (p.accumulate) {
                             const float4 old = *reinterpret_cast<const float4*>(o + g4 * 4);
@@ -624,7 +639,15 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
         p.dbg = e ? atoi(e) : 0;
     }
     p.row_tiles = (int)cdiv(n_rows, TC_BM);
-    p.total_tiles = p.row_tiles * (pairs_mode ? K : 1);
+    // few row tiles (deep U-Net levels): deal each tile's active offsets to nsplit CTAs so the machine is not idle
+    // behind two or three serial tiles; the partial sums meet in the output through float4 atomics
+    p.nsplit = 1;
+    if (!pairs_mode && tab && K > 1 && p.row_tiles * 2 <= num_sms()) {
+        const char* e = getenv("B200SP_TC_NOSPLIT");
+        if (!(e && atoi(e))) p.nsplit = std::max(1, std::min(K, 2 * num_sms() / p.row_tiles));
+    }
+    if (p.nsplit > 1 && !accumulate) B200SP_CUDA(cudaMemsetAsync(out, 0, (size_t)n_rows * Cout * sizeof(float), st));
+    p.total_tiles = p.row_tiles * (pairs_mode ? K : p.nsplit);
     if (pl.KC == 32) return launch_tc<32>(p, KT, st);
     if (pl.KC == 16) return launch_tc<16>(p, KT, st);
     return launch_tc<8>(p, KT, st);

@@ -18,14 +18,36 @@ constexpr int BN_MAXGRID = 592;  // 4 CTAs x 148 SMs
 // MODE 0: q0 = sum x, q1 = sum x^2                       (BN forward statistics)
 // MODE 1: q0 = sum g, q1 = sum g*xhat,  g = dy * relu'   (BN backward)
 // ---------------------------------------------------------------------------------------------
+// everything the LAST block of the reduction needs to finish the layer's statistics in the same launch
+struct BNFinal {
+    unsigned* ticket;  // zero before the launch; the last block resets it
+    int64_t M;
+    const float* w;
+    const float* b;
+    float eps, momentum;
+    float* mean;
+    float* invstd;
+    float* running_mean;
+    float* running_var;
+    long long* num_batches_tracked;
+    float* scale;
+    float* shift;
+    float* dw;
+    float* db;
+    float* c_g;
+    float* c_mean_g;
+    float* c_mean_gx;
+};
+
 template <int VEC, int MODE>
 __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restrict__ x, const float* __restrict__ dy,
                                                           int64_t M, int C, const float* __restrict__ scale,
                                                           const float* __restrict__ shift,
                                                           const float* __restrict__ mean,
                                                           const float* __restrict__ invstd, int relu,
-                                                          float* __restrict__ partial) {
+                                                          float* __restrict__ partial, BNFinal fin) {
     extern __shared__ float s_part[];  // [2][rpb][C]
+    __shared__ int s_last;
     const int CG = C / VEC;
     const int rpb = BN_THREADS / CG;
     const int tid = threadIdx.x;
@@ -36,13 +58,15 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restric
     for (int v = 0; v < VEC; ++v) a0[v] = a1[v] = 0.f;
     float sc[VEC], sh[VEC], mu[VEC], is[VEC];
     if (MODE == 1 && active) {
+        (void)scale;
+        (void)shift;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
             int c = cg * VEC + v;
-            sc[v] = scale[c];
-            sh[v] = shift[c];
             mu[v] = mean[c];
             is[v] = invstd[c];
+            sc[v] = (fin.w ? fin.w[c] : 1.f) * is[v];  // the forward's fused scale / shift, recomputed per block
+            sh[v] = (fin.b ? fin.b[c] : 0.f) - mu[v] * sc[v];
         }
     }
     if (active) {
@@ -85,57 +109,60 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restric
         for (int r = 0; r < rpb; ++r) s += s_part[(q * rpb + r) * C + c];
         partial[((int64_t)blockIdx.x * 2 + q) * C + c] = s;
     }
-}
-
-// forward finalize: mean / invstd / unbiased var, and the fused scale/shift used by the apply pass
-__global__ void k_bn_finalize_fwd(const float* __restrict__ partial, int G, int64_t M, int C,
-                                  const float* __restrict__ w, const float* __restrict__ b, float eps,
-                                  float* __restrict__ mean, float* __restrict__ invstd,
-                                  float* __restrict__ running_mean, float* __restrict__ running_var,
-                                  float momentum, long long* __restrict__ num_batches_tracked,
-                                  float* __restrict__ scale, float* __restrict__ shift) {
-    // one warp per channel: lanes stride over the G per-block partials, fp64 shuffle reduction
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (c == 0 && lane == 0 && num_batches_tracked) *num_batches_tracked += 1;
-    if (c >= C) return;
-    double s = 0.0, ss = 0.0;
-    for (int g = lane; g < G; g += 32) {
-        s += partial[((int64_t)g * 2 + 0) * C + c];
-        ss += partial[((int64_t)g * 2 + 1) * C + c];
+    // ---- last block to finish folds the per-block partials (one warp per channel, fp64) and finalises ----
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(fin.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int G = gridDim.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int c = warp; c < C; c += BN_THREADS / 32) {
+        double s0 = 0.0, s1 = 0.0;
+        for (int g = lane; g < G; g += 32) {
+            s0 += __ldcg(&partial[((int64_t)g * 2 + 0) * C + c]);
+            s1 += __ldcg(&partial[((int64_t)g * 2 + 1) * C + c]);
+        }
+        for (int o = 16; o; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        }
+        if (lane != 0) continue;
+        if (MODE == 0) {
+            const double mu = s0 / (double)fin.M;
+            double var = s1 / (double)fin.M - mu * mu;
+            if (var < 0.0) var = 0.0;
+            const float is = (float)(1.0 / sqrt(var + (double)fin.eps));
+            fin.mean[c] = (float)mu;
+            fin.invstd[c] = is;
+            // running statistics exactly as F.batch_norm: unbiased variance, exponential average
+            if (fin.running_mean) fin.running_mean[c] = (1.f - fin.momentum) * fin.running_mean[c] + fin.momentum * (float)mu;
+            if (fin.running_var) {
+                const float vu = (float)(fin.M > 1 ? var * (double)fin.M / (double)(fin.M - 1) : var);
+                fin.running_var[c] = (1.f - fin.momentum) * fin.running_var[c] + fin.momentum * vu;
+            }
+            const float wv = fin.w ? fin.w[c] : 1.f, bv = fin.b ? fin.b[c] : 0.f;
+            const float scv = wv * is;
+            fin.scale[c] = scv;
+            fin.shift[c] = bv - (float)mu * scv;
+        } else {
+            if (fin.dw) fin.dw[c] = (float)s1;
+            if (fin.db) fin.db[c] = (float)s0;
+            const float wv = fin.w ? fin.w[c] : 1.f;
+            const float isv = invstd[c];
+            fin.c_g[c] = wv * isv;
+            fin.c_mean_g[c] = (float)(s0 / (double)fin.M);
+            fin.c_mean_gx[c] = (float)(s1 / (double)fin.M);
+            const float scv = wv * isv;
+            fin.scale[c] = scv;
+            fin.shift[c] = (fin.b ? fin.b[c] : 0.f) - mean[c] * scv;
+        }
     }
-    for (int o = 16; o; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (tid == 0) {
+        *fin.ticket = 0u;  // ready for the next launch on this workspace
+        if (MODE == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
     }
-    if (lane != 0) return;
-    double mu = s / (double)M;
-    double var = ss / (double)M - mu * mu;
-    if (var < 0.0) var = 0.0;
-    float is = (float)(1.0 / sqrt(var + (double)eps));
-    mean[c] = (float)mu;
-    invstd[c] = is;
-    // running statistics exactly as F.batch_norm: unbiased variance, exponential average
-    if (running_mean) running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
-    if (running_var) {
-        float vu = (float)(M > 1 ? var * (double)M / (double)(M - 1) : var);
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * vu;
-    }
-    float wv = w ? w[c] : 1.f, bv = b ? b[c] : 0.f;
-    float sc = wv * is;
-    scale[c] = sc;
-    shift[c] = bv - (float)mu * sc;
-}
-
-__global__ void k_bn_scale_shift(const float* __restrict__ w, const float* __restrict__ b,
-                                 const float* __restrict__ mean, const float* __restrict__ invstd, int C,
-                                 float* __restrict__ scale, float* __restrict__ shift) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float wv = w ? w[c] : 1.f, bv = b ? b[c] : 0.f;
-    float sc = wv * invstd[c];
-    scale[c] = sc;
-    shift[c] = bv - mean[c] * sc;
 }
 
 // y = [relu](x*scale + shift)
@@ -165,31 +192,6 @@ __global__ void __launch_bounds__(256) k_affine_relu(const float* __restrict__ x
 }
 
 // backward finalize: dw = sum g*xhat, db = sum g; coefficient rows for the apply pass
-__global__ void k_bn_finalize_bwd(const float* __restrict__ partial, int G, int64_t M, int C,
-                                  const float* __restrict__ w, const float* __restrict__ invstd,
-                                  float* __restrict__ dw, float* __restrict__ db, float* __restrict__ c_g,
-                                  float* __restrict__ c_mean_g, float* __restrict__ c_mean_gx) {
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (c >= C) return;
-    double sg = 0.0, sgx = 0.0;
-    for (int g = lane; g < G; g += 32) {
-        sg += partial[((int64_t)g * 2 + 0) * C + c];
-        sgx += partial[((int64_t)g * 2 + 1) * C + c];
-    }
-    for (int o = 16; o; o >>= 1) {
-        sg += __shfl_xor_sync(0xffffffffu, sg, o);
-        sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
-    }
-    if (lane != 0) return;
-    if (dw) dw[c] = (float)sgx;
-    if (db) db[c] = (float)sg;
-    float wv = w ? w[c] : 1.f;
-    c_g[c] = wv * invstd[c];
-    c_mean_g[c] = (float)(sg / (double)M);
-    c_mean_gx[c] = (float)(sgx / (double)M);
-}
-
 // dx = w*invstd * (g - mean(g) - xhat*mean(g*xhat))
 template <int VEC>
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ dy,
@@ -314,7 +316,9 @@ using namespace b200sp;
 
 extern "C" int64_t b200sp_bn_ws_bytes(int64_t M, int C) {
     (void)M;
-    return (int64_t)sizeof(float) * ((int64_t)BN_MAXGRID * 2 * C + 8 * (int64_t)C) + 1024;
+    // ticket (first 256 bytes, same place for every C) | partials | scale, shift, c_g, c_mean_g, c_mean_gx.  The caller
+    // zero-fills the workspace ONCE; every launch leaves the ticket at zero again
+    return (int64_t)sizeof(float) * ((int64_t)BN_MAXGRID * 2 * C + 8 * (int64_t)C) + 1024 + 256;
 }
 
 static int bn_grid(int64_t M, int C, int VEC) {
@@ -335,25 +339,27 @@ extern "C" int b200sp_bn_fwd_train(const float* x, int64_t M, int C, const float
     B200SP_CHECK_ARG(ws_bytes >= b200sp_bn_ws_bytes(M, C), "bn_fwd_train: workspace too small");
     const bool v4 = vec4_ok(C, x, y) && C / 4 <= BN_THREADS;
     B200SP_CHECK_ARG(v4 || C <= BN_THREADS, "bn_fwd_train: C=%d unsupported", C);
-    float* partial = (float*)ws;
+    float* partial = (float*)ws + 64;
     float* scale = partial + (int64_t)BN_MAXGRID * 2 * C;
     float* shift = scale + C;
     int VEC = v4 ? 4 : 1;
     int G = bn_grid(M, C, VEC);
     int rpb = BN_THREADS / (C / VEC);
     size_t smem = sizeof(float) * 2 * rpb * C;
+    BNFinal fin{};
+    fin.ticket = reinterpret_cast<unsigned*>(ws);
+    fin.M = M; fin.w = w; fin.b = b; fin.eps = eps; fin.momentum = momentum; fin.mean = mean; fin.invstd = invstd;
+    fin.running_mean = running_mean; fin.running_var = running_var;
+    fin.num_batches_tracked = (long long*)num_batches_tracked; fin.scale = scale; fin.shift = shift;
     if (v4)
-        k_bn_reduce<4, 0><<<G, BN_THREADS, smem, st>>>(x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, partial);
+        k_bn_reduce<4, 0><<<G, BN_THREADS, smem, st>>>(x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, partial, fin);
     else
-        k_bn_reduce<1, 0><<<G, BN_THREADS, smem, st>>>(x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, partial);
-    k_bn_finalize_fwd<<<(unsigned)cdiv(C, 4), 128, 0, st>>>(partial, G, M, C, w, b, eps, mean, invstd, running_mean,
-                                                             running_var, momentum,
-                                                             (long long*)num_batches_tracked, scale, shift);
+        k_bn_reduce<1, 0><<<G, BN_THREADS, smem, st>>>(x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, partial, fin);
     if (v4)
         k_affine_relu<4><<<stream_grid(M * (C / 4), 256), 256, 0, st>>>(x, M, C, scale, shift, relu, y);
     else
         k_affine_relu<1><<<stream_grid(M * C, 256), 256, 0, st>>>(x, M, C, scale, shift, relu, y);
-    B200SP_LAUNCH_CHECK_N(3);
+    B200SP_LAUNCH_CHECK_N(2);
     return B200SP_OK;
 }
 
@@ -378,7 +384,7 @@ extern "C" int b200sp_bn_bwd(const float* x, const float* dy, int64_t M, int C, 
     B200SP_CHECK_ARG(ws_bytes >= b200sp_bn_ws_bytes(M, C), "bn_bwd: workspace too small");
     const bool v4 = vec4_ok(C, x, dy, dx) && C / 4 <= BN_THREADS;
     B200SP_CHECK_ARG(v4 || C <= BN_THREADS, "bn_bwd: C=%d unsupported", C);
-    float* partial = (float*)ws;
+    float* partial = (float*)ws + 64;
     float* scale = partial + (int64_t)BN_MAXGRID * 2 * C;
     float* shift = scale + C;
     float* c_g = shift + C;
@@ -388,19 +394,21 @@ extern "C" int b200sp_bn_bwd(const float* x, const float* dy, int64_t M, int C, 
     int G = bn_grid(M, C, VEC);
     int rpb = BN_THREADS / (C / VEC);
     size_t smem = sizeof(float) * 2 * rpb * C;
-    k_bn_scale_shift<<<(unsigned)cdiv(C, 128), 128, 0, st>>>(w, b, mean, invstd, C, scale, shift);
+    BNFinal fin{};
+    fin.ticket = reinterpret_cast<unsigned*>(ws);
+    fin.M = M; fin.w = w; fin.b = b; fin.scale = scale; fin.shift = shift; fin.dw = dw; fin.db = db;
+    fin.c_g = c_g; fin.c_mean_g = c_mg; fin.c_mean_gx = c_mgx;
     if (v4)
-        k_bn_reduce<4, 1><<<G, BN_THREADS, smem, st>>>(x, dy, M, C, scale, shift, mean, invstd, relu, partial);
+        k_bn_reduce<4, 1><<<G, BN_THREADS, smem, st>>>(x, dy, M, C, nullptr, nullptr, mean, invstd, relu, partial, fin);
     else
-        k_bn_reduce<1, 1><<<G, BN_THREADS, smem, st>>>(x, dy, M, C, scale, shift, mean, invstd, relu, partial);
-    k_bn_finalize_bwd<<<(unsigned)cdiv(C, 4), 128, 0, st>>>(partial, G, M, C, w, invstd, dw, db, c_g, c_mg, c_mgx);
+        k_bn_reduce<1, 1><<<G, BN_THREADS, smem, st>>>(x, dy, M, C, nullptr, nullptr, mean, invstd, relu, partial, fin);
     if (v4)
         k_bn_bwd_apply<4><<<stream_grid(M * (C / 4), 256), 256, 0, st>>>(x, dy, M, C, scale, shift, mean, invstd, c_g,
                                                                         c_mg, c_mgx, relu, dx);
     else
         k_bn_bwd_apply<1><<<stream_grid(M * C, 256), 256, 0, st>>>(x, dy, M, C, scale, shift, mean, invstd, c_g, c_mg,
                                                                   c_mgx, relu, dx);
-    B200SP_LAUNCH_CHECK_N(4);
+    B200SP_LAUNCH_CHECK_N(2);
     return B200SP_OK;
 }
 

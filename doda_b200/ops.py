@@ -13,7 +13,13 @@ _I32 = torch.int32
 _F32 = torch.float32
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    # torch.cuda.current_stream() costs ~10 us of Python per call; the raw getter is ~0.3 us
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -84,12 +90,24 @@ class _Timed(object):
 _ws = {}
 
 
+_ws_bytes_cache = {}
+
+
+def _conv_ws_bytes(K, Cin, Cout):
+    key = (K, Cin, Cout)
+    v = _ws_bytes_cache.get(key)
+    if v is None:
+        v = _ws_bytes_cache[key] = int(lib.b200sp_conv_ws_bytes(K, Cin, Cout))
+    return v
+
+
 def _workspace(nbytes, device, tag):
     """Grow-only scratch buffer per (device, tag); safe because all launches are ordered on one stream."""
-    key = (device.index, tag, torch.cuda.current_stream().cuda_stream)
+    key = (device.index, tag, _stream())
     buf = _ws.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        # zero-filled: the BN kernels keep a completion ticket in their workspace that must start at zero
+        buf = torch.zeros(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
         _ws[key] = buf
     return buf
 
@@ -134,9 +152,42 @@ def conv_out_shape(shape, ksize, stride, padding, dilation):
 mask_order = True  # SubM convs walk the rows sorted by neighbour bitmask (tiles share one set of present offsets)
 
 
+index_stream = True  # build rulebooks on a side stream (see build_rulebook)
+_idx_streams = {}
+
+
 def build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding=0, dilation=1, subm=False,
                    need_pairs=True):
-    """indices int32 [M,4] (batch, i0, i1, i2) on CUDA -> Rulebook."""
+    """indices int32 [M,4] (batch, i0, i1, i2) on CUDA -> Rulebook.
+
+    Rulebooks depend on coordinates only, never on features, and the strided builder has to read the number of
+    output sites back to the host.  Built on the caller's stream that read-back would drain every feature kernel
+    queued so far (six pipeline bubbles per forward of DODA's U-Net); built on a dedicated index stream it only waits
+    for the few index kernels, and the caller's stream picks the result up through an event."""
+    _req_cuda(indices)
+    if not index_stream:
+        return _build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, subm, need_pairs)
+    dev = indices.device
+    main = torch.cuda.current_stream(dev)
+    side = _idx_streams.get(dev.index)
+    if side is None:
+        side = _idx_streams[dev.index] = torch.cuda.Stream(dev)
+    if not getattr(indices, "_b200sp_idx_stream", False):
+        side.wait_stream(main)  # coordinates produced on the caller's stream (first level only)
+    with torch.cuda.stream(side):
+        rb = _build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, subm, need_pairs)
+        for name in ("pairs", "pairnum", "nbr", "fwd", "bwd", "order", "nbr_perm", "outids"):
+            t = getattr(rb, name)
+            if t is not None:
+                t.record_stream(main)
+        ev = side.record_event()
+    main.wait_event(ev)
+    rb.outids._b200sp_idx_stream = True
+    return rb
+
+
+def _build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding=0, dilation=1, subm=False,
+                    need_pairs=True):
     _req_cuda(indices)
     if indices.dtype != _I32:
         raise TypeError("indices must be int32 (spconv contract: voxel_coords.int(), model/unet.py:94)")
@@ -235,7 +286,7 @@ def gather_gemm(feat, W3, tab, n_out, out=None, accumulate=False, wflags=W_FWD, 
     assert feat.shape[1] == Cin
     if out is None:
         out = torch.empty((n_out, Cout), dtype=_F32, device=feat.device)
-    ws = _workspace(lib.b200sp_conv_ws_bytes(K, Cin, Cout), feat.device, "conv")
+    ws = _workspace(_conv_ws_bytes(K, Cin, Cout), feat.device, "conv")
     with _Timed(kernel="k_gather_gemm", n_in=feat.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K,
                 tab_entries=n_out * K if tab is not None else 0, pairs_dense=n_out * K):
         check(lib.b200sp_gather_gemm(feat.data_ptr(), feat.shape[0], Cin, W3.data_ptr(), wflags,
@@ -250,7 +301,7 @@ def gather_gemm_pairs(feat, W3, pin, pout, pairnum, n_upper, n_out, wflags=W_FWD
     K, Cin, Cout = _conv_dims(W3, wflags)
     assert feat.shape[1] == Cin
     out = torch.zeros((n_out, Cout), dtype=_F32, device=feat.device)
-    ws = _workspace(lib.b200sp_conv_ws_bytes(K, Cin, Cout), feat.device, "conv")
+    ws = _workspace(_conv_ws_bytes(K, Cin, Cout), feat.device, "conv")
     with _Timed(kernel="k_gather_gemm", n_in=feat.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K,
                 tab_entries=2 * n_upper, pairs_dense=n_upper, pairs_mode=1):
         check(lib.b200sp_gather_gemm_pairs(feat.data_ptr(), Cin, W3.data_ptr(), wflags, pin.data_ptr(),
@@ -260,10 +311,36 @@ def gather_gemm_pairs(feat, W3, pin, pout, pairnum, n_upper, n_out, wflags=W_FWD
     return out
 
 
+class _ZeroArena(object):
+    """Zero-filled fp32 slices for the weight gradients: one 32 MB fill per ~step instead of one fill kernel per
+    conv.  Slices stay valid as long as someone (autograd / .grad) references them; a fresh block is taken when
+    the current one is used up, never recycled."""
+
+    BLOCK = 8 << 20  # floats
+
+    def __init__(self):
+        self.buf, self.off, self.dev = None, 0, None
+
+    def take(self, shape, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        n_al = (n + 63) // 64 * 64  # 256-byte aligned slices (float4 atomics)
+        if self.buf is None or self.dev != device or self.off + n_al > self.buf.numel():
+            self.buf = torch.zeros(max(self.BLOCK, n_al), dtype=_F32, device=device)
+            self.off, self.dev = 0, device
+        out = self.buf[self.off:self.off + n].view(shape)
+        self.off += n_al
+        return out
+
+
+_dw_arena = _ZeroArena()
+
+
 def wgrad(a, b, pa, pb, pairnum, n_upper, K):
     """dW[k] = sum_i a[pa[k][i]]^T b[pb[k][i]]  -> [K, Ca, Cb]"""
     Ca, Cb = a.shape[1], b.shape[1]
-    dW = torch.zeros((K, Ca, Cb), dtype=_F32, device=a.device)
+    dW = _dw_arena.take((K, Ca, Cb), a.device)
     with _Timed(kernel="k_wgrad", n_rows=a.shape[0], Ca=Ca, Cb=Cb, K=K, n_upper=n_upper):
         check(lib.b200sp_wgrad(a.data_ptr(), Ca, b.data_ptr(), Cb, pa.data_ptr() if pa is not None else None,
                                pb.data_ptr() if pb is not None else None,

@@ -14,7 +14,8 @@ from ._lib import lib, check
 
 
 def _s():
-    return torch.cuda.current_stream().cuda_stream
+    from .ops import _stream
+    return _stream()
 
 
 def _cuda(*ts):

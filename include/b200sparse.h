@@ -120,6 +120,8 @@ int b200sp_weight_transpose(const float* W_dev, int K, int Cin, int Cout, int mi
  * [N_active, C] feature matrix (model/unet.py:28,43; model/unet_block.py:24-28,46-47,68-69,76-77) and
  * DSNorm's F.batch_norm call (model/dsnorm.py:79-84).
  * ------------------------------------------------------------------------------------------ */
+/* workspace for the two calls below: the caller zero-fills it ONCE after allocation (it holds a completion ticket
+ * that every launch leaves at zero again); it may then be reused by any number of stream-ordered calls */
 int64_t b200sp_bn_ws_bytes(int64_t M, int C);
 /* training: batch statistics -> mean/invstd (saved for backward); y = [relu]((x-mean)*invstd*w + b).
  * running_mean/var (nullable) are updated in place with `momentum` and the unbiased variance exactly as
