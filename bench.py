@@ -252,19 +252,36 @@ def main():
         recs = ops.profile_end()
         gg = [r for r in recs if r["kernel"] == "k_gather_gemm"]
         if gg:
+            # dominant kernel = k_conv_tc (tcgen05 gather-GEMM, fwd + dgrad); dominant LAUNCH SHAPE = the group of
+            # identical launches with the largest total time.  achieved = algorithmic bytes of one such launch
+            # (SURVEY.md 8(d) / DESIGN.md 3) / its average CUDA-event duration (events on the launch stream).
+            groups = {}
+            for r in gg:
+                groups.setdefault((r["n_out"], r["Cin"], r["Cout"], r["K"], r.get("pairs_mode", 0)), []).append(r)
+            key, grp = max(groups.items(), key=lambda kv: sum(r["ms"] for r in kv[1]))
+            g_ms = sum(r["ms"] for r in grp) / len(grp)
+            g_bytes = conv_layer_bytes(grp[0])
             tot_ms = sum(r["ms"] for r in gg)
             tot_bytes = sum(conv_layer_bytes(r) for r in gg)
             tot_flops = sum(2.0 * r["pairs_dense"] * r["Cin"] * r["Cout"] for r in gg)
             all_ms = sum(r["ms"] for r in recs)
             peak, how = peaks()
-            ach = tot_bytes / (tot_ms * 1e-3) / 1e9
-            top = max(gg, key=lambda r: r["ms"])
-            roof = {"bound": "hbm", "kernel": "k_gather_gemm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": None, "peak_source": how, "launches_per_step": len(gg),
-                    "avg_launch_ms": tot_ms / len(gg), "share_of_engine_kernel_time": tot_ms / max(all_ms, 1e-9),
-                    "dense_tflops": tot_flops / (tot_ms * 1e-3) / 1e12,
-                    "top_launch": {"ms": top["ms"], "n_out": top["n_out"], "Cin": top["Cin"], "Cout": top["Cout"],
-                                   "K": top["K"], "GBs": conv_layer_bytes(top) / (top["ms"] * 1e-3) / 1e9}}
+            ach = g_bytes / (g_ms * 1e-3) / 1e9
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from `ncu --set full`
+            if os.path.exists(tpath):
+                for t in json.load(open(tpath)).get("k_conv_tc", []):
+                    if (t["Cin"], t["Cout"], t["K"]) == key[1:4] and abs(t["n_out"] - key[0]) <= 0.1 * key[0]:
+                        traffic = t["dram_bytes"]
+            roof = {"bound": "hbm", "kernel": "k_conv_tc", "achieved": ach, "peak": peak, "unit": "GB/s",
+                    "frac": ach / peak, "traffic": traffic, "peak_source": how,
+                    "launch_shape": {"rows": key[0], "Cin": key[1], "Cout": key[2], "K": key[3], "pairs_mode": key[4],
+                                     "launches_per_step": len(grp), "avg_launch_ms": g_ms,
+                                     "algorithmic_bytes": g_bytes},
+                    "all_conv_launches": {"launches_per_step": len(gg), "total_ms": tot_ms,
+                                          "algorithmic_GBs": tot_bytes / (tot_ms * 1e-3) / 1e9,
+                                          "useful_dense_tflops": tot_flops / (tot_ms * 1e-3) / 1e12,
+                                          "share_of_engine_kernel_time": tot_ms / max(all_ms, 1e-9)}}
             detail = recs
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -9,7 +9,7 @@
 namespace b200sp {
 
 constexpr int BN_THREADS = 256;
-constexpr int BN_MAXGRID = 592;  // 4 CTAs x 148 SMs
+constexpr int BN_MAXGRID = 296;  // 2 CTAs x 148 SMs (the last block folds this many partial rows per channel)
 
 // ---------------------------------------------------------------------------------------------
 // per-channel reduction of up to two quantities over rows.  Layout: thread (rl, cg) with cg the float4
@@ -109,26 +109,37 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restric
         for (int r = 0; r < rpb; ++r) s += s_part[(q * rpb + r) * C + c];
         partial[((int64_t)blockIdx.x * 2 + q) * C + c] = s;
     }
-    // ---- last block to finish folds the per-block partials (one warp per channel, fp64) and finalises ----
+    // ---- last block to finish folds the per-block partials (fp64) and finalises ----
     __threadfence();
     __syncthreads();
     if (tid == 0) s_last = (atomicAdd(fin.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    // all threads fold the G per-block partials: item (slice, entry) sums every SL-th partial row of one of the 2C
+    // entries (coalesced across threads), slices meet in shared memory, then one thread per channel finalises
+    __shared__ double s_fold[512];
     const int G = gridDim.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int c = warp; c < C; c += BN_THREADS / 32) {
+    const int E = 2 * C;
+    const int SL = E >= BN_THREADS ? 1 : BN_THREADS / E;
+    for (int i = tid; i < E * SL; i += BN_THREADS) {
+        const int sl = i / E, e = i - sl * E;
+        double a = 0.0, b2 = 0.0;
+        int g = sl;
+        for (; g + SL < G; g += 2 * SL) {  // two independent chains keep loads in flight
+            a += (double)__ldcg(&partial[(int64_t)g * E + e]);
+            b2 += (double)__ldcg(&partial[(int64_t)(g + SL) * E + e]);
+        }
+        if (g < G) a += (double)__ldcg(&partial[(int64_t)g * E + e]);
+        s_fold[i] = a + b2;
+    }
+    __syncthreads();
+    for (int c = tid; c < C; c += BN_THREADS) {
         double s0 = 0.0, s1 = 0.0;
-        for (int g = lane; g < G; g += 32) {
-            s0 += __ldcg(&partial[((int64_t)g * 2 + 0) * C + c]);
-            s1 += __ldcg(&partial[((int64_t)g * 2 + 1) * C + c]);
+        for (int sl = 0; sl < SL; ++sl) {
+            s0 += s_fold[sl * E + c];
+            s1 += s_fold[sl * E + C + c];
         }
-        for (int o = 16; o; o >>= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        }
-        if (lane != 0) continue;
         if (MODE == 0) {
             const double mu = s0 / (double)fin.M;
             double var = s1 / (double)fin.M - mu * mu;

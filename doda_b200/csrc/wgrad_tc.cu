@@ -321,6 +321,10 @@ int wgrad_tc_run(const float* a, int Ca, const float* b, int Cb, const int* pa, 
     // pairs per stage: biggest of {128, 64, 32, 16} with 4 slots under ~170 KB
     const int slots = 4;
     int PS = 128;
+    {
+        const char* e = getenv("B200SP_WG_PS");  // dev knob: cap on pairs per stage
+        if (e && atoi(e) >= 16) PS = atoi(e);
+    }
     uint32_t slot = 0;
     for (; PS >= 16; PS >>= 1) {
         p.stgA = (uint32_t)PS * p.rsA;
@@ -354,6 +358,10 @@ int wgrad_tc_run(const float* a, int Ca, const float* b, int Cb, const int* pa, 
     while ((1 << p.psh) < PS) ++p.psh;
     // pairs per block: enough CTAs to fill the machine, few enough that the final atomics stay cheap
     int64_t ppb = 4096;
+    {
+        const char* e = getenv("B200SP_WG_PPB");  // dev knob: cap on pairs per CTA
+        if (e && atoi(e) >= 256) ppb = atoi(e);
+    }
     while (ppb > 2 * PS && ppb > 256 && cdiv(n_upper, ppb) * K < 3 * 148) ppb >>= 1;
     if (ppb < PS) ppb = PS;
     p.ppb = (int)ppb;
