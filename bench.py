@@ -245,11 +245,14 @@ def main():
 
     roof = None
     detail = None
-    if rank == 0 and not args.no_roofline:
+    if not args.no_roofline:
+        # every rank runs this extra step (DDP's gradient all-reduce is a collective); only rank 0 keeps the records
         ops.profile_begin()
         step(resident)
         torch.cuda.synchronize()
         recs = ops.profile_end()
+        if rank != 0:
+            recs = []
         gg = [r for r in recs if r["kernel"] == "k_gather_gemm"]
         if gg:
             # dominant kernel = k_conv_tc (tcgen05 gather-GEMM, fwd + dgrad); dominant LAUNCH SHAPE = the group of
