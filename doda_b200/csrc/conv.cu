@@ -407,6 +407,7 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
                 const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out, int Cout,
                 int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st);
 int64_t conv_tc_ws_bytes(int K, int Cin, int Cout);
+int conv_tc_prep_batch(const int64_t* desc_host, int n, void* desc_dev, int64_t desc_dev_bytes, cudaStream_t st);
 int wgrad_tc_run(const float* a, int Ca, const float* b, int Cb, const int* pa, const int* pb, const int* pairnum,
                  int64_t n_upper, int K, int64_t pstride, float* dW, cudaStream_t st);
 
@@ -450,6 +451,14 @@ extern "C" int b200sp_set_conv_impl(int impl) {
     return B200SP_OK;
 }
 
+extern "C" int64_t b200sp_conv_prepared_bytes(int K, int Cin, int Cout) { return b200sp::conv_tc_ws_bytes(K, Cin, Cout); }
+
+extern "C" int b200sp_prep_weights_batch(const int64_t* desc_host, int n, void* desc_dev, int64_t desc_dev_bytes,
+                                         void* stream) {
+    B200SP_CHECK_ARG(desc_host && n >= 0 && desc_dev, "prep_weights_batch: bad arguments");
+    return b200sp::conv_tc_prep_batch(desc_host, n, desc_dev, desc_dev_bytes, (cudaStream_t)stream);
+}
+
 extern "C" int64_t b200sp_conv_ws_bytes(int K, int Cin, int Cout) {
     int64_t a = b200sp::conv_tc_ws_bytes(K, Cin, Cout);
     int64_t b = (int64_t)K * Cin * Cout * 4;
@@ -471,6 +480,7 @@ extern "C" int b200sp_gather_gemm(const float* in, int64_t n_in, int Cin, const 
                              accumulate, 0, ws, ws_bytes, st);
         if (rc != B200SP_EUNSUP) return rc;
     }
+    B200SP_CHECK_ARG(!(wflags & 4), "gather_gemm: a prepared weight image needs the tensor path");
     const float* Wuse = nullptr;
     int rc = fp32_weights(W, K, Cin, Cout, wflags, ws, ws_bytes, st, &Wuse);
     if (rc) return rc;

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <algorithm>
+#include <vector>
 #include <stdlib.h>
 #include <string.h>
 
@@ -543,6 +544,40 @@ __global__ void k_prep_weights(const float* __restrict__ W, int K, int Ci_w, int
     }
 }
 
+// one launch for MANY weight tensors (all conv layers of a model): blockIdx.y = tensor
+struct PrepItem {
+    const float* W;
+    float* Wp;
+    int K, Ci_w, Co_w, transposed, mirror, KC, nchunks, Cout_pad;
+};
+__global__ void k_prep_weights_batch(const PrepItem* __restrict__ items) {
+    const PrepItem it = items[blockIdx.y];
+    const int Cin = it.transposed ? it.Co_w : it.Ci_w;
+    const int Cout = it.transposed ? it.Ci_w : it.Co_w;
+    const int64_t per_block = (int64_t)it.Cout_pad * it.KC;
+    const int64_t total = (int64_t)it.K * it.nchunks * per_block;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i % it.Cout_pad);
+        int64_t t = i / it.Cout_pad;
+        const int kl = (int)(t % it.KC);
+        t /= it.KC;
+        const int c = (int)(t % it.nchunks);
+        const int k = (int)(t / it.nchunks);
+        const int kin = c * it.KC + kl;
+        float v = 0.f;
+        if (kin < Cin && n < Cout) {
+            const int ks = it.mirror ? it.K - 1 - k : k;
+            v = it.transposed ? it.W[((int64_t)ks * it.Ci_w + n) * it.Co_w + kin] : it.W[((int64_t)ks * it.Ci_w + kin) * it.Co_w + n];
+        }
+        float hi, lo;
+        tc::split_tf32(v, hi, lo);
+        const int64_t base = ((int64_t)k * it.nchunks + c) * 2 * per_block;
+        const int64_t off = ((int64_t)(kl >> 2) * (it.Cout_pad >> 3) + (n >> 3)) * 32 + (n & 7) * 4 + (kl & 3);
+        it.Wp[base + off] = hi;
+        it.Wp[base + per_block + off] = lo;
+    }
+}
+
 struct TCPlan {
     int KC, nchunks, Cout_pad, nslots, ni;
     uint32_t stageB, tmem_cols, smem;
@@ -616,13 +651,15 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
     TCPlan pl;
     const int KT = pairs_mode ? 1 : K;
     if (!tc_plan(K, Cin, Cout, KT, pl)) return B200SP_EUNSUP;
-    if (!ws || ws_bytes < pl.wp_bytes) {
+    if (!(wflags & 4) && (!ws || ws_bytes < pl.wp_bytes)) {
         set_error("conv_tc: workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)pl.wp_bytes);
         return B200SP_ENOMEM;
     }
     if (cdiv(n_rows, TC_BM) * (pairs_mode ? K : 1) > (int64_t)1 << 30) return B200SP_EUNSUP;
     float* Wp = static_cast<float*>(ws);
-    {
+    if (wflags & 4) {
+        Wp = const_cast<float*>(W);  // W already IS the prepared image (b200sp_prep_weights_batch)
+    } else {
         const int64_t total = (int64_t)K * pl.nchunks * pl.Cout_pad * pl.KC;
         const unsigned blocks = (unsigned)std::min<int64_t>(cdiv(total, 256), 4 * 148);
         k_prep_weights<<<blocks, 256, 0, st>>>(W, K, Ci_w, Co_w, wflags & 1, (wflags >> 1) & 1, pl.KC, pl.nchunks,
@@ -651,6 +688,38 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
     if (pl.KC == 32) return launch_tc<32>(p, KT, st);
     if (pl.KC == 16) return launch_tc<16>(p, KT, st);
     return launch_tc<8>(p, KT, st);
+}
+
+// rows of desc_host: {W ptr, Wp ptr, K, Ci_w, Co_w, wflags}; desc_dev: device scratch of n * sizeof(PrepItem) bytes
+int conv_tc_prep_batch(const int64_t* desc_host, int n, void* desc_dev, int64_t desc_dev_bytes, cudaStream_t st) {
+    if (n <= 0) return B200SP_OK;
+    if (desc_dev_bytes < (int64_t)n * (int64_t)sizeof(PrepItem)) {
+        set_error("prep_weights_batch: descriptor scratch too small");
+        return B200SP_ENOMEM;
+    }
+    std::vector<PrepItem> items((size_t)n);
+    int64_t max_total = 1;
+    for (int i = 0; i < n; ++i) {
+        const int64_t* d = desc_host + (size_t)i * 6;
+        PrepItem& it = items[(size_t)i];
+        it.W = reinterpret_cast<const float*>(d[0]);
+        it.Wp = reinterpret_cast<float*>(d[1]);
+        it.K = (int)d[2]; it.Ci_w = (int)d[3]; it.Co_w = (int)d[4];
+        it.transposed = (int)(d[5] & 1); it.mirror = (int)((d[5] >> 1) & 1);
+        const int Cin = it.transposed ? it.Co_w : it.Ci_w, Cout = it.transposed ? it.Ci_w : it.Co_w;
+        TCPlan pl;
+        if (!tc_plan(it.K, Cin, Cout, it.K, pl)) {
+            set_error("prep_weights_batch: shape K=%d Cin=%d Cout=%d is not covered by the tensor path", it.K, Cin, Cout);
+            return B200SP_EUNSUP;
+        }
+        it.KC = pl.KC; it.nchunks = pl.nchunks; it.Cout_pad = pl.Cout_pad;
+        max_total = std::max<int64_t>(max_total, (int64_t)it.K * pl.nchunks * pl.Cout_pad * pl.KC);
+    }
+    B200SP_CUDA(cudaMemcpyAsync(desc_dev, items.data(), (size_t)n * sizeof(PrepItem), cudaMemcpyHostToDevice, st));
+    dim3 grid((unsigned)std::min<int64_t>(cdiv(max_total, 256), 64), (unsigned)n);
+    k_prep_weights_batch<<<grid, 256, 0, st>>>(static_cast<const PrepItem*>(desc_dev));
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
 }
 
 int64_t conv_tc_ws_bytes(int K, int Cin, int Cout) {

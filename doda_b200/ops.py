@@ -38,7 +38,9 @@ def _f32c(t):
 
 def set_conv_impl(name):
     """'tc' (default): tcgen05 3xTF32 tensor-core kernels; 'fp32': CUDA-core kernels only (A/B testing)."""
+    global _conv_impl_name
     check(lib.b200sp_set_conv_impl({"tc": 0, "fp32": 1}[name]), "set_conv_impl")
+    _conv_impl_name = name
 
 
 def launch_count():
@@ -91,6 +93,15 @@ _ws = {}
 
 
 _ws_bytes_cache = {}
+_bn_ws_cache = {}
+
+
+def _bn_ws_bytes(C):
+    v = _bn_ws_cache.get(C)
+    if v is None:
+        v = _bn_ws_cache[C] = int(lib.b200sp_bn_ws_bytes(1, C))  # independent of M
+    return v
+
 
 
 def _conv_ws_bytes(K, Cin, Cout):
@@ -272,6 +283,7 @@ def pairs_to_table(pairs, pairnum, n_out, inverse=False):
 # conv primitives
 # ------------------------------------------------------------------------------------------------
 W_FWD, W_T, W_T_MIRROR = 0, 1, 3  # wflags of the C ABI: bit0 = use W[k]^T (dgrad), bit1 = mirrored offsets (SubM dgrad)
+W_PREP = 4  # bit2: the weight pointer is an image made by b200sp_prep_weights_batch
 
 
 def _conv_dims(W3, wflags):
@@ -279,36 +291,120 @@ def _conv_dims(W3, wflags):
     return (K, Co_w, Ci_w) if (wflags & 1) else (K, Ci_w, Co_w)
 
 
-def gather_gemm(feat, W3, tab, n_out, out=None, accumulate=False, wflags=W_FWD, orow=None):
+def gather_gemm(feat, W3, tab, n_out, out=None, accumulate=False, wflags=W_FWD, orow=None, wimg=None):
     """out[r] = sum_k feat[tab[r,k]] @ Wk;  W3 = the module weight viewed [K,Ci_w,Co_w]; Wk = W3[k] (wflags 0),
-    W3[k]^T (W_T) or W3[K-1-k]^T (W_T_MIRROR); tab None -> dense GEMM (K==1)."""
+    W3[k]^T (W_T) or W3[K-1-k]^T (W_T_MIRROR); tab None -> dense GEMM (K==1).  wimg: the tensor-core image of W3
+    for these wflags, prepared ahead by prepare_weights (skips the per-call weight pre-pass)."""
     K, Cin, Cout = _conv_dims(W3, wflags)
     assert feat.shape[1] == Cin
     if out is None:
         out = torch.empty((n_out, Cout), dtype=_F32, device=feat.device)
-    ws = _workspace(_conv_ws_bytes(K, Cin, Cout), feat.device, "conv")
-    with _Timed(kernel="k_gather_gemm", n_in=feat.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K,
-                tab_entries=n_out * K if tab is not None else 0, pairs_dense=n_out * K):
-        check(lib.b200sp_gather_gemm(feat.data_ptr(), feat.shape[0], Cin, W3.data_ptr(), wflags,
+    if wimg is not None:
+        wptr, wfl, wsp, wsn = wimg.data_ptr(), wflags | W_PREP, None, 0
+    else:
+        ws = _workspace(_conv_ws_bytes(K, Cin, Cout), feat.device, "conv")
+        wptr, wfl, wsp, wsn = W3.data_ptr(), wflags, ws.data_ptr(), ws.numel()
+    if _prof is None:
+        check(lib.b200sp_gather_gemm(feat.data_ptr(), feat.shape[0], Cin, wptr, wfl,
                                      tab.data_ptr() if tab is not None else None,
                                      orow.data_ptr() if orow is not None else None, K, out.data_ptr(), n_out, Cout,
-                                     1 if accumulate else 0, ws.data_ptr(), ws.numel(), _stream()), "gather_gemm")
+                                     1 if accumulate else 0, wsp, wsn, _stream()), "gather_gemm")
+        return out
+    with _Timed(kernel="k_gather_gemm", n_in=feat.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K,
+                tab_entries=n_out * K if tab is not None else 0, pairs_dense=n_out * K):
+        check(lib.b200sp_gather_gemm(feat.data_ptr(), feat.shape[0], Cin, wptr, wfl,
+                                     tab.data_ptr() if tab is not None else None,
+                                     orow.data_ptr() if orow is not None else None, K, out.data_ptr(), n_out, Cout,
+                                     1 if accumulate else 0, wsp, wsn, _stream()), "gather_gemm")
     return out
 
 
-def gather_gemm_pairs(feat, W3, pin, pout, pairnum, n_upper, n_out, wflags=W_FWD):
+def gather_gemm_pairs(feat, W3, pin, pout, pairnum, n_upper, n_out, wflags=W_FWD, wimg=None):
     """out[pout[k][i]] = feat[pin[k][i]] @ Wk; rows not covered stay zero."""
     K, Cin, Cout = _conv_dims(W3, wflags)
     assert feat.shape[1] == Cin
     out = torch.zeros((n_out, Cout), dtype=_F32, device=feat.device)
-    ws = _workspace(_conv_ws_bytes(K, Cin, Cout), feat.device, "conv")
+    if wimg is not None:
+        wptr, wfl, wsp, wsn = wimg.data_ptr(), wflags | W_PREP, None, 0
+    else:
+        ws = _workspace(_conv_ws_bytes(K, Cin, Cout), feat.device, "conv")
+        wptr, wfl, wsp, wsn = W3.data_ptr(), wflags, ws.data_ptr(), ws.numel()
     with _Timed(kernel="k_gather_gemm", n_in=feat.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K,
                 tab_entries=2 * n_upper, pairs_dense=n_upper, pairs_mode=1):
-        check(lib.b200sp_gather_gemm_pairs(feat.data_ptr(), Cin, W3.data_ptr(), wflags, pin.data_ptr(),
+        check(lib.b200sp_gather_gemm_pairs(feat.data_ptr(), Cin, wptr, wfl, pin.data_ptr(),
                                            pout.data_ptr(), pairnum.data_ptr(), n_upper, K, pin.stride(0),
-                                           out.data_ptr(), Cout, 0, ws.data_ptr(), ws.numel(), _stream()),
+                                           out.data_ptr(), Cout, 0, wsp, wsn, _stream()),
               "gather_gemm_pairs")
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# weight images prepared ahead, for every conv layer of the process in ONE launch per optimizer step
+# ------------------------------------------------------------------------------------------------
+import weakref  # noqa: E402
+
+_conv_modules = weakref.WeakSet()
+_conv_impl_name = "tc"
+prepare_ahead = True
+
+
+def register_conv_module(m):
+    _conv_modules.add(m)
+
+
+def _bwd_flags(m):
+    return W_T_MIRROR if (m.subm and not m.conv1x1) else W_T
+
+
+def prepared_weights(module):
+    """-> (image for the forward, image for dgrad) of module.weight, or None when the tensor path does not cover the
+    shape / is switched off.  Images are keyed on (data_ptr, _version): the first conv that finds its image stale
+    re-prepares EVERY registered conv layer whose weight changed (one optimizer step -> one launch)."""
+    w = module.weight
+    if not (prepare_ahead and w.is_cuda and _conv_impl_name == "tc"):
+        return None
+    key = (w.data_ptr(), w._version)
+    st = module.__dict__.get("_b200sp_prep")
+    if st is None or st[0] != key:
+        _prepare_all(w.device)
+        st = module.__dict__.get("_b200sp_prep")
+        if st is None or st[0] != key:
+            return None
+    return st[1]
+
+
+def _prepare_all(device):
+    import numpy as np
+    rows, todo = [], []
+    for m in list(_conv_modules):
+        w = m.weight
+        if w.device != device or w.dtype != _F32:
+            continue
+        key = (w.data_ptr(), w._version)
+        st = m.__dict__.get("_b200sp_prep")
+        if st is not None and st[0] == key:
+            continue
+        Ci_w, Co_w = int(w.shape[-2]), int(w.shape[-1])
+        K = int(w.numel() // (Ci_w * Co_w))
+        nb_f = int(lib.b200sp_conv_prepared_bytes(K, Ci_w, Co_w))
+        nb_b = int(lib.b200sp_conv_prepared_bytes(K, Co_w, Ci_w))
+        if nb_f == 0 or nb_b == 0 or not w.is_contiguous():
+            m.__dict__["_b200sp_prep"] = (key, None)
+            continue
+        imgs = m.__dict__.get("_b200sp_img")
+        if imgs is None or imgs[0].numel() != nb_f or imgs[1].numel() != nb_b or imgs[0].device != device:
+            imgs = (torch.empty(nb_f, dtype=torch.uint8, device=device), torch.empty(nb_b, dtype=torch.uint8, device=device))
+            m.__dict__["_b200sp_img"] = imgs
+        rows.append((w.data_ptr(), imgs[0].data_ptr(), K, Ci_w, Co_w, W_FWD))
+        rows.append((w.data_ptr(), imgs[1].data_ptr(), K, Ci_w, Co_w, _bwd_flags(m)))
+        todo.append((m, key, imgs))
+    if rows:
+        desc = np.ascontiguousarray(np.asarray(rows, dtype=np.int64))
+        scratch = _workspace(64 * len(rows), device, "prepdesc")
+        check(lib.b200sp_prep_weights_batch(desc.ctypes.data, len(rows), scratch.data_ptr(), scratch.numel(), _stream()),
+              "prep_weights_batch")
+    for m, key, imgs in todo:
+        m.__dict__["_b200sp_prep"] = (key, imgs)
 
 
 class _ZeroArena(object):
@@ -341,6 +437,12 @@ def wgrad(a, b, pa, pb, pairnum, n_upper, K):
     """dW[k] = sum_i a[pa[k][i]]^T b[pb[k][i]]  -> [K, Ca, Cb]"""
     Ca, Cb = a.shape[1], b.shape[1]
     dW = _dw_arena.take((K, Ca, Cb), a.device)
+    if _prof is None:
+        check(lib.b200sp_wgrad(a.data_ptr(), Ca, b.data_ptr(), Cb, pa.data_ptr() if pa is not None else None,
+                               pb.data_ptr() if pb is not None else None,
+                               pairnum.data_ptr() if pairnum is not None else None, n_upper, K,
+                               pa.stride(0) if pa is not None else 0, dW.data_ptr(), _stream()), "wgrad")
+        return dW
     with _Timed(kernel="k_wgrad", n_rows=a.shape[0], Ca=Ca, Cb=Cb, K=K, n_upper=n_upper):
         check(lib.b200sp_wgrad(a.data_ptr(), Ca, b.data_ptr(), Cb, pa.data_ptr() if pa is not None else None,
                                pb.data_ptr() if pb is not None else None,
@@ -368,14 +470,14 @@ class SubMConvFunction(Function):
     """spconv.functional.indice_subm_conv: out[q] = sum_k W[k] . in[q + k - centre] on the input's own sites."""
 
     @staticmethod
-    def forward(ctx, features, filters, rb):
+    def forward(ctx, features, filters, rb, prep=None):
         _req_cuda(features, filters)
         features = _f32c(features)
         W3 = _w3(filters)
-        ctx.rb = rb
+        ctx.rb, ctx.prep = rb, prep
         ctx.save_for_backward(features, filters)
         tab, orow = (rb.nbr_perm, rb.order) if rb.nbr_perm is not None else (rb.nbr, None)
-        return gather_gemm(features, W3, tab, features.shape[0], orow=orow)
+        return gather_gemm(features, W3, tab, features.shape[0], orow=orow, wimg=prep[0] if prep else None)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -387,21 +489,23 @@ class SubMConvFunction(Function):
         din = dW = None
         if ctx.needs_input_grad[0]:
             tab, orow = (rb.nbr_perm, rb.order) if rb.nbr_perm is not None else (rb.nbr, None)
-            din = gather_gemm(grad_out, W3, tab, M, wflags=W_T_MIRROR, orow=orow)
+            din = gather_gemm(grad_out, W3, tab, M, wflags=W_T_MIRROR, orow=orow,
+                              wimg=ctx.prep[1] if ctx.prep else None)
         if ctx.needs_input_grad[1]:
             dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K).view(filters.shape)
-        return din, dW, None
+        return din, dW, None, None
 
 
 class DenseConvFunction(Function):
     """kernel_size == 1: features @ W.view(Cin, Cout) (spconv SparseConvolution.forward)."""
 
     @staticmethod
-    def forward(ctx, features, filters):
+    def forward(ctx, features, filters, prep=None):
         _req_cuda(features, filters)
         features = _f32c(features)
+        ctx.prep = prep
         ctx.save_for_backward(features, filters)
-        return gather_gemm(features, _w3(filters), None, features.shape[0])
+        return gather_gemm(features, _w3(filters), None, features.shape[0], wimg=prep[0] if prep else None)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -411,22 +515,22 @@ class DenseConvFunction(Function):
         M = features.shape[0]
         din = dW = None
         if ctx.needs_input_grad[0]:
-            din = gather_gemm(grad_out, W3, None, M, wflags=W_T)
+            din = gather_gemm(grad_out, W3, None, M, wflags=W_T, wimg=ctx.prep[1] if ctx.prep else None)
         if ctx.needs_input_grad[1]:
             dW = wgrad(features, grad_out, None, None, None, M, 1).view(filters.shape)
-        return din, dW
+        return din, dW, None
 
 
 class SparseConvFunction(Function):
     """spconv.functional.indice_conv (regular / strided sparse conv)."""
 
     @staticmethod
-    def forward(ctx, features, filters, rb):
+    def forward(ctx, features, filters, rb, prep=None):
         _req_cuda(features, filters)
         features = _f32c(features)
-        ctx.rb = rb
+        ctx.rb, ctx.prep = rb, prep
         ctx.save_for_backward(features, filters)
-        return gather_gemm(features, _w3(filters), rb.bwd, rb.outids.shape[0])
+        return gather_gemm(features, _w3(filters), rb.bwd, rb.outids.shape[0], wimg=prep[0] if prep else None)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -437,29 +541,32 @@ class SparseConvFunction(Function):
         M_in = features.shape[0]
         din = dW = None
         if ctx.needs_input_grad[0]:
+            wb = ctx.prep[1] if ctx.prep else None
             if rb.nonoverlap:  # every input has at most one (output, offset): pair-grouped, no accumulation
-                din = gather_gemm_pairs(grad_out, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, M_in, M_in, wflags=W_T)
+                din = gather_gemm_pairs(grad_out, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, M_in, M_in, wflags=W_T,
+                                        wimg=wb)
             else:
-                din = gather_gemm(grad_out, W3, rb.fwd, M_in, wflags=W_T)
+                din = gather_gemm(grad_out, W3, rb.fwd, M_in, wflags=W_T, wimg=wb)
         if ctx.needs_input_grad[1]:
             dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M_in, rb.K).view(filters.shape)
-        return din, dW, None
+        return din, dW, None, None
 
 
 class SparseInverseConvFunction(Function):
     """spconv.functional.indice_inverse_conv: reuses the strided conv's rulebook with roles swapped."""
 
     @staticmethod
-    def forward(ctx, features, filters, rb):
+    def forward(ctx, features, filters, rb, prep=None):
         _req_cuda(features, filters)
         features = _f32c(features)
-        ctx.rb = rb
+        ctx.rb, ctx.prep = rb, prep
         ctx.save_for_backward(features, filters)
         W3 = _w3(filters)
         n_fine = rb.indices.shape[0]
+        wf = prep[0] if prep else None
         if rb.nonoverlap:
-            return gather_gemm_pairs(features, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, n_fine)
-        return gather_gemm(features, W3, rb.fwd, n_fine)
+            return gather_gemm_pairs(features, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, n_fine, wimg=wf)
+        return gather_gemm(features, W3, rb.fwd, n_fine, wimg=wf)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -470,10 +577,11 @@ class SparseInverseConvFunction(Function):
         n_fine = rb.indices.shape[0]
         din = dW = None
         if ctx.needs_input_grad[0]:
-            din = gather_gemm(grad_out, W3, rb.bwd, features.shape[0], wflags=W_T)
+            din = gather_gemm(grad_out, W3, rb.bwd, features.shape[0], wflags=W_T,
+                              wimg=ctx.prep[1] if ctx.prep else None)
         if ctx.needs_input_grad[1]:
             dW = wgrad(features, grad_out, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, rb.K).view(filters.shape)
-        return din, dW, None
+        return din, dW, None, None
 
 
 def indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_out, inverse=False, subm=False):
@@ -513,7 +621,7 @@ class BNReLUFunction(Function):
         dev = x.device
         y = torch.empty_like(x)
         stats = torch.empty((2, C), dtype=_F32, device=dev)
-        ws = _workspace(lib.b200sp_bn_ws_bytes(M, C), dev, "bn")
+        ws = _workspace(_bn_ws_bytes(C), dev, "bn")
         check(lib.b200sp_bn_fwd_train(x.data_ptr(), M, C, weight.data_ptr() if weight is not None else None,
                                       bias.data_ptr() if bias is not None else None, float(eps), 1 if relu else 0,
                                       y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
@@ -533,7 +641,7 @@ class BNReLUFunction(Function):
         dev = x.device
         dx = torch.empty_like(x)
         dwb = torch.empty((2, C), dtype=_F32, device=dev)
-        ws = _workspace(lib.b200sp_bn_ws_bytes(M, C), dev, "bn")
+        ws = _workspace(_bn_ws_bytes(C), dev, "bn")
         check(lib.b200sp_bn_bwd(x.data_ptr(), dy.data_ptr(), M, C, weight.data_ptr() if weight is not None else None,
                                 bias.data_ptr() if bias is not None else None, stats[0].data_ptr(),
                                 stats[1].data_ptr(), 1 if ctx.relu else 0, dx.data_ptr(), dwb[0].data_ptr(),

@@ -52,6 +52,7 @@ class SparseConvolution(SparseModule):
         else:
             self.register_parameter("bias", None)
         self.reset_parameters()
+        _ops.register_conv_module(self)
 
     def reset_parameters(self):
         init.kaiming_uniform_(self.weight, a=math.sqrt(5))
@@ -71,7 +72,7 @@ class SparseConvolution(SparseModule):
         spatial_shape = input.spatial_shape
         batch_size = input.batch_size
         if self.conv1x1:
-            out_features = _ops.DenseConvFunction.apply(features, self.weight)
+            out_features = _ops.DenseConvFunction.apply(features, self.weight, _ops.prepared_weights(self))
             if self.bias is not None:
                 out_features = out_features + self.bias
             out_tensor = SparseConvTensor(out_features, indices, spatial_shape, batch_size)
@@ -82,7 +83,7 @@ class SparseConvolution(SparseModule):
         if self.inverse:
             assert rb is not None and self.indice_key is not None, "inverse conv needs the rulebook of its key"
             assert rb.kind == "conv" and rb.K == int(np.prod(self.kernel_size)), "kernel size mismatch with the key"
-            out_features = _ops.SparseInverseConvFunction.apply(features, self.weight, rb)
+            out_features = _ops.SparseInverseConvFunction.apply(features, self.weight, rb, _ops.prepared_weights(self))
             outids, out_spatial_shape = rb.indices, rb.spatial_shape
         else:
             if rb is None:
@@ -91,9 +92,9 @@ class SparseConvolution(SparseModule):
                 if self.indice_key is not None:
                     input.indice_dict[self.indice_key] = rb
             if self.subm:
-                out_features = _ops.SubMConvFunction.apply(features, self.weight, rb)
+                out_features = _ops.SubMConvFunction.apply(features, self.weight, rb, _ops.prepared_weights(self))
             else:
-                out_features = _ops.SparseConvFunction.apply(features, self.weight, rb)
+                out_features = _ops.SparseConvFunction.apply(features, self.weight, rb, _ops.prepared_weights(self))
             outids, out_spatial_shape = rb.outids, rb.out_spatial_shape
         if self.bias is not None:
             out_features = out_features + self.bias

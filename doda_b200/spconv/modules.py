@@ -24,7 +24,18 @@ def is_sparse_conv(module):
     return isinstance(module, SparseConvolution)
 
 
+_bn_like_types = {}
+
+
 def _is_bn_like(m):
+    t = type(m)
+    v = _bn_like_types.get(t)
+    if v is None:
+        v = _bn_like_types[t] = _is_bn_like_slow(m)
+    return v
+
+
+def _is_bn_like_slow(m):
     if isinstance(m, nn.SyncBatchNorm):
         return False  # needs cross-rank statistics: keep torch's implementation
     if isinstance(m, nn.modules.batchnorm._BatchNorm):

@@ -85,7 +85,7 @@ int b200sp_pairs_to_table(const int32_t* pairs_dev, const int32_t* pairnum_dev, 
  *
  * W is the module's weight viewed as [K][Ci_w][Co_w] contiguous.  wflags = 0: forward (Cin = Ci_w, Cout = Co_w).
  * wflags bit0: use W[k]^T (dgrad: Cin = Co_w, Cout = Ci_w); bit1: mirrored offsets W[K-1-k] (SubM dgrad), with
- * the out->in table of the adjoint.
+ * the out->in table of the adjoint; bit2: W_dev is an image made by b200sp_prep_weights_batch with the same bits 0-1.
  * ------------------------------------------------------------------------------------------ */
 int b200sp_gather_gemm(const float* in_dev, int64_t n_in, int Cin, const float* W_dev, int wflags,
                        const int32_t* tab_dev, const int32_t* orow_dev, int K, float* out_dev, int64_t n_out, int Cout,
@@ -99,6 +99,13 @@ int b200sp_gather_gemm_pairs(const float* in_dev, int Cin, const float* W_dev, i
                              const int32_t* pairs_in_dev /*[K,stride]*/, const int32_t* pairs_out_dev,
                              const int32_t* pairnum_dev, int64_t n_upper, int K, int64_t pair_stride, float* out_dev,
                              int Cout, int accumulate, void* ws_dev, int64_t ws_bytes, void* stream);
+
+/* Weight images for the tensor path can be prepared ahead, for MANY layers in one launch (weights change once per
+ * optimizer step, not per call).  desc_host: n rows of 6 x int64 {W_dev, image_dev, K, Ci_w, Co_w, wflags};
+ * image_dev must hold b200sp_conv_prepared_bytes(K, Cin, Cout) bytes (0 = shape not covered: do not prepare);
+ * desc_dev: device scratch of >= 64*n bytes.  A prepared image is then passed as W_dev with (wflags | 4). */
+int64_t b200sp_conv_prepared_bytes(int K, int Cin, int Cout);
+int b200sp_prep_weights_batch(const int64_t* desc_host, int n, void* desc_dev, int64_t desc_dev_bytes, void* stream);
 
 /* device workspace both calls above need (pre-split tensor-core weight image / transposed weights) */
 int64_t b200sp_conv_ws_bytes(int K, int Cin, int Cout);

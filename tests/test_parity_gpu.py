@@ -136,6 +136,31 @@ def test_conv_many_tiles_per_cta(cuda_dev, kind, Cin, Cout):
     _conv_case(cuda_dev, kind, Cin, Cout, seed=7, n=45000, shape=(96, 96, 64))
 
 
+def test_prepared_weight_images_follow_updates(cuda_dev):
+    """module path: weight images are prepared ahead (one launch for all layers) and must track in-place updates"""
+    from doda_b200 import spconv, ops
+    from oracle.conv import indice_conv_ref
+    torch.manual_seed(11)
+    shape = (20, 18, 16)
+    coords = random_coords(11, 900, 2, shape)
+    _, pairs, pairnum, _ = _rb_oracle(coords, 2, list(shape), 3, 1, 1, 1, True)
+    conv = spconv.SubMConv3d(16, 32, 3, padding=1, bias=False, indice_key="k").to(cuda_dev)
+    other = spconv.SubMConv3d(32, 16, 3, padding=1, bias=False, indice_key="k").to(cuda_dev)
+    feats = torch.randn(coords.shape[0], 16)
+    for it in range(3):
+        x = spconv.SparseConvTensor(feats.to(cuda_dev).requires_grad_(True), torch.from_numpy(coords).to(cuda_dev),
+                                    list(shape), 2)
+        y = other(conv(x))
+        ref = indice_conv_ref(feats.double(), conv.weight.detach().double().cpu(), pairs, pairnum, coords.shape[0], subm=True)
+        ref = indice_conv_ref(ref, other.weight.detach().double().cpu(), pairs, pairnum, coords.shape[0], subm=True)
+        assert rel_err(y.features, ref) <= TOL, it
+        y.features.sum().backward()
+        with torch.no_grad():  # an optimizer step: in-place update bumps the version, images must be rebuilt
+            conv.weight.add_(0.05 * torch.randn_like(conv.weight))
+            other.weight.mul_(1.1)
+    assert ops.prepared_weights(conv) is not None
+
+
 def test_conv1x1_fwd_bwd(cuda_dev):
     from doda_b200 import ops
     torch.manual_seed(0)
