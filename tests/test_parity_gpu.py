@@ -161,6 +161,44 @@ def test_prepared_weight_images_follow_updates(cuda_dev):
     assert ops.prepared_weights(conv) is not None
 
 
+def test_full_size_adjoint_and_linearity(cuda_dev):
+    """BASELINE configs[1] size (2 x 150 k voxels): properties that need no CPU oracle.
+    <g, conv(x)> = <dgrad(g), x> = <W, wgrad(x, g)> (the three kernels are mutually adjoint), linearity in x, and
+    rulebook sanity (symmetric SubM table, centre offset = identity, order is a permutation)."""
+    from doda_b200 import ops
+    torch.manual_seed(3)
+    coords, shape = surface_coords(0, 150000, 2)
+    c = torch.from_numpy(coords).to(cuda_dev)
+    n = c.shape[0]
+    assert n == 300000
+    rb = ops.build_rulebook(c, 2, shape, 3, 1, 1, 1, subm=True)
+    nbr = rb.nbr
+    assert torch.equal(nbr[:, 13], torch.arange(n, device=cuda_dev, dtype=torch.int32))
+    # symmetry: j = nbr[i, k]  <=>  i = nbr[j, 26 - k]
+    for k in (0, 5, 12, 20):
+        i = torch.nonzero(nbr[:, k] >= 0).squeeze(1)
+        j = nbr[i, k].long()
+        assert torch.equal(nbr[j, 26 - k].long(), i)
+    assert torch.equal(torch.sort(rb.order.long()).values, torch.arange(n, device=cuda_dev))
+    assert int(rb.pairnum.sum()) == int((nbr >= 0).sum())
+    for Cin, Cout in ((16, 16), (32, 16)):
+        x = torch.randn(n, Cin, device=cuda_dev, requires_grad=True)
+        x2 = torch.randn(n, Cin, device=cuda_dev)
+        W = (torch.randn(3, 3, 3, Cin, Cout, device=cuda_dev) * 0.2).requires_grad_(True)
+        g = torch.randn(n, Cout, device=cuda_dev)
+        y = ops.SubMConvFunction.apply(x, W, rb)
+        y.backward(g)
+        a = float((g.double() * y.detach().double()).sum())
+        b = float((x.grad.double() * x.detach().double()).sum())
+        cc = float((W.grad.double() * W.detach().double()).sum())
+        scale = float(g.double().norm() * y.detach().double().norm())
+        assert abs(a - b) <= 1e-5 * scale and abs(a - cc) <= 1e-5 * scale, (a, b, cc, scale)
+        with torch.no_grad():
+            y2 = ops.SubMConvFunction.apply(x2, W, rb)
+            y12 = ops.SubMConvFunction.apply(2.0 * x.detach() - 3.0 * x2, W, rb)
+        assert rel_err(y12, 2.0 * y.detach().double() - 3.0 * y2.double()) <= TOL
+
+
 def test_conv1x1_fwd_bwd(cuda_dev):
     from doda_b200 import ops
     torch.manual_seed(0)
