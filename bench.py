@@ -225,14 +225,20 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # the clock sampler is an nvidia-smi subprocess: its start-up (fork + NVML init) stalls driver calls for up to a
+    # second, so it is started BEFORE the warm-up and must have delivered a sample before anything is timed
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(resident)
     timed(resident, 2, False)  # untimed pass through the timing harness itself (allocator / L2-flush steady state)
     timed(host, 1, True)
-    sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()
-        time.sleep(0.3)
+        t_wait = time.time()
+        while not sampler.rows and time.time() - t_wait < 10.0:
+            time.sleep(0.05)
+        sampler.rows.clear()  # keep only samples taken during the timed regions
     calls0 = ops.launch_count()
     ms_total = timed(resident, args.steps, False)
     launches = ops.launch_count() - calls0

@@ -403,7 +403,7 @@ using namespace b200sp;
 
 namespace b200sp {
 int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, int wflags, const int* tab, const int* orow,
-                const int* pin,
+                const int* rowmask, const int* pin,
                 const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out, int Cout,
                 int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st);
 int64_t conv_tc_ws_bytes(int K, int Cin, int Cout);
@@ -466,8 +466,8 @@ extern "C" int64_t b200sp_conv_ws_bytes(int K, int Cin, int Cout) {
 }
 
 extern "C" int b200sp_gather_gemm(const float* in, int64_t n_in, int Cin, const float* W, int wflags, const int32_t* tab,
-                                  const int32_t* orow, int K, float* out, int64_t n_out, int Cout, int accumulate,
-                                  void* ws, int64_t ws_bytes, void* stream) {
+                                  const int32_t* orow, const int32_t* rowmask, int K, float* out, int64_t n_out, int Cout,
+                                  int accumulate, void* ws, int64_t ws_bytes, void* stream) {
     (void)n_in;
     B200SP_CHECK_ARG(Cin >= 1 && Cout >= 1 && K >= 1, "gather_gemm: bad Cin/Cout/K");
     B200SP_CHECK_ARG(K <= GG_MAXK, "gather_gemm: K=%d > %d not supported by this build", K, GG_MAXK);
@@ -476,7 +476,7 @@ extern "C" int b200sp_gather_gemm(const float* in, int64_t n_in, int Cin, const 
     cudaStream_t st = (cudaStream_t)stream;
     if (conv_impl() == 0) {
         const int Ci_w = (wflags & 1) ? Cout : Cin, Co_w = (wflags & 1) ? Cin : Cout;
-        int rc = conv_tc_run(in, Cin, W, Ci_w, Co_w, wflags, tab, orow, nullptr, nullptr, nullptr, n_out, 0, K, out, Cout,
+        int rc = conv_tc_run(in, Cin, W, Ci_w, Co_w, wflags, tab, orow, rowmask, nullptr, nullptr, nullptr, n_out, 0, K, out, Cout,
                              accumulate, 0, ws, ws_bytes, st);
         if (rc != B200SP_EUNSUP) return rc;
     }
@@ -501,7 +501,7 @@ extern "C" int b200sp_gather_gemm_pairs(const float* in, int Cin, const float* W
     cudaStream_t st = (cudaStream_t)stream;
     if (conv_impl() == 0) {
         const int Ci_w = (wflags & 1) ? Cout : Cin, Co_w = (wflags & 1) ? Cin : Cout;
-        int rc = conv_tc_run(in, Cin, W, Ci_w, Co_w, wflags, nullptr, nullptr, pin, pout, pairnum_dev, n_upper, pstride, K,
+        int rc = conv_tc_run(in, Cin, W, Ci_w, Co_w, wflags, nullptr, nullptr, nullptr, pin, pout, pairnum_dev, n_upper, pstride, K,
                              out, Cout, accumulate, 1, ws, ws_bytes, st);
         if (rc != B200SP_EUNSUP) return rc;
     }

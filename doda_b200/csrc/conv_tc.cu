@@ -53,6 +53,7 @@ struct TCParams {
     const float* Wp;     // prepared weights: [K][nchunks]{hi block, lo block}, block = canonical [KC/4][Cout_pad/8][8][4] fp32
     const int* tab;      // [n_rows][K] or NULL (identity, K == 1)
     const int* orow;     // output row of table row r (NULL: identity)
+    const int* rowmask;  // K-bit mask of table row r (NULL: scan the table)
     const int* pin;      // pairs mode: [K][pstride]
     const int* pout;
     const int* pairnum;  // device [K]
@@ -62,14 +63,15 @@ struct TCParams {
     int Cin, Cout, K;
     int nchunks, Cout_pad;
     int accumulate, pairs_mode;
-    int nslots;
+    int nslots;             // A ring (gathered rows, hi + lo tiles)
+    int nslots_b;           // B ring (weight blocks): deeper, so weight copies run far ahead of the A slots
     uint32_t stageB_bytes;  // 2 * Cout_pad * KC * 4
     uint32_t tmem_cols;
     int ni;                 // MMA issuer warps in use (accumulators per set)
     int row_tiles;          // ceil(n_rows / 128)
     int total_tiles;        // row_tiles * (pairs_mode ? K : 1)
     int nsplit;             // table mode: the active offsets of a row tile are dealt to nsplit CTAs (atomic epilogue)
-    int dbg;                // dev only: 1 = skip the MMAs, 2 = skip the gathers, 4 = skip the transform
+    int dbg;                // dev only: 1 no MMAs, 2 no gathers, 4 no transform, 8 no epilogue data, 16 no table copy/mask, 32 no weight copies
 };
 
 template <int KC>
@@ -81,13 +83,15 @@ struct TCLayout {
     static constexpr uint32_t A_BYTES = (CPR * LBO + 127u) & ~127u;  // one of {hi, lo}
     __host__ __device__ static uint32_t meta_ints(int KT) { return (uint32_t)(TC_BM * KT + TC_BM + TC_MAXK + 4); }
     __host__ __device__ static uint32_t offB(int nslots) { return (uint32_t)nslots * 2u * A_BYTES; }
-    __host__ __device__ static uint32_t offMeta(int nslots, uint32_t stageB) { return offB(nslots) + (uint32_t)nslots * stageB; }
-    __host__ __device__ static uint32_t offBars(int nslots, uint32_t stageB, int KT) {
-        uint32_t o = offMeta(nslots, stageB) + TC_NBUF * meta_ints(KT) * 4u;
+    __host__ __device__ static uint32_t offMeta(int nslots, int nslots_b, uint32_t stageB) {
+        return offB(nslots) + (uint32_t)nslots_b * stageB;
+    }
+    __host__ __device__ static uint32_t offBars(int nslots, int nslots_b, uint32_t stageB, int KT) {
+        uint32_t o = offMeta(nslots, nslots_b, stageB) + TC_NBUF * meta_ints(KT) * 4u;
         return (o + 15u) & ~15u;
     }
-    __host__ __device__ static uint32_t total(int nslots, uint32_t stageB, int KT) {
-        return offBars(nslots, stageB, KT) + (uint32_t)(3 * nslots + 5 * TC_NBUF) * 8u + 16u;
+    __host__ __device__ static uint32_t total(int nslots, int nslots_b, uint32_t stageB, int KT) {
+        return offBars(nslots, nslots_b, stageB, KT) + (uint32_t)(3 * nslots + 2 * nslots_b + 5 * TC_NBUF) * 8u + 16u;
     }
 };
 
@@ -118,13 +122,16 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
     const int ni = p.ni;
     unsigned char* sA = smem;
     unsigned char* sB = smem + L::offB(S);
-    int* s_meta = reinterpret_cast<int*>(smem + L::offMeta(S, p.stageB_bytes));
+    const int SB = p.nslots_b;
+    int* s_meta = reinterpret_cast<int*>(smem + L::offMeta(S, SB, p.stageB_bytes));
     const int meta_ints = (int)L::meta_ints(KT);
     // per buffer: idx[128*KT] | orow[128] | klist[32] | nk | kfixed | pad
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::offBars(S, p.stageB_bytes, KT));  // hi+lo+weights ready -> MMA
-    uint64_t* empty = full + S;                                                            // MMA done -> slot reusable
-    uint64_t* raw = empty + S;                                                             // gathered rows landed -> transform
-    uint64_t* tready = raw + S;           // [NBUF] tile metadata published
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::offBars(S, SB, p.stageB_bytes, KT));  // hi+lo tiles ready -> MMA
+    uint64_t* empty = full + S;                                                                // MMA done -> A slot reusable
+    uint64_t* raw = empty + S;                                                                 // gathered rows landed -> transform
+    uint64_t* fullb = raw + S;            // [SB] weight block landed -> MMA
+    uint64_t* emptyb = fullb + SB;        // [SB] MMA done -> B slot reusable
+    uint64_t* tready = emptyb + SB;       // [NBUF] tile metadata published
     uint64_t* tfree = tready + TC_NBUF;   // [NBUF] every reader is done with the tile metadata
     uint64_t* accf = tfree + TC_NBUF;     // [NBUF] accumulator set complete -> epilogue
     uint64_t* acce = accf + TC_NBUF;      // [NBUF] accumulator set drained -> issuers
@@ -135,9 +142,13 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], TC_XFORM_THREADS / 32 + 1);
+            mbar_init(&full[s], TC_XFORM_THREADS / 32);
             mbar_init(&empty[s], 1);
             mbar_init(&raw[s], TC_LOADERS);
+        }
+        for (int s = 0; s < SB; ++s) {
+            mbar_init(&fullb[s], 1);
+            mbar_init(&emptyb[s], 1);
         }
         for (int b = 0; b < TC_NBUF; ++b) {
             mbar_init(&tready[b], 1);
@@ -193,13 +204,14 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                 const int rt = tile / p.nsplit, split = tile - rt * p.nsplit;
                 const int64_t row0 = (int64_t)rt * TC_BM;
                 const int rows = (int)min((int64_t)TC_BM, p.n_rows - row0);
-                unsigned mask = 0;
+                unsigned mask = 0, mrow = 0;
                 {
                     int ov[TC_BM / 32];
 #pragma unroll
                     for (int q = 0; q < TC_BM / 32; ++q) {
                         const int r = lane + 32 * q;
                         ov[q] = r < rows ? (p.orow ? __ldg(p.orow + row0 + r) : (int)(row0 + r)) : -1;
+                        if (p.rowmask && r < rows) mrow |= (unsigned)__ldg(p.rowmask + row0 + r);
                     }
 #pragma unroll
                     for (int q = 0; q < TC_BM / 32; ++q) orow[lane + 32 * q] = ov[q];
@@ -208,7 +220,10 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                     const int* t = p.tab + row0 * K;
                     const int tot = rows * K;
                     const uint32_t bytes = (uint32_t)tot * 4u;
-                    if (rows == TC_BM && (bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(t) & 15) == 0)) {
+                    if (p.dbg & 16) {
+                        if (lane == 0) mbar_arrive(&tload[b]);
+                        __syncwarp();
+                    } else if (rows == TC_BM && (bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(t) & 15) == 0)) {
                         // full tile: one bulk copy of the 128 x K table rows, then the offset mask from shared memory
                         if (lane == 0) {
                             mbar_arrive_expect_tx(&tload[b], bytes);
@@ -220,17 +235,22 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                         if (lane == 0) mbar_arrive(&tload[b]);  // keep the phase of this buffer's barrier in step
                         __syncwarp();
                     }
-                    int kk = lane % K;  // column of element e = lane, lane+32, ...
-                    const int step = 32 % K;
-                    for (int e = lane; e < TC_BM * K; e += 32) {
-                        if (idx[e] >= 0) mask |= 1u << kk;
-                        kk += step;
-                        if (kk >= K) kk -= K;
+                    if (p.rowmask) {
+                        mask = mrow;  // per-row masks from the rulebook builder: 4 words per lane instead of 4*K
+                    } else {
+                        int kk = lane % K;  // column of element e = lane, lane+32, ...
+                        const int step = 32 % K;
+                        for (int e = lane; e < ((p.dbg & 16) ? 0 : TC_BM * K); e += 32) {
+                            if (idx[e] >= 0) mask |= 1u << kk;
+                            kk += step;
+                            if (kk >= K) kk -= K;
+                        }
                     }
                 } else {
                     for (int r = lane; r < TC_BM; r += 32) idx[r] = r < rows ? (int)(row0 + r) : -1;
                     mask = rows > 0 ? 1u : 0u;
                 }
+                if (p.dbg & 16) mask = 0x1FFu;  // pretend 9 offsets
 #pragma unroll
                 for (int o = 16; o; o >>= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
                 if (lane == 0) {
@@ -364,7 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             const int nused = min(ni, nit);
             const uint32_t set_col = tmem + (uint32_t)(b * ni * p.Cout_pad);
             const bool split_mode = p.nsplit > 1;
-            for (int ch = 0; ch * 16 < ((split_mode && nit == 0) ? 0 : p.Cout_pad); ++ch) {
+            for (int ch = 0; ch * 16 < (((split_mode && nit == 0) || (p.dbg & 8)) ? 0 : p.Cout_pad); ++ch) {
                 float v[16];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) v[e] = 0.f;
@@ -446,12 +466,13 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                     // first global stage >= g0 owned by this issuer
                     int g = g0 + ((w - g0 % ni) + ni) % ni;
                     for (; g < g0 + nit; g += ni) {
-                        const int slot = g % S;
-                        const uint32_t sph = (uint32_t)(g / S) & 1u;
+                        const int slot = g % S, sb = g % SB;
+                        const uint32_t sph = (uint32_t)(g / S) & 1u, bph = (uint32_t)(g / SB) & 1u;
+                        mbar_wait(&fullb[sb], bph);
                         mbar_wait(&full[slot], sph);
                         tc_fence_after();
                         const uint64_t da = dA0 + (uint64_t)((uint32_t)slot * slotA16);
-                        const uint64_t db = dB0 + (uint64_t)((uint32_t)slot * slotB16);
+                        const uint64_t db = dB0 + (uint64_t)((uint32_t)sb * slotB16);
                         if (elect_one()) {
 #pragma unroll
                             for (int j = 0; j < ((p.dbg & 1) ? 0 : KC / 8); ++j) {
@@ -461,6 +482,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                                 acc = 1u;
                             }
                             mma_commit(&empty[slot]);
+                            mma_commit(&emptyb[sb]);
                         }
                         acc = 1u;
                         __syncwarp();
@@ -485,12 +507,16 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                 for (int kk = 0; kk < nk; ++kk) {
                     const int kw = p.pairs_mode ? kfixed : klist[kk];
                     for (int c = 0; c < nchunks; ++c) {
-                        mbar_wait(&empty[slot], sph ^ 1u);
-                        mbar_arrive_expect_tx(&full[slot], p.stageB_bytes);
+                        mbar_wait(&emptyb[slot], sph ^ 1u);
+                        if (p.dbg & 32) {
+                            mbar_arrive(&fullb[slot]);
+                        } else {
+                        mbar_arrive_expect_tx(&fullb[slot], p.stageB_bytes);
                         bulk_g2s(sB + (size_t)slot * p.stageB_bytes,
                                  reinterpret_cast<const unsigned char*>(p.Wp) + ((size_t)kw * nchunks + c) * p.stageB_bytes,
-                                 p.stageB_bytes, &full[slot]);
-                        if (++slot == S) {
+                                 p.stageB_bytes, &fullb[slot]);
+                        }
+                        if (++slot == SB) {
                             slot = 0;
                             sph ^= 1u;
                         }
@@ -579,7 +605,7 @@ __global__ void k_prep_weights_batch(const PrepItem* __restrict__ items) {
 }
 
 struct TCPlan {
-    int KC, nchunks, Cout_pad, nslots, ni;
+    int KC, nchunks, Cout_pad, nslots, nslots_b, ni;
     uint32_t stageB, tmem_cols, smem;
     int64_t wp_bytes;
 };
@@ -595,18 +621,39 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
     pl.wp_bytes = (int64_t)K * pl.nchunks * pl.stageB;
     const uint32_t cpr = (uint32_t)pl.KC / 4u;
     const uint32_t a_bytes = 2u * ((cpr * (TC_BM * 16u + 128u / cpr) + 127u) & ~127u);
-    const uint32_t fixed = TC_NBUF * (uint32_t)(TC_BM * KT + TC_BM + TC_MAXK + 4) * 4u + 512u;
+    const uint32_t fixed = TC_NBUF * (uint32_t)(TC_BM * KT + TC_BM + TC_MAXK + 4) * 4u + 1536u;
     // slots: 4 under ~110 KB lets two CTAs share an SM; big stages fall back to fewer slots / one CTA per SM
     int best = 0;
-    for (int s = 4; s >= 2; --s) {
+    int smax = 4;
+    uint32_t two_cta_budget = 110u * 1024u;
+    {
+        const char* e = getenv("B200SP_TC_SLOTS");  // dev knob: > 4 trades the second CTA per SM for a deeper ring
+        if (e && atoi(e) >= 2) {
+            smax = atoi(e);
+            if (smax > 4) two_cta_budget = 0;
+        }
+    }
+    uint32_t budget = 0;
+    for (int s = smax; s >= 2; --s) {
         const uint32_t tot = (uint32_t)s * (a_bytes + pl.stageB) + fixed;
-        if (tot <= 110u * 1024u || (s <= 3 && tot <= 220u * 1024u)) {
+        if (tot <= two_cta_budget || ((s <= 3 || smax > 4) && tot <= 220u * 1024u)) {
             best = s;
+            budget = tot <= two_cta_budget ? two_cta_budget : 220u * 1024u;
             break;
         }
     }
     if (best == 0) return false;
     pl.nslots = best;
+    // weight ring: as deep as the remaining budget allows (multiple of the A ring, at most 4x), because a weight
+    // block can only be requested once its slot is free and its L2 latency would otherwise sit in every A slot's chain
+    {
+        const uint32_t used = (uint32_t)best * a_bytes + fixed;
+        int mult = 4;
+        const char* e = getenv("B200SP_TC_BMULT");
+        if (e && atoi(e) >= 1) mult = atoi(e);
+        while (mult > 1 && used + (uint32_t)(best * mult) * (pl.stageB + 16u) > budget) --mult;
+        pl.nslots_b = best * mult;
+    }
     // issuer warps: each smem slot must belong to exactly ONE issuer (its mbarrier waits are parity waits, an issuer
     // running a fill ahead of a slot it shares would alias phases), so ni divides nslots; two accumulator sets
     {
@@ -629,7 +676,7 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
 template <int KC>
 static int launch_tc(const TCParams& p, int KT, cudaStream_t st) {
     using L = TCLayout<KC>;
-    const uint32_t smem = L::total(p.nslots, p.stageB_bytes, KT);
+    const uint32_t smem = L::total(p.nslots, p.nslots_b, p.stageB_bytes, KT);
     static uint32_t attr_smem = 0;
     if (smem > attr_smem) {
         B200SP_CUDA(cudaFuncSetAttribute(k_conv_tc<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -646,7 +693,7 @@ static int launch_tc(const TCParams& p, int KT, cudaStream_t st) {
 
 // returns B200SP_EUNSUP when the shape is outside what the tensor path covers (caller falls back to the fp32 kernel)
 int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, int wflags, const int* tab, const int* orow,
-                const int* pin, const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out,
+                const int* rowmask, const int* pin, const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out,
                 int Cout, int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st) {
     TCPlan pl;
     const int KT = pairs_mode ? 1 : K;
@@ -667,10 +714,10 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
         B200SP_LAUNCH_CHECK();
     }
     TCParams p{};
-    p.in = in; p.Wp = Wp; p.tab = tab; p.orow = orow; p.pin = pin; p.pout = pout; p.pairnum = pairnum; p.out = out;
+    p.in = in; p.Wp = Wp; p.tab = tab; p.orow = orow; p.rowmask = rowmask; p.pin = pin; p.pout = pout; p.pairnum = pairnum; p.out = out;
     p.n_rows = n_rows; p.pstride = pstride; p.Cin = Cin; p.Cout = Cout; p.K = K;
     p.nchunks = pl.nchunks; p.Cout_pad = pl.Cout_pad; p.accumulate = accumulate; p.pairs_mode = pairs_mode;
-    p.nslots = pl.nslots; p.stageB_bytes = pl.stageB; p.tmem_cols = pl.tmem_cols; p.ni = pl.ni;
+    p.nslots = pl.nslots; p.nslots_b = pl.nslots_b; p.stageB_bytes = pl.stageB; p.tmem_cols = pl.tmem_cols; p.ni = pl.ni;
     {
         const char* e = getenv("B200SP_TC_DEBUG");
         p.dbg = e ? atoi(e) : 0;

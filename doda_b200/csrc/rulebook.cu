@@ -80,12 +80,14 @@ __global__ void k_row_masks(const int* __restrict__ nbr, int64_t M, int K, unsig
     }
 }
 __global__ void k_permute_rows(const int* __restrict__ nbr, const int* __restrict__ order, int64_t M, int K,
-                               int* __restrict__ nbr_perm) {
+                               int* __restrict__ nbr_perm, const unsigned long long* __restrict__ sorted_masks,
+                               int* __restrict__ rowmask) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * K) return;
     int64_t i = idx / K;
     int k = (int)(idx - i * K);
     nbr_perm[idx] = __ldg(&nbr[(int64_t)__ldg(&order[i]) * K + k]);
+    if (k == 0 && rowmask) rowmask[i] = (int)(unsigned)sorted_masks[i];  // the sort keys ARE the masks, in order
 }
 
 // ---------------- strided conv ----------------
@@ -336,8 +338,8 @@ extern "C" int64_t b200sp_rulebook_ws_bytes(int64_t M_in, int K, int cand_per_in
 
 extern "C" int b200sp_rulebook_subm(const int32_t* coords, int64_t M, int batch, const int32_t* shape,
                                     const int32_t* ksize, const int32_t* dil, int32_t* nbr, int32_t* pairs,
-                                    int32_t* pairnum, int32_t* order, int32_t* nbr_perm, void* ws, int64_t ws_bytes,
-                                    void* stream) {
+                                    int32_t* pairnum, int32_t* order, int32_t* nbr_perm, int32_t* rowmask, void* ws,
+                                    int64_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     Geo g;
     B200SP_CHECK_ARG(shape && ksize, "rulebook_subm: null shape/ksize");
@@ -385,7 +387,7 @@ extern "C" int b200sp_rulebook_subm(const int32_t* coords, int64_t M, int batch,
         }
         k_row_masks<<<(unsigned)std::min<int64_t>(cdiv(M, 8), 148 * 8), 256, 0, st>>>(nbr, M, g.K, mk, iota);
         B200SP_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cub_bytes, mk, mk2, iota, order, (int)M, 0, g.K, st));
-        k_permute_rows<<<(unsigned)cdiv(M * g.K, 256), 256, 0, st>>>(nbr, order, M, g.K, nbr_perm);
+        k_permute_rows<<<(unsigned)cdiv(M * g.K, 256), 256, 0, st>>>(nbr, order, M, g.K, nbr_perm, mk2, rowmask);
         B200SP_LAUNCH_CHECK_N(2 + 4);
     }
     if (pairs) {

@@ -144,7 +144,7 @@ class Rulebook(object):
 
     __slots__ = ("kind", "outids", "indices", "pairs", "pairnum", "spatial_shape", "out_spatial_shape", "K",
                  "ksize", "stride", "padding", "dilation", "nbr", "fwd", "bwd", "nonoverlap", "batch_size", "order",
-                 "nbr_perm")
+                 "nbr_perm", "rowmask")
 
     def __iter__(self):
         return iter((self.outids, self.indices, self.pairs, self.pairnum, self.spatial_shape))
@@ -187,7 +187,7 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding=
         side.wait_stream(main)  # coordinates produced on the caller's stream (first level only)
     with torch.cuda.stream(side):
         rb = _build_rulebook(indices, batch_size, spatial_shape, ksize, stride, padding, dilation, subm, need_pairs)
-        for name in ("pairs", "pairnum", "nbr", "fwd", "bwd", "order", "nbr_perm", "outids"):
+        for name in ("pairs", "pairnum", "nbr", "fwd", "bwd", "order", "nbr_perm", "rowmask", "outids"):
             t = getattr(rb, name)
             if t is not None:
                 t.record_stream(main)
@@ -211,7 +211,7 @@ def _build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding
     rb = Rulebook()
     rb.K, rb.ksize, rb.stride, rb.padding, rb.dilation = K, ks, st, pd, dl
     rb.indices, rb.spatial_shape, rb.batch_size = indices, shape, int(batch_size)
-    rb.nbr = rb.fwd = rb.bwd = rb.order = rb.nbr_perm = None
+    rb.nbr = rb.fwd = rb.bwd = rb.order = rb.nbr_perm = rb.rowmask = None
     rb.pairs = torch.empty((2, K, M), dtype=_I32, device=dev) if need_pairs else None
     rb.pairnum = torch.empty((K,), dtype=_I32, device=dev) if need_pairs else None
     pp = rb.pairs.data_ptr() if need_pairs else None
@@ -225,12 +225,14 @@ def _build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding
         if mask_order:
             rb.order = torch.empty((M,), dtype=_I32, device=dev)
             rb.nbr_perm = torch.empty((M, K), dtype=_I32, device=dev)
+            rb.rowmask = torch.empty((M,), dtype=_I32, device=dev)
         wsb = lib.b200sp_rulebook_ws_bytes(M, K, 1)
         ws = _workspace(wsb, dev, "rb")
         check(lib.b200sp_rulebook_subm(indices.data_ptr(), M, int(batch_size), _carr(shape), _carr(ks), _carr(dl),
                                        rb.nbr.data_ptr(), pp, pn,
                                        rb.order.data_ptr() if mask_order else None,
                                        rb.nbr_perm.data_ptr() if mask_order else None,
+                                       rb.rowmask.data_ptr() if mask_order else None,
                                        ws.data_ptr(), ws.numel(), _stream()), "rulebook_subm")
         return rb
     rb.kind = "conv"
@@ -291,7 +293,7 @@ def _conv_dims(W3, wflags):
     return (K, Co_w, Ci_w) if (wflags & 1) else (K, Ci_w, Co_w)
 
 
-def gather_gemm(feat, W3, tab, n_out, out=None, accumulate=False, wflags=W_FWD, orow=None, wimg=None):
+def gather_gemm(feat, W3, tab, n_out, out=None, accumulate=False, wflags=W_FWD, orow=None, wimg=None, rowmask=None):
     """out[r] = sum_k feat[tab[r,k]] @ Wk;  W3 = the module weight viewed [K,Ci_w,Co_w]; Wk = W3[k] (wflags 0),
     W3[k]^T (W_T) or W3[K-1-k]^T (W_T_MIRROR); tab None -> dense GEMM (K==1).  wimg: the tensor-core image of W3
     for these wflags, prepared ahead by prepare_weights (skips the per-call weight pre-pass)."""
@@ -307,14 +309,16 @@ def gather_gemm(feat, W3, tab, n_out, out=None, accumulate=False, wflags=W_FWD, 
     if _prof is None:
         check(lib.b200sp_gather_gemm(feat.data_ptr(), feat.shape[0], Cin, wptr, wfl,
                                      tab.data_ptr() if tab is not None else None,
-                                     orow.data_ptr() if orow is not None else None, K, out.data_ptr(), n_out, Cout,
+                                     orow.data_ptr() if orow is not None else None,
+                                     rowmask.data_ptr() if rowmask is not None else None, K, out.data_ptr(), n_out, Cout,
                                      1 if accumulate else 0, wsp, wsn, _stream()), "gather_gemm")
         return out
     with _Timed(kernel="k_gather_gemm", n_in=feat.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K,
                 tab_entries=n_out * K if tab is not None else 0, pairs_dense=n_out * K):
         check(lib.b200sp_gather_gemm(feat.data_ptr(), feat.shape[0], Cin, wptr, wfl,
                                      tab.data_ptr() if tab is not None else None,
-                                     orow.data_ptr() if orow is not None else None, K, out.data_ptr(), n_out, Cout,
+                                     orow.data_ptr() if orow is not None else None,
+                                     rowmask.data_ptr() if rowmask is not None else None, K, out.data_ptr(), n_out, Cout,
                                      1 if accumulate else 0, wsp, wsn, _stream()), "gather_gemm")
     return out
 
@@ -477,7 +481,8 @@ class SubMConvFunction(Function):
         ctx.rb, ctx.prep = rb, prep
         ctx.save_for_backward(features, filters)
         tab, orow = (rb.nbr_perm, rb.order) if rb.nbr_perm is not None else (rb.nbr, None)
-        return gather_gemm(features, W3, tab, features.shape[0], orow=orow, wimg=prep[0] if prep else None)
+        return gather_gemm(features, W3, tab, features.shape[0], orow=orow, wimg=prep[0] if prep else None,
+                           rowmask=rb.rowmask if rb.nbr_perm is not None else None)
 
     @staticmethod
     def backward(ctx, grad_out):
@@ -490,7 +495,8 @@ class SubMConvFunction(Function):
         if ctx.needs_input_grad[0]:
             tab, orow = (rb.nbr_perm, rb.order) if rb.nbr_perm is not None else (rb.nbr, None)
             din = gather_gemm(grad_out, W3, tab, M, wflags=W_T_MIRROR, orow=orow,
-                              wimg=ctx.prep[1] if ctx.prep else None)
+                              wimg=ctx.prep[1] if ctx.prep else None,
+                              rowmask=rb.rowmask if rb.nbr_perm is not None else None)
         if ctx.needs_input_grad[1]:
             dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K).view(filters.shape)
         return din, dW, None, None

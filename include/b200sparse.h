@@ -42,6 +42,8 @@ int64_t b200sp_launch_count(void);
  *   nbr  [M, K]           SubM: nbr[q,k] = input row at site(q) + (k - centre)   (out -> in view)
  *   order [M]             SubM: the engine's processing order = rows stably sorted by their neighbour bitmask
  *                         (bit k set <=> nbr[q,k] >= 0);
+ *   rowmask [M]           rowmask[i] = the K-bit mask of row order[i] (lets the conv kernel find a tile's present
+ *                         offsets from 128 words instead of scanning 128 x K table entries);
  *   nbr_perm [M, K]       nbr_perm[i,k] = nbr[order[i],k].  The 128 rows of a tile then share (nearly) one set of
  *                         present offsets: absent offsets drop out per tile and most gathered rows are real
  *   fwd  [M_in, K]        strided conv: fwd[j,k] = output row reached by input j through offset k
@@ -58,7 +60,8 @@ int b200sp_rulebook_subm(const int32_t* coords_dev, int64_t M, int batch, const 
                          const int32_t* ksize_host /*[3]*/, const int32_t* dil_host /*[3]*/,
                          int32_t* nbr_dev /*[M,K] or NULL*/, int32_t* pairs_dev /*[2,K,M] or NULL*/,
                          int32_t* pairnum_dev /*[K] or NULL*/, int32_t* order_dev /*[M] or NULL*/,
-                         int32_t* nbr_perm_dev /*[M,K] or NULL*/, void* ws_dev, int64_t ws_bytes, void* stream);
+                         int32_t* nbr_perm_dev /*[M,K] or NULL*/, int32_t* rowmask_dev /*[M] or NULL*/, void* ws_dev,
+                         int64_t ws_bytes, void* stream);
 
 /* Regular (strided) sparse conv.  Output sites are returned in ascending flattened index
  * (the spconv-CUDA convention).  out_coords/bwd must be sized for the upper bound
@@ -88,8 +91,9 @@ int b200sp_pairs_to_table(const int32_t* pairs_dev, const int32_t* pairnum_dev, 
  * the out->in table of the adjoint; bit2: W_dev is an image made by b200sp_prep_weights_batch with the same bits 0-1.
  * ------------------------------------------------------------------------------------------ */
 int b200sp_gather_gemm(const float* in_dev, int64_t n_in, int Cin, const float* W_dev, int wflags,
-                       const int32_t* tab_dev, const int32_t* orow_dev, int K, float* out_dev, int64_t n_out, int Cout,
-                       int accumulate, void* ws_dev, int64_t ws_bytes, void* stream);
+                       const int32_t* tab_dev, const int32_t* orow_dev, const int32_t* rowmask_dev /*or NULL*/, int K,
+                       float* out_dev, int64_t n_out, int Cout, int accumulate, void* ws_dev, int64_t ws_bytes,
+                       void* stream);
 
 /* pair-grouped variant (each output row written by exactly one pair; used for the non-overlapping
  * inverse conv forward and the strided conv dgrad):  out[po[k][i],:] = in[pi[k][i],:] @ W[k].

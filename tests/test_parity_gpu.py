@@ -353,6 +353,7 @@ def test_conv_impls_agree(cuda_dev, impl):
     assert np.array_equal(rb.nbr_perm.cpu().numpy(), nbr[order])
     masks = ((nbr >= 0).astype(np.int64) << np.arange(27)).sum(1)
     assert np.all(np.diff(masks[order]) >= 0)
+    assert np.array_equal(rb.rowmask.cpu().numpy().astype(np.int64), masks[order])
     feat = torch.randn(n, 32, device=cuda_dev)
     W3 = torch.randn(27, 32, 48, device=cuda_dev) * 0.2
     ref = torch.zeros(n, 48, dtype=torch.float64)
@@ -364,6 +365,8 @@ def test_conv_impls_agree(cuda_dev, impl):
     try:
         a = ops.gather_gemm(feat, W3, rb.nbr, n)
         b = ops.gather_gemm(feat, W3, rb.nbr_perm, n, orow=rb.order)
+        b2 = ops.gather_gemm(feat, W3, rb.nbr_perm, n, orow=rb.order, rowmask=rb.rowmask)
+        assert torch.equal(b, b2) or impl == "tc" and rel_err(b2, b) <= 1e-5
     finally:
         ops.set_conv_impl("tc")
     assert rel_err(a, ref) <= TOL and rel_err(b, ref) <= TOL

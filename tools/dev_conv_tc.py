@@ -60,9 +60,9 @@ def case(M, Cin, Cout, check=True, surface=False):
         else:
             err2 = float("nan")
         ms = timeit(lambda: ops.gather_gemm(feat, W3, rb.nbr, n))
-        outm = ops.gather_gemm(feat, W3, rb.nbr_perm, n, orow=rb.order)
+        outm = ops.gather_gemm(feat, W3, rb.nbr_perm, n, orow=rb.order, rowmask=rb.rowmask)
         errm = float((outm - out).abs().max() / out.abs().max())
-        msm = timeit(lambda: ops.gather_gemm(feat, W3, rb.nbr_perm, n, orow=rb.order))
+        msm = timeit(lambda: ops.gather_gemm(feat, W3, rb.nbr_perm, n, orow=rb.order, rowmask=rb.rowmask))
         res[impl] = (err, err2, ms, errm, msm)
     P = int((rb.nbr >= 0).sum())
     t = (rb.nbr_perm[: (n // 128) * 128].view(-1, 128, 27) >= 0).any(1).sum(1).float().mean().item()

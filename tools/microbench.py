@@ -48,8 +48,8 @@ for name, M, occ in cases:
         x = torch.randn(n, C, device=dev)
         g = torch.randn(n, C, device=dev)
         W3 = torch.randn(27, C, C, device=dev) * 0.1
-        t_f = timeit(lambda: ops.gather_gemm(x, W3, rb.nbr_perm, n, orow=rb.order))
-        t_d = timeit(lambda: ops.gather_gemm(g, W3, rb.nbr_perm, n, orow=rb.order, wflags=ops.W_T_MIRROR))
+        t_f = timeit(lambda: ops.gather_gemm(x, W3, rb.nbr_perm, n, orow=rb.order, rowmask=rb.rowmask))
+        t_d = timeit(lambda: ops.gather_gemm(g, W3, rb.nbr_perm, n, orow=rb.order, wflags=ops.W_T_MIRROR, rowmask=rb.rowmask))
         t_w = timeit(lambda: ops.wgrad(x, g, rb.pairs[0], rb.pairs[1], rb.pairnum, n, 27))
         b_c = 4 * (2 * n * C) + 4 * 27 * C * C + 4 * n * 27
         b_w = P * (8 + 8 * C) + 4 * 27 * C * C

@@ -18,7 +18,7 @@ W3 = torch.randn(27, Cin, Cout, device=dev) * 0.2
 g = torch.randn(n, Cout, device=dev)
 ops.set_conv_impl(impl)
 for _ in range(reps):
-    out = ops.gather_gemm(feat, W3, rb.nbr_perm, n, orow=rb.order)
+    out = ops.gather_gemm(feat, W3, rb.nbr_perm, n, orow=rb.order, rowmask=rb.rowmask)
     dW = ops.wgrad(feat, g, rb.pairs[0], rb.pairs[1], rb.pairnum, n, 27)
 torch.cuda.synchronize()
 print("done", out.shape, dW.shape)
