@@ -52,25 +52,49 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe), taken in-process
+    through NVML (nvidia_ml_py).  An `nvidia-smi -lms` subprocess was used first: its queries stalled the CUDA
+    process for 40-100 ms at a time (visible as outlier steps); it remains the fallback when NVML is unavailable."""
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.2):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt, self.proc = index, [], threading.Event(), None
+        self.index, self.rows, self._stop_evt, self.proc, self.period = index, [], threading.Event(), None, period
 
-    def run(self):
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        bits = [("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8))),
+                ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40))),
+                ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20))),
+                ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))]
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop_evt.is_set():
+            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+            r = int(get_reasons(h))
+            self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
+            self._stop_evt.wait(self.period)
+
+    def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits", "-lms", "500"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+            if self._stop_evt.is_set():
+                break
+
+    def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
-                if self._stop_evt.is_set():
-                    break
+            self._run_nvml()
         except Exception:
-            pass
+            try:
+                self._run_smi()
+            except Exception:
+                pass
 
     def stop(self):
         self._stop_evt.set()
@@ -104,10 +128,10 @@ def make_batch(rank, bs, voxels):
 
 
 def conv_layer_bytes(rec):
-    """Algorithmic (compulsory) bytes of one gather-GEMM launch, SURVEY.md §8(d):
-    4*(M_in*Cin + M_out*Cout) + 4*K*Cin*Cout + 4*(table entries read)."""
+    """Algorithmic (compulsory) bytes of one conv launch, SURVEY.md §8(d):
+    4*(M_in*Cin + M_out*Cout) + 4*K*Cin*Cout + 8*P   (P = rulebook pairs of the layer)."""
     return 4 * (rec["n_in"] * rec["Cin"] + rec["n_out"] * rec["Cout"]) + 4 * rec["K"] * rec["Cin"] * rec["Cout"] \
-        + 4 * rec["tab_entries"]
+        + 8 * rec["pairs"]
 
 
 def run_reference(args):
@@ -207,7 +231,10 @@ def main():
         torch.cuda.synchronize()
 
     def timed(b, nsteps, read_loss):
+        import gc
         evs = []
+        gc.collect()
+        gc.disable()  # a gen-2 collection inside the loop shows up as a 50-100 ms outlier step
         barrier()
         for _ in range(nsteps):
             flush.zero_()  # L2 flush between timed iterations (not timed)
@@ -219,7 +246,10 @@ def main():
             e.record()
             evs.append((s, e))
         barrier()
-        tot = sum(s.elapsed_time(e) for s, e in evs)
+        gc.enable()
+        per_step = [s.elapsed_time(e) for s, e in evs]
+        timed.last_steps = per_step
+        tot = sum(per_step)
         t = torch.tensor([tot], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -241,6 +271,7 @@ def main():
         sampler.rows.clear()  # keep only samples taken during the timed regions
     calls0 = ops.launch_count()
     ms_total = timed(resident, args.steps, False)
+    steps_ms = [round(v, 3) for v in timed.last_steps]
     launches = ops.launch_count() - calls0
     ms_e2e = timed(host, args.steps, True)
     if sampler:
@@ -272,7 +303,7 @@ def main():
             g_bytes = conv_layer_bytes(grp[0])
             tot_ms = sum(r["ms"] for r in gg)
             tot_bytes = sum(conv_layer_bytes(r) for r in gg)
-            tot_flops = sum(2.0 * r["pairs_dense"] * r["Cin"] * r["Cout"] for r in gg)
+            tot_flops = sum(2.0 * r["pairs"] * r["Cin"] * r["Cout"] for r in gg)
             all_ms = sum(r["ms"] for r in recs)
             peak, how = peaks()
             ach = g_bytes / (g_ms * 1e-3) / 1e9
@@ -316,7 +347,8 @@ def main():
                           % world, "l2": "256 MB flush between timed steps"},
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                        "ms_per_step": ms_e2e / args.steps},
-               "gpu_launches": launches, "clocks": sampler.summary() if sampler else None}
+               "gpu_launches": launches, "clocks": sampler.summary() if sampler else None,
+               "step_ms_rank0": steps_ms}
         if roof:
             out["roofline"] = roof
         if cpu_base:

@@ -313,8 +313,9 @@ def gather_gemm(feat, W3, tab, n_out, out=None, accumulate=False, wflags=W_FWD, 
                                      rowmask.data_ptr() if rowmask is not None else None, K, out.data_ptr(), n_out, Cout,
                                      1 if accumulate else 0, wsp, wsn, _stream()), "gather_gemm")
         return out
+    pairs = int((tab >= 0).sum()) if tab is not None else int(n_out)  # profile pass only (host sync)
     with _Timed(kernel="k_gather_gemm", n_in=feat.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K,
-                tab_entries=n_out * K if tab is not None else 0, pairs_dense=n_out * K):
+                tab_entries=n_out * K if tab is not None else 0, pairs_dense=n_out * K, pairs=pairs):
         check(lib.b200sp_gather_gemm(feat.data_ptr(), feat.shape[0], Cin, wptr, wfl,
                                      tab.data_ptr() if tab is not None else None,
                                      orow.data_ptr() if orow is not None else None,
@@ -333,8 +334,9 @@ def gather_gemm_pairs(feat, W3, pin, pout, pairnum, n_upper, n_out, wflags=W_FWD
     else:
         ws = _workspace(_conv_ws_bytes(K, Cin, Cout), feat.device, "conv")
         wptr, wfl, wsp, wsn = W3.data_ptr(), wflags, ws.data_ptr(), ws.numel()
+    pairs = int(pairnum.sum()) if _prof is not None else 0
     with _Timed(kernel="k_gather_gemm", n_in=feat.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K,
-                tab_entries=2 * n_upper, pairs_dense=n_upper, pairs_mode=1):
+                tab_entries=2 * n_upper, pairs_dense=n_upper, pairs_mode=1, pairs=pairs):
         check(lib.b200sp_gather_gemm_pairs(feat.data_ptr(), Cin, wptr, wfl, pin.data_ptr(),
                                            pout.data_ptr(), pairnum.data_ptr(), n_upper, K, pin.stride(0),
                                            out.data_ptr(), Cout, 0, wsp, wsn, _stream()),

@@ -28,7 +28,7 @@ def timeit(fn, n=5):
 
 print("# Microbench sweep (round 1): SubM 3x3x3 rulebook build and fused conv kernels, L2 flushed between launches\n")
 print("peak = " + ("%.1f" % peak) + " GB/s (MEASURED_PEAKS.json, of measured).  Algorithmic bytes: rulebook 16M + 8P + 4K + 8MK (two tables); "
-      "conv 4(M Cin + M Cout) + 4 K Cin Cout + 4 M K; wgrad P(8 + 4Cin + 4Cout) + 4 K Cin Cout.\n")
+      "conv 4(M Cin + M Cout) + 4 K Cin Cout + 8 P; wgrad P(8 + 4Cin + 4Cout) + 4 K Cin Cout.\n")
 print("| scene | M | P/M | rulebook ms | GB/s | frac | C | fwd ms | GB/s | frac | dgrad ms | wgrad ms | GB/s | frac |")
 print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
 cases = [("uniform %.1f%%" % (100 * occ), M, occ) for M in (10000, 100000, 1000000) for occ in (0.005, 0.02, 0.05)]
@@ -51,7 +51,7 @@ for name, M, occ in cases:
         t_f = timeit(lambda: ops.gather_gemm(x, W3, rb.nbr_perm, n, orow=rb.order, rowmask=rb.rowmask))
         t_d = timeit(lambda: ops.gather_gemm(g, W3, rb.nbr_perm, n, orow=rb.order, wflags=ops.W_T_MIRROR, rowmask=rb.rowmask))
         t_w = timeit(lambda: ops.wgrad(x, g, rb.pairs[0], rb.pairs[1], rb.pairnum, n, 27))
-        b_c = 4 * (2 * n * C) + 4 * 27 * C * C + 4 * n * 27
+        b_c = 4 * (2 * n * C) + 4 * 27 * C * C + 8 * P
         b_w = P * (8 + 8 * C) + 4 * 27 * C * C
         gf, gw = b_c / t_f / 1e6, b_w / t_w / 1e6
         print("| %s | %d | %.1f | %s | %s | %s | %d | %.3f | %.0f | %.3f | %.3f | %.3f | %.0f | %.3f |" % (
