@@ -592,6 +592,151 @@ class SparseInverseConvFunction(Function):
         return din, dW, None, None
 
 
+_CONV_FN = {"subm": SubMConvFunction, "dense": DenseConvFunction, "conv": SparseConvFunction,
+            "inverse": SparseInverseConvFunction}
+
+
+def conv_forward_raw(kind, features, filters, rb, prep):
+    """forward of one sparse conv on contiguous fp32 CUDA features (no autograd bookkeeping)"""
+    W3 = _w3(filters)
+    wf = prep[0] if prep else None
+    if kind == "subm":
+        if rb.nbr_perm is not None:
+            return gather_gemm(features, W3, rb.nbr_perm, features.shape[0], orow=rb.order, wimg=wf, rowmask=rb.rowmask)
+        return gather_gemm(features, W3, rb.nbr, features.shape[0], wimg=wf)
+    if kind == "dense":
+        return gather_gemm(features, W3, None, features.shape[0], wimg=wf)
+    if kind == "conv":
+        return gather_gemm(features, W3, rb.bwd, rb.outids.shape[0], wimg=wf)
+    n_fine = rb.indices.shape[0]  # inverse
+    if rb.nonoverlap:
+        return gather_gemm_pairs(features, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, n_fine, wimg=wf)
+    return gather_gemm(features, W3, rb.fwd, n_fine, wimg=wf)
+
+
+def conv_backward_raw(kind, features, filters, grad_out, rb, prep, need_din=True, need_dw=True):
+    """-> (din, dW) of one sparse conv"""
+    W3 = _w3(filters)
+    wb = prep[1] if prep else None
+    M = features.shape[0]
+    din = dW = None
+    if kind == "subm":
+        if need_din:
+            if rb.nbr_perm is not None:
+                din = gather_gemm(grad_out, W3, rb.nbr_perm, M, wflags=W_T_MIRROR, orow=rb.order, wimg=wb,
+                                  rowmask=rb.rowmask)
+            else:
+                din = gather_gemm(grad_out, W3, rb.nbr, M, wflags=W_T_MIRROR, wimg=wb)
+        if need_dw:
+            dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K)
+    elif kind == "dense":
+        if need_din:
+            din = gather_gemm(grad_out, W3, None, M, wflags=W_T, wimg=wb)
+        if need_dw:
+            dW = wgrad(features, grad_out, None, None, None, M, 1)
+    elif kind == "conv":
+        if need_din:
+            if rb.nonoverlap:
+                din = gather_gemm_pairs(grad_out, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, M, M, wflags=W_T, wimg=wb)
+            else:
+                din = gather_gemm(grad_out, W3, rb.fwd, M, wflags=W_T, wimg=wb)
+        if need_dw:
+            dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K)
+    else:  # inverse
+        n_fine = rb.indices.shape[0]
+        if need_din:
+            din = gather_gemm(grad_out, W3, rb.bwd, M, wflags=W_T, wimg=wb)
+        if need_dw:
+            dW = wgrad(features, grad_out, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, rb.K)
+    return din, (dW.view(filters.shape) if dW is not None else None)
+
+
+def _bn_forward_raw(x, weight, bias, running_mean, running_var, nbt, momentum, eps, relu):
+    M, C = x.shape
+    dev = x.device
+    y = torch.empty_like(x)
+    stats = torch.empty((2, C), dtype=_F32, device=dev)
+    ws = _workspace(_bn_ws_bytes(C), dev, "bn")
+    with _Timed(kernel="bn_fwd", M=M, C=C):
+        check(lib.b200sp_bn_fwd_train(x.data_ptr(), M, C, weight.data_ptr() if weight is not None else None,
+                                      bias.data_ptr() if bias is not None else None, float(eps), 1 if relu else 0,
+                                      y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+                                      running_mean.data_ptr() if running_mean is not None else None,
+                                      running_var.data_ptr() if running_var is not None else None,
+                                      float(momentum), nbt.data_ptr() if nbt is not None else None, ws.data_ptr(),
+                                      ws.numel(), _stream()), "bn_fwd_train")
+    return y, stats
+
+
+def _bn_backward_raw(x, dy, weight, bias, stats, relu):
+    M, C = x.shape
+    dev = x.device
+    dx = torch.empty_like(x)
+    dwb = torch.empty((2, C), dtype=_F32, device=dev)
+    ws = _workspace(_bn_ws_bytes(C), dev, "bn")
+    with _Timed(kernel="bn_bwd", M=M, C=C):
+        check(lib.b200sp_bn_bwd(x.data_ptr(), dy.data_ptr(), M, C,
+                                weight.data_ptr() if weight is not None else None,
+                                bias.data_ptr() if bias is not None else None, stats[0].data_ptr(),
+                                stats[1].data_ptr(), 1 if relu else 0, dx.data_ptr(), dwb[0].data_ptr(),
+                                dwb[1].data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "bn_bwd")
+    return dx, dwb
+
+
+class BNReLUConvFunction(Function):
+    """BatchNorm (batch statistics) -> ReLU -> sparse conv as ONE autograd node: DODA puts this triplet in front of
+    64 of its 71 convs (model/unet_block.py:24-29,46-48,68-70,76-78).  Same kernels as the separate nodes, half the
+    Python / autograd-engine overhead per layer.  Returns (conv output, the BN+ReLU activation); the second output
+    keeps spconv's SparseSequential semantics (it becomes `input.features`) and stays differentiable."""
+
+    @staticmethod
+    def forward(ctx, x, bn_w, bn_b, filters, running_mean, running_var, nbt, momentum, eps, rb, prep, kind):
+        _req_cuda(x, filters)
+        x = _f32c(x)
+        y, stats = _bn_forward_raw(x, bn_w, bn_b, running_mean, running_var, nbt, momentum, eps, True)
+        out = conv_forward_raw(kind, y, filters, rb, prep)
+        ctx.save_for_backward(x, bn_w, bn_b, stats, y, filters)
+        ctx.rb, ctx.prep, ctx.kind = rb, prep, kind
+        ctx.set_materialize_grads(False)
+        return out, y
+
+    @staticmethod
+    def backward(ctx, grad_out, grad_y):
+        x, bn_w, bn_b, stats, y, filters = ctx.saved_tensors
+        dy = dW = None
+        if grad_out is not None:
+            grad_out = _f32c(grad_out)
+            dy, dW = conv_backward_raw(ctx.kind, y, filters, grad_out, ctx.rb, ctx.prep, True, ctx.needs_input_grad[3])
+        if grad_y is not None:
+            dy = grad_y if dy is None else dy + grad_y
+        if dy is None:
+            return (None,) * 12
+        dx, dwb = _bn_backward_raw(x, _f32c(dy), bn_w, bn_b, stats, True)
+        dw = dwb[0] if bn_w is not None and ctx.needs_input_grad[1] else None
+        db = dwb[1] if bn_b is not None and ctx.needs_input_grad[2] else None
+        return dx, dw, db, dW, None, None, None, None, None, None, None, None
+
+
+def bn_batch_stats_args(bn):
+    """-> (running_mean, running_var, num_batches_tracked, momentum) for a training-mode pass of a BatchNorm-like
+    module, or None when it normalises with fixed statistics (eval mode)."""
+    if hasattr(bn, "domain_label") and hasattr(bn, "running_mean_source"):  # DSNorm: per-domain running stats
+        rm = bn.running_mean_target if bn.domain_label else bn.running_mean_source
+        rv = bn.running_var_target if bn.domain_label else bn.running_var_source
+    else:
+        rm, rv = bn.running_mean, bn.running_var
+    if not (bn.training or not bn.track_running_stats or rm is None):
+        return None
+    nbt = None
+    momentum = 0.0 if bn.momentum is None else bn.momentum
+    if bn.training and bn.track_running_stats and bn.num_batches_tracked is not None:
+        nbt = bn.num_batches_tracked
+        if bn.momentum is None:  # cumulative moving average
+            momentum = 1.0 / float(int(nbt.item()) + 1)
+    upd = bn.training and bn.track_running_stats
+    return (rm if upd else None, rv if upd else None, nbt, momentum)
+
+
 def indice_conv(features, filters, indice_pairs, indice_pair_num, num_activate_out, inverse=False, subm=False):
     """spconv v1.2 `ops.indice_conv` on a raw spconv-layout rulebook (any pair order)."""
     _req_cuda(features, filters, indice_pairs)
@@ -630,13 +775,14 @@ class BNReLUFunction(Function):
         y = torch.empty_like(x)
         stats = torch.empty((2, C), dtype=_F32, device=dev)
         ws = _workspace(_bn_ws_bytes(C), dev, "bn")
-        check(lib.b200sp_bn_fwd_train(x.data_ptr(), M, C, weight.data_ptr() if weight is not None else None,
-                                      bias.data_ptr() if bias is not None else None, float(eps), 1 if relu else 0,
-                                      y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
-                                      running_mean.data_ptr() if running_mean is not None else None,
-                                      running_var.data_ptr() if running_var is not None else None, float(momentum),
-                                      nbt.data_ptr() if nbt is not None else None, ws.data_ptr(), ws.numel(),
-                                      _stream()), "bn_fwd_train")
+        with _Timed(kernel="bn_fwd", M=M, C=C):
+            check(lib.b200sp_bn_fwd_train(x.data_ptr(), M, C, weight.data_ptr() if weight is not None else None,
+                                          bias.data_ptr() if bias is not None else None, float(eps), 1 if relu else 0,
+                                          y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+                                          running_mean.data_ptr() if running_mean is not None else None,
+                                          running_var.data_ptr() if running_var is not None else None,
+                                          float(momentum), nbt.data_ptr() if nbt is not None else None, ws.data_ptr(),
+                                          ws.numel(), _stream()), "bn_fwd_train")
         ctx.save_for_backward(x, weight, bias, stats)
         ctx.relu = relu
         return y
@@ -650,10 +796,12 @@ class BNReLUFunction(Function):
         dx = torch.empty_like(x)
         dwb = torch.empty((2, C), dtype=_F32, device=dev)
         ws = _workspace(_bn_ws_bytes(C), dev, "bn")
-        check(lib.b200sp_bn_bwd(x.data_ptr(), dy.data_ptr(), M, C, weight.data_ptr() if weight is not None else None,
-                                bias.data_ptr() if bias is not None else None, stats[0].data_ptr(),
-                                stats[1].data_ptr(), 1 if ctx.relu else 0, dx.data_ptr(), dwb[0].data_ptr(),
-                                dwb[1].data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "bn_bwd")
+        with _Timed(kernel="bn_bwd", M=M, C=C):
+            check(lib.b200sp_bn_bwd(x.data_ptr(), dy.data_ptr(), M, C,
+                                    weight.data_ptr() if weight is not None else None,
+                                    bias.data_ptr() if bias is not None else None, stats[0].data_ptr(),
+                                    stats[1].data_ptr(), 1 if ctx.relu else 0, dx.data_ptr(), dwb[0].data_ptr(),
+                                    dwb[1].data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "bn_bwd")
         dw = dwb[0] if weight is not None and ctx.needs_input_grad[1] else None
         db = dwb[1] if bias is not None and ctx.needs_input_grad[2] else None
         return dx, dw, db, None, None, None, None, None, None

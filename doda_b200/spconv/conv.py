@@ -65,43 +65,50 @@ class SparseConvolution(SparseModule):
         return "{in_channels}, {out_channels}, kernel_size={kernel_size}, stride={stride}, subm={subm}, " \
                "inverse={inverse}, indice_key={indice_key}".format(**self.__dict__)
 
-    def forward(self, input):
-        assert isinstance(input, SparseConvTensor)
-        features = input.features
-        indices = input.indices
-        spatial_shape = input.spatial_shape
-        batch_size = input.batch_size
+    def _resolve(self, input):
+        """-> (kind, rulebook, output indices, output spatial shape) for this conv on `input`"""
         if self.conv1x1:
-            out_features = _ops.DenseConvFunction.apply(features, self.weight, _ops.prepared_weights(self))
-            if self.bias is not None:
-                out_features = out_features + self.bias
-            out_tensor = SparseConvTensor(out_features, indices, spatial_shape, batch_size)
-            out_tensor.indice_dict = input.indice_dict
-            out_tensor.grid = input.grid
-            return out_tensor
+            return "dense", None, input.indices, input.spatial_shape
         rb = input.find_indice_pair(self.indice_key)
         if self.inverse:
             assert rb is not None and self.indice_key is not None, "inverse conv needs the rulebook of its key"
             assert rb.kind == "conv" and rb.K == int(np.prod(self.kernel_size)), "kernel size mismatch with the key"
-            out_features = _ops.SparseInverseConvFunction.apply(features, self.weight, rb, _ops.prepared_weights(self))
-            outids, out_spatial_shape = rb.indices, rb.spatial_shape
-        else:
-            if rb is None:
-                rb = _ops.build_rulebook(indices, batch_size, spatial_shape, self.kernel_size, self.stride,
-                                         self.padding, self.dilation, subm=self.subm)
-                if self.indice_key is not None:
-                    input.indice_dict[self.indice_key] = rb
-            if self.subm:
-                out_features = _ops.SubMConvFunction.apply(features, self.weight, rb, _ops.prepared_weights(self))
-            else:
-                out_features = _ops.SparseConvFunction.apply(features, self.weight, rb, _ops.prepared_weights(self))
-            outids, out_spatial_shape = rb.outids, rb.out_spatial_shape
+            return "inverse", rb, rb.indices, rb.spatial_shape
+        if rb is None:
+            rb = _ops.build_rulebook(input.indices, input.batch_size, input.spatial_shape, self.kernel_size, self.stride,
+                                     self.padding, self.dilation, subm=self.subm)
+            if self.indice_key is not None:
+                input.indice_dict[self.indice_key] = rb
+        return ("subm" if self.subm else "conv"), rb, rb.outids, rb.out_spatial_shape
+
+    def _wrap(self, input, out_features, outids, out_spatial_shape):
         if self.bias is not None:
             out_features = out_features + self.bias
-        out_tensor = SparseConvTensor(out_features, outids, out_spatial_shape, batch_size)
+        out_tensor = SparseConvTensor(out_features, outids, out_spatial_shape, input.batch_size)
         out_tensor.indice_dict = input.indice_dict
         out_tensor.grid = input.grid
         return out_tensor
+
+    def forward(self, input):
+        assert isinstance(input, SparseConvTensor)
+        kind, rb, outids, oshape = self._resolve(input)
+        prep = _ops.prepared_weights(self)
+        if kind == "dense":
+            out_features = _ops.DenseConvFunction.apply(input.features, self.weight, prep)
+        else:
+            out_features = _ops._CONV_FN[kind].apply(input.features, self.weight, rb, prep)
+        return self._wrap(input, out_features, outids, oshape)
+
+    def forward_after_bn_relu(self, input, bn, stats_args):
+        """[BatchNorm (batch statistics), ReLU, this conv] on `input` as one autograd node (SparseSequential calls
+        this when it sees the triplet).  `input.features` is rebound to the BN+ReLU activation, as the unfused
+        sequence would leave it."""
+        kind, rb, outids, oshape = self._resolve(input)
+        rm, rv, nbt, momentum = stats_args
+        out_features, act = _ops.BNReLUConvFunction.apply(input.features, bn.weight, bn.bias, self.weight, rm, rv, nbt,
+                                                          momentum, bn.eps, rb, _ops.prepared_weights(self), kind)
+        input.features = act
+        return self._wrap(input, out_features, outids, oshape)
 
 
 class SparseConv3d(SparseConvolution):

@@ -19,6 +19,9 @@ class SparseModule(nn.Module):
     pass
 
 
+fuse_conv = True  # run [BatchNorm, ReLU, sparse conv] triplets as one autograd node
+
+
 def is_sparse_conv(module):
     from .conv import SparseConvolution
     return isinstance(module, SparseConvolution)
@@ -98,6 +101,13 @@ class SparseSequential(SparseModule):
                     feats = input.features
                     if _is_bn_like(module) and feats.is_cuda and feats.dim() == 2:
                         fuse_relu = i + 1 < n and isinstance(mods[i + 1], nn.ReLU)
+                        if fuse_conv and fuse_relu and i + 2 < n and is_sparse_conv(mods[i + 2]) \
+                                and feats.dtype == torch.float32:
+                            stats_args = _ops.bn_batch_stats_args(module)
+                            if stats_args is not None:  # training-mode statistics: the whole triplet in one node
+                                input = mods[i + 2].forward_after_bn_relu(input, module, stats_args)
+                                i += 3
+                                continue
                         input.features = _ops.batch_norm_relu(feats, module, relu=fuse_relu)
                         i += 2 if fuse_relu else 1
                         continue

@@ -250,6 +250,91 @@ def test_bn_relu_fwd_bwd(cuda_dev, M, C, relu):
     assert rel_err(ye, yer) <= TOL
 
 
+class _DSNormLike(torch.nn.Module):
+    """Stand-in with the attribute surface of DODA's DSNorm (model/dsnorm.py:20-84): one affine pair, separate
+    running statistics per domain selected by `domain_label`.  forward() is the reference computation."""
+
+    def __init__(self, C, eps=1e-4, momentum=0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum, self.affine, self.track_running_stats = C, eps, momentum, True, True
+        self.weight = torch.nn.Parameter(torch.rand(C) + 0.5)
+        self.bias = torch.nn.Parameter(torch.rand(C) - 0.5)
+        for dom in ("source", "target"):
+            self.register_buffer("running_mean_" + dom, torch.zeros(C))
+            self.register_buffer("running_var_" + dom, torch.ones(C))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+        self.domain_label = 0
+
+    def forward(self, x):
+        if self.training:
+            self.num_batches_tracked += 1
+        rm = self.running_mean_target if self.domain_label else self.running_mean_source
+        rv = self.running_var_target if self.domain_label else self.running_var_source
+        return torch.nn.functional.batch_norm(x, rm, rv, self.weight, self.bias, self.training, self.momentum, self.eps)
+
+
+def test_dsnorm_domain_statistics(cuda_dev):
+    """SparseSequential routes DSNorm through the fused BN kernels; each domain updates only its own running stats"""
+    from doda_b200 import spconv
+    torch.manual_seed(0)
+    C = 32
+    mine = _DSNormLike(C).to(cuda_dev)
+    ref = _DSNormLike(C).double()
+    ref.load_state_dict({k: (v.double() if v.is_floating_point() else v) for k, v in mine.state_dict().items()})
+    seq = spconv.SparseSequential(mine, torch.nn.ReLU())
+    coords = torch.zeros(500, 4, dtype=torch.int32, device=cuda_dev)
+    for dom in (0, 1, 1, 0):
+        mine.domain_label = ref.domain_label = dom
+        x = torch.randn(500, C) * 3 + dom
+        t = spconv.SparseConvTensor(x.to(cuda_dev), coords, [8, 8, 8], 1)
+        y = seq(t).features
+        yr = torch.relu(ref(x.double()))
+        assert rel_err(y, yr) <= TOL
+    for k, v in mine.state_dict().items():
+        assert rel_err(v.float(), ref.state_dict()[k].float()) <= TOL, k
+    mine.eval(); ref.eval()
+    mine.domain_label = ref.domain_label = 1
+    x = torch.randn(300, C)
+    with torch.no_grad():
+        y = seq(spconv.SparseConvTensor(x.to(cuda_dev), coords[:300], [8, 8, 8], 1)).features
+    assert rel_err(y, torch.relu(ref(x.double()))) <= TOL
+
+
+def test_fused_bn_relu_conv_matches_unfused(cuda_dev):
+    """the one-node [BN, ReLU, conv] path of SparseSequential gives the same activations, gradients, running
+    statistics and `input.features` side effect as the three separate nodes"""
+    from doda_b200 import spconv
+    from doda_b200.spconv import modules as spm
+    torch.manual_seed(2)
+    shape = (24, 22, 20)
+    coords = torch.from_numpy(random_coords(2, 1500, 2, shape)).to(cuda_dev)
+    feats = torch.randn(coords.shape[0], 16)
+    res = []
+    for fuse in (True, False):
+        torch.manual_seed(9)
+        seq = spconv.SparseSequential(torch.nn.BatchNorm1d(16, eps=1e-4, momentum=0.1), torch.nn.ReLU(),
+                                      spconv.SubMConv3d(16, 32, 3, padding=1, bias=False, indice_key="s"),
+                                      torch.nn.BatchNorm1d(32, eps=1e-4, momentum=0.1), torch.nn.ReLU(),
+                                      spconv.SparseConv3d(32, 48, 2, stride=2, bias=False, indice_key="d")).to(cuda_dev)
+        spm.fuse_conv = fuse
+        try:
+            f = feats.to(cuda_dev).requires_grad_(True)
+            x = spconv.SparseConvTensor(f, coords, list(shape), 2)
+            y = seq(x)
+            side = x.features  # rebound to the first BN+ReLU activation
+            (y.features.pow(2).sum() + side.sum()).backward()
+        finally:
+            spm.fuse_conv = True
+        res.append((y.features.detach(), side.detach(), f.grad, [p.grad for p in seq.parameters()],
+                    [b.clone() for b in seq.buffers()]))
+    a, b = res
+    assert rel_err(a[0], b[0]) <= 1e-5 and rel_err(a[1], b[1]) <= 1e-6 and rel_err(a[2], b[2]) <= 1e-4
+    for ga, gb in zip(a[3], b[3]):
+        assert rel_err(ga, gb) <= 1e-4
+    for ba, bb in zip(a[4], b[4]):
+        assert rel_err(ba.float(), bb.float()) <= 1e-6
+
+
 def test_voxelize_and_devoxelize(cuda_dev):
     from doda_b200 import pointgroup_ops, ops
     from oracle.unet_ref import voxelize_mean_ref
