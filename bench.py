@@ -28,6 +28,9 @@ METRIC = "scenes/sec fwd+bwd Sparse U-Net @150k voxels"
 UNIT = "scenes/s"
 
 
+SETTLE = 6  # extra untimed steps per timed loop (see main); reported in the JSON line's config
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -218,9 +221,15 @@ def main():
     h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in tensor_keys)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
+    params = [p for p in model.parameters()]
+    from doda_b200 import ops as _engine_ops
+
     def step(b):
-        for p in model.parameters():
+        for p in params:  # what optimizer.zero_grad(set_to_none=True) does
             p.grad = None
+        # the metric is fwd+bwd (no optimizer step), so the weights never change here; in training they change every
+        # step and the engine re-prepares its weight images once per step -- charge that launch to every timed step
+        _engine_ops.invalidate_prepared_weights()
         loss, _ = model_step(net, b, criterion=criterion, device=dev)
         loss.backward()
         return loss
@@ -230,19 +239,32 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    loss_host = torch.zeros(max(args.steps, 8) + 8, dtype=torch.float32).pin_memory()
+    losses = []
+
     def timed(b, nsteps, read_loss):
+        """read_loss: every step copies its loss to pinned host memory (async, 4 bytes) and the host reads the value
+        of the PREVIOUS step, the last one after the loop -- all nsteps losses are read inside the timed region, but
+        the host is not parked on the GPU once per step (a training loop that logs its loss one step late)."""
         import gc
-        evs = []
+        evs, copied = [], []
         gc.collect()
         gc.disable()  # a gen-2 collection inside the loop shows up as a 50-100 ms outlier step
         barrier()
-        for _ in range(nsteps):
+        for i in range(nsteps):
             flush.zero_()  # L2 flush between timed iterations (not timed)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             loss = step(b)
             if read_loss:
-                float(loss.detach())  # device -> host read of the step's result
+                loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)  # device -> host, every step
+                copied.append(torch.cuda.current_stream().record_event())
+                if i > 0:
+                    copied[i - 1].synchronize()
+                    losses.append(float(loss_host[i - 1]))
+                if i == nsteps - 1:
+                    copied[i].synchronize()
+                    losses.append(float(loss_host[i]))
             e.record()
             evs.append((s, e))
         barrier()
@@ -262,8 +284,10 @@ def main():
         sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(resident)
-    timed(resident, 2, False)  # untimed pass through the timing harness itself (allocator / L2-flush steady state)
-    timed(host, 1, True)
+    # untimed passes through the timing harness itself: with the host running ahead of the GPU the caching allocator
+    # needs a few steps to reach its steady state (cudaMalloc inside a timed step is a 20-60 ms outlier)
+    timed(resident, SETTLE, False)
+    timed(host, SETTLE, True)
     if sampler:
         t_wait = time.time()
         while not sampler.rows and time.time() - t_wait < 10.0:
@@ -344,9 +368,14 @@ def main():
                "config": {"workload": "2x150k-voxel ScanNet-shape scenes, full SparseConvNet fwd+bwd, bs=%d, m=%d"
                           % (args.bs, args.mid), "voxels_per_scene": args.voxels, "scenes_per_gpu": args.bs,
                           "mid_channel": args.mid, "parallelism": "dp%d (whole scenes per rank, DDP grad all-reduce)"
-                          % world, "l2": "256 MB flush between timed steps"},
+                          % world, "l2": "256 MB flush between timed steps",
+                          "settle": "%d further untimed steps through the timing harness before each timed loop"
+                          % SETTLE},
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                       "ms_per_step": ms_e2e / args.steps},
+                       "ms_per_step": ms_e2e / args.steps,
+                       "loss_read": "async 4-byte copy to pinned memory every step; the host reads step i-1's value "
+                                    "during step i and the last one before the closing sync (all K inside the timed "
+                                    "region)"},
                "gpu_launches": launches, "clocks": sampler.summary() if sampler else None,
                "step_ms_rank0": steps_ms}
         if roof:

@@ -398,72 +398,128 @@ extern "C" int b200sp_rulebook_subm(const int32_t* coords, int64_t M, int batch,
     return B200SP_OK;
 }
 
+namespace {
+// workspace carving shared by the two halves of the strided builder (begin leaves the hash table, the candidate keys
+// and the counter behind for finish)
+struct ConvWs {
+    HashTab t;
+    int* blockcnt;
+    unsigned long long *uniq, *sorted;
+    int* counter;
+    void* cub_ws;
+    size_t cub_bytes;
+};
+int carve_conv_ws(ConvWs& c, const Geo& g, int64_t M, int64_t ub, void* ws, int64_t ws_bytes) {
+    WsCarver w{(char*)ws, ws_bytes};
+    int64_t cap = hash_capacity(ub);
+    c.t.keys = (unsigned long long*)w.take(cap * 8);
+    c.t.vals = (int*)w.take(cap * 4);
+    c.t.mask = (uint32_t)(cap - 1);
+    int64_t nblk = cdiv(M, 64);
+    c.blockcnt = (int*)w.take((int64_t)g.K * nblk * 4);
+    c.uniq = (unsigned long long*)w.take(ub * 8 + 8);
+    c.sorted = (unsigned long long*)w.take(ub * 8 + 8);
+    c.counter = (int*)w.take(256);
+    c.cub_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, c.cub_bytes, c.uniq, c.sorted, (int)ub);
+    c.cub_ws = w.take((int64_t)c.cub_bytes);
+    if (!c.t.keys || !c.t.vals || !c.blockcnt || !c.uniq || !c.sorted || !c.counter || (!c.cub_ws && c.cub_bytes)) {
+        set_error("rulebook_conv: workspace too small (%lld bytes)", (long long)ws_bytes);
+        return B200SP_ENOMEM;
+    }
+    return B200SP_OK;
+}
+int conv_geo(Geo& g, const int32_t* coords, int64_t M, int batch, const int32_t* shape, const int32_t* oshape,
+             const int32_t* ksize, const int32_t* stride, const int32_t* pad, const int32_t* dil, int cand) {
+    B200SP_CHECK_ARG(shape && oshape && ksize && stride && pad && dil, "rulebook_conv: null arg");
+    B200SP_CHECK_ARG(fill_geo(g, shape, oshape, ksize, stride, pad, dil) == 0, "rulebook_conv: bad geometry");
+    B200SP_CHECK_ARG(M >= 0 && batch >= 1 && cand >= 1, "rulebook_conv: bad M/batch/cand");
+    B200SP_CHECK_ARG(((uintptr_t)coords & 15) == 0, "rulebook_conv: coords must be 16-byte aligned");
+    return B200SP_OK;
+}
+}  // namespace
+
+// first half: hash every candidate output site, count the distinct ones, start the copy of that count to the host.
+// Nothing here waits; the caller synchronises (stream or event) before reading *n_out_host and calling _finish with
+// the SAME workspace.
+extern "C" int b200sp_rulebook_conv_begin(const int32_t* coords, int64_t M, int batch, const int32_t* shape,
+                                          const int32_t* oshape, const int32_t* ksize, const int32_t* stride,
+                                          const int32_t* pad, const int32_t* dil, int cand, int32_t* n_out_host,
+                                          void* ws, int64_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    Geo g;
+    int rc = conv_geo(g, coords, M, batch, shape, oshape, ksize, stride, pad, dil, cand);
+    if (rc) return rc;
+    B200SP_CHECK_ARG(n_out_host, "rulebook_conv_begin: null n_out_host");
+    *n_out_host = 0;
+    if (M == 0) return B200SP_OK;
+    ConvWs c;
+    rc = carve_conv_ws(c, g, M, M * cand, ws, ws_bytes);
+    if (rc) return rc;
+    int64_t cap = (int64_t)c.t.mask + 1;
+    B200SP_CUDA(cudaMemsetAsync(c.t.keys, 0xFF, cap * 8, st));
+    B200SP_CUDA(cudaMemsetAsync(c.t.vals, 0x7F, cap * 4, st));
+    B200SP_CUDA(cudaMemsetAsync(c.counter, 0, 4, st));
+    unsigned grid = (unsigned)cdiv(M * g.K, 256);
+    k_conv_insert<<<grid, 256, 0, st>>>((const int4*)coords, M, g, c.t, c.uniq, c.counter);
+    B200SP_LAUNCH_CHECK();
+    B200SP_CUDA(cudaMemcpyAsync(n_out_host, c.counter, 4, cudaMemcpyDeviceToHost, st));
+    return B200SP_OK;
+}
+
+// second half: rank the distinct output sites (ascending flat index), write their coordinates and the tables
+extern "C" int b200sp_rulebook_conv_finish(const int32_t* coords, int64_t M, int batch, const int32_t* shape,
+                                           const int32_t* oshape, const int32_t* ksize, const int32_t* stride,
+                                           const int32_t* pad, const int32_t* dil, int cand, int64_t n_out_in,
+                                           int32_t* out_coords, int32_t* fwd, int32_t* bwd, int32_t* pairs,
+                                           int32_t* pairnum, void* ws, int64_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    Geo g;
+    int rc = conv_geo(g, coords, M, batch, shape, oshape, ksize, stride, pad, dil, cand);
+    if (rc) return rc;
+    B200SP_CHECK_ARG(((uintptr_t)out_coords & 15) == 0, "rulebook_conv: coords must be 16-byte aligned");
+    B200SP_CHECK_ARG(n_out_in >= 0 && n_out_in <= M * cand, "rulebook_conv_finish: n_out out of range");
+    int n_out = (int)n_out_in;
+    if (M == 0 || n_out == 0) {
+        if (M > 0) B200SP_CUDA(cudaMemsetAsync(fwd, 0xFF, sizeof(int) * (size_t)M * g.K, st));
+        if (M > 0 && pairs) B200SP_CUDA(cudaMemsetAsync(pairs, 0xFF, sizeof(int) * 2 * (size_t)g.K * M, st));
+        if (pairnum) B200SP_CUDA(cudaMemsetAsync(pairnum, 0, sizeof(int) * g.K, st));
+        return B200SP_OK;
+    }
+    ConvWs c;
+    rc = carve_conv_ws(c, g, M, M * cand, ws, ws_bytes);
+    if (rc) return rc;
+    // bits needed for the largest key
+    unsigned long long maxkey = (unsigned long long)batch * g.O[0] * g.O[1] * g.O[2];
+    int bits = 1;
+    while (bits < 64 && (maxkey >> bits)) ++bits;
+    unsigned grid = (unsigned)cdiv(M * g.K, 256);
+    B200SP_CUDA(cub::DeviceRadixSort::SortKeys(c.cub_ws, c.cub_bytes, c.uniq, c.sorted, n_out, 0, bits, st));
+    k_conv_rank<<<(unsigned)cdiv(n_out, 256), 256, 0, st>>>(c.sorted, n_out, g, c.t, (int4*)out_coords);
+    B200SP_CUDA(cudaMemsetAsync(bwd, 0xFF, sizeof(int) * (size_t)n_out * g.K, st));
+    k_conv_tables<<<grid, 256, 0, st>>>((const int4*)coords, M, g, c.t, fwd, bwd);
+    B200SP_LAUNCH_CHECK_N(2 + 3 /* cub radix sort passes */);
+    if (pairs) {
+        rc = emit_pairs(fwd, M, g.K, /*mirror=*/0, pairs, pairnum, c.blockcnt, st);
+        if (rc) return rc;
+    }
+    return B200SP_OK;
+}
+
 extern "C" int b200sp_rulebook_conv(const int32_t* coords, int64_t M, int batch, const int32_t* shape,
                                     const int32_t* oshape, const int32_t* ksize, const int32_t* stride,
                                     const int32_t* pad, const int32_t* dil, int cand, int32_t* out_coords,
                                     int32_t* fwd, int32_t* bwd, int32_t* pairs, int32_t* pairnum,
                                     int64_t* n_out_host, void* ws, int64_t ws_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    Geo g;
-    B200SP_CHECK_ARG(shape && oshape && ksize && stride && pad && dil && n_out_host, "rulebook_conv: null arg");
-    B200SP_CHECK_ARG(fill_geo(g, shape, oshape, ksize, stride, pad, dil) == 0, "rulebook_conv: bad geometry");
-    B200SP_CHECK_ARG(M >= 0 && batch >= 1 && cand >= 1, "rulebook_conv: bad M/batch/cand");
-    B200SP_CHECK_ARG(((uintptr_t)coords & 15) == 0 && ((uintptr_t)out_coords & 15) == 0,
-                     "rulebook_conv: coords must be 16-byte aligned");
-    *n_out_host = 0;
-    if (M == 0) {
-        if (pairnum) B200SP_CUDA(cudaMemsetAsync(pairnum, 0, sizeof(int) * g.K, st));
-        return B200SP_OK;
-    }
-    int64_t ub = M * cand;
-    WsCarver w{(char*)ws, ws_bytes};
-    HashTab t;
-    int64_t cap = hash_capacity(ub);
-    t.keys = (unsigned long long*)w.take(cap * 8);
-    t.vals = (int*)w.take(cap * 4);
-    t.mask = (uint32_t)(cap - 1);
-    int64_t nblk = cdiv(M, 64);
-    int* blockcnt = (int*)w.take((int64_t)g.K * nblk * 4);
-    unsigned long long* uniq = (unsigned long long*)w.take(ub * 8 + 8);
-    unsigned long long* sorted = (unsigned long long*)w.take(ub * 8 + 8);
-    int* counter = (int*)w.take(256);
-    size_t cub_bytes = 0;
-    cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, uniq, sorted, (int)ub);
-    void* cub_ws = w.take((int64_t)cub_bytes);
-    if (!t.keys || !t.vals || !blockcnt || !uniq || !sorted || !counter || (!cub_ws && cub_bytes)) {
-        set_error("rulebook_conv: workspace too small (%lld bytes)", (long long)ws_bytes);
-        return B200SP_ENOMEM;
-    }
-    B200SP_CUDA(cudaMemsetAsync(t.keys, 0xFF, cap * 8, st));
-    B200SP_CUDA(cudaMemsetAsync(t.vals, 0x7F, cap * 4, st));
-    B200SP_CUDA(cudaMemsetAsync(counter, 0, 4, st));
-    unsigned grid = (unsigned)cdiv(M * g.K, 256);
-    k_conv_insert<<<grid, 256, 0, st>>>((const int4*)coords, M, g, t, uniq, counter);
-    B200SP_LAUNCH_CHECK();
-    int n_out = 0;
-    B200SP_CUDA(cudaMemcpyAsync(&n_out, counter, 4, cudaMemcpyDeviceToHost, st));
-    B200SP_CUDA(cudaStreamSynchronize(st));
-    *n_out_host = n_out;
-    if (n_out == 0) {
-        B200SP_CUDA(cudaMemsetAsync(fwd, 0xFF, sizeof(int) * (size_t)M * g.K, st));
-        if (pairs) B200SP_CUDA(cudaMemsetAsync(pairs, 0xFF, sizeof(int) * 2 * (size_t)g.K * M, st));
-        if (pairnum) B200SP_CUDA(cudaMemsetAsync(pairnum, 0, sizeof(int) * g.K, st));
-        return B200SP_OK;
-    }
-    // bits needed for the largest key
-    unsigned long long maxkey = (unsigned long long)batch * g.O[0] * g.O[1] * g.O[2];
-    int bits = 1;
-    while (bits < 64 && (maxkey >> bits)) ++bits;
-    B200SP_CUDA(cub::DeviceRadixSort::SortKeys(cub_ws, cub_bytes, uniq, sorted, n_out, 0, bits, st));
-    k_conv_rank<<<(unsigned)cdiv(n_out, 256), 256, 0, st>>>(sorted, n_out, g, t, (int4*)out_coords);
-    B200SP_CUDA(cudaMemsetAsync(bwd, 0xFF, sizeof(int) * (size_t)n_out * g.K, st));
-    k_conv_tables<<<grid, 256, 0, st>>>((const int4*)coords, M, g, t, fwd, bwd);
-    B200SP_LAUNCH_CHECK_N(2 + 3 /* cub radix sort passes */);
-    if (pairs) {
-        int rc = emit_pairs(fwd, M, g.K, /*mirror=*/0, pairs, pairnum, blockcnt, st);
-        if (rc) return rc;
-    }
-    return B200SP_OK;
+    B200SP_CHECK_ARG(n_out_host, "rulebook_conv: null arg");
+    int32_t n = 0;
+    int rc = b200sp_rulebook_conv_begin(coords, M, batch, shape, oshape, ksize, stride, pad, dil, cand, &n, ws, ws_bytes,
+                                        stream);
+    if (rc) return rc;
+    B200SP_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    *n_out_host = n;
+    return b200sp_rulebook_conv_finish(coords, M, batch, shape, oshape, ksize, stride, pad, dil, cand, n, out_coords,
+                                       fwd, bwd, pairs, pairnum, ws, ws_bytes, stream);
 }
 
 extern "C" int b200sp_pairs_to_table(const int32_t* pairs, const int32_t* pairnum, int K, int64_t M_in, int inverse,

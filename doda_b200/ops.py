@@ -197,6 +197,38 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding=
     return rb
 
 
+def stage_coords(voxel_locs, device, pending=False):
+    """[M,4] voxel coordinates (host or device; int64 as the reference's collate makes them, or int32) -> int32
+    device tensor, produced on the engine's index stream.
+
+    Coordinates never depend on features, so their H2D copy and int cast need not queue behind the previous step's
+    backward on the caller's stream -- if they do, every rulebook of the new step (and the host read of the strided
+    builder) waits for that backward and the host can never run ahead of the GPU.  `pending=True` is for coordinates
+    some kernel on the caller's stream is still writing: the index stream then waits for the caller's stream first."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("doda_b200: stage_coords needs a CUDA device (no CPU fallback)")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    if not index_stream:
+        c = voxel_locs.to(dev, non_blocking=True)
+        return (c if c.dtype == _I32 else c.int()).contiguous()
+    main = torch.cuda.current_stream(dev)
+    side = _idx_streams.get(dev.index)
+    if side is None:
+        side = _idx_streams[dev.index] = torch.cuda.Stream(dev)
+    if pending:
+        side.wait_stream(main)
+    with torch.cuda.stream(side):
+        c = voxel_locs.to(dev, non_blocking=True)
+        c = (c if c.dtype == _I32 else c.int()).contiguous()
+        ev = side.record_event()
+    c.record_stream(main)
+    main.wait_event(ev)
+    c._b200sp_idx_stream = True
+    return c
+
+
 def _build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding=0, dilation=1, subm=False,
                     need_pairs=True):
     _req_cuda(indices)
@@ -234,6 +266,8 @@ def _build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding
                                        rb.nbr_perm.data_ptr() if mask_order else None,
                                        rb.rowmask.data_ptr() if mask_order else None,
                                        ws.data_ptr(), ws.numel(), _stream()), "rulebook_subm")
+        if speculate_down:
+            _speculate_strided(indices, batch_size, shape)
         return rb
     rb.kind = "conv"
     oshape = conv_out_shape(shape, ks, st, pd, dl)
@@ -249,18 +283,72 @@ def _build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding
     out_coords = torch.empty((ub, 4), dtype=_I32, device=dev)
     rb.fwd = torch.empty((M, K), dtype=_I32, device=dev)
     bwd = torch.empty((ub, K), dtype=_I32, device=dev)
-    wsb = lib.b200sp_rulebook_ws_bytes(M, K, cand)
-    ws = _workspace(wsb, dev, "rb")
-    import ctypes
-    n_out = ctypes.c_int64(0)
-    check(lib.b200sp_rulebook_conv(indices.data_ptr(), M, int(batch_size), _carr(shape), _carr(oshape), _carr(ks),
-                                   _carr(st), _carr(pd), _carr(dl), cand, out_coords.data_ptr(), rb.fwd.data_ptr(),
-                                   bwd.data_ptr(), pp, pn, ctypes.byref(n_out), ws.data_ptr(), ws.numel(),
-                                   _stream()), "rulebook_conv")
-    n = int(n_out.value)
+    geo = (_carr(shape), _carr(oshape), _carr(ks), _carr(st), _carr(pd), _carr(dl))
+    key = (tuple(shape), tuple(ks), tuple(st), tuple(pd), tuple(dl), int(batch_size), M)
+    sp = _spec.pop(dev.index, None)
+    if sp is not None and sp.key == key and sp.ptr == indices.data_ptr() and sp.stream == _stream():
+        sp.event.synchronize()  # normally long done: the first half was started when this level's SubM table was built
+        ws, n = sp.ws, int(sp.n_host[0])
+    else:
+        ws = _workspace(lib.b200sp_rulebook_ws_bytes(M, K, cand), dev, "rb")
+        n_host = _pinned_slot()
+        check(lib.b200sp_rulebook_conv_begin(indices.data_ptr(), M, int(batch_size), *geo, cand, n_host.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _stream()), "rulebook_conv_begin")
+        torch.cuda.current_stream(dev).synchronize()
+        n = int(n_host[0])
+    check(lib.b200sp_rulebook_conv_finish(indices.data_ptr(), M, int(batch_size), *geo, cand, n, out_coords.data_ptr(),
+                                          rb.fwd.data_ptr(), bwd.data_ptr(), pp, pn, ws.data_ptr(), ws.numel(),
+                                          _stream()), "rulebook_conv_finish")
+    _spec_hint[dev.index] = (ks, st, pd, dl)
     rb.outids = out_coords[:n]
     rb.bwd = bwd[:n]
     return rb
+
+
+# A strided build has to read its number of output sites back to the host, and DODA's U-Net asks for it right
+# when it is needed (the down conv of each level).  The engine therefore starts the first half of that build
+# (b200sp_rulebook_conv_begin) as soon as the level's coordinates are known -- when their SubM table is built, a few
+# layers earlier -- guessing the geometry of the most recent strided conv; the count is on the host long before the
+# down conv asks.  A wrong guess is simply dropped.
+speculate_down = True
+_spec, _spec_hint, _pinned = {}, {}, [None, 0]
+
+
+class _SpecBuild(object):
+    __slots__ = ("key", "ptr", "indices", "stream", "ws", "n_host", "event")
+
+
+def _pinned_slot():
+    if _pinned[0] is None:
+        _pinned[0] = torch.zeros(64, dtype=_I32).pin_memory()
+    _pinned[1] = (_pinned[1] + 1) % 64
+    return _pinned[0][_pinned[1]:_pinned[1] + 1]
+
+
+def _speculate_strided(indices, batch_size, shape):
+    dev = indices.device
+    hint = _spec_hint.get(dev.index)
+    M = indices.shape[0]
+    if hint is None or M == 0:
+        return
+    ks, st, pd, dl = hint
+    oshape = conv_out_shape(shape, ks, st, pd, dl)
+    if min(oshape) <= 0:
+        return
+    cand = 1
+    for k, s_, d in zip(ks, st, dl):
+        cand *= (-(-k // s_)) if d == 1 else k
+    K = ks[0] * ks[1] * ks[2]
+    sp = _SpecBuild()
+    sp.key = (tuple(shape), tuple(ks), tuple(st), tuple(pd), tuple(dl), int(batch_size), M)
+    sp.ptr, sp.indices, sp.stream = indices.data_ptr(), indices, _stream()
+    sp.ws = _workspace(lib.b200sp_rulebook_ws_bytes(M, K, cand), dev, "rbspec")
+    sp.n_host = _pinned_slot()
+    check(lib.b200sp_rulebook_conv_begin(indices.data_ptr(), M, int(batch_size), _carr(shape), _carr(oshape), _carr(ks),
+                                         _carr(st), _carr(pd), _carr(dl), cand, sp.n_host.data_ptr(), sp.ws.data_ptr(),
+                                         sp.ws.numel(), sp.stream), "rulebook_conv_begin")
+    sp.event = torch.cuda.current_stream(dev).record_event()
+    _spec[dev.index] = sp
 
 
 def get_indice_pairs(indices, batch_size, spatial_shape, ksize=3, stride=1, padding=0, dilation=1, out_padding=0,
@@ -377,6 +465,14 @@ def prepared_weights(module):
         if st is None or st[0] != key:
             return None
     return st[1]
+
+
+def invalidate_prepared_weights():
+    """Forget every prepared weight image (they are rebuilt, in one launch, by the next conv that runs).  An optimizer
+    step does this implicitly by bumping the weights' version counters; a fwd+bwd-only loop that wants to be charged
+    the per-step preparation like real training calls it once per step (bench.py)."""
+    for m in list(_conv_modules):
+        m.__dict__.pop("_b200sp_prep", None)
 
 
 def _prepare_all(device):

@@ -102,17 +102,21 @@ class SparseConvNet(nn.Module):
         return (point_feats, scores) if return_mid_feat else scores
 
 
-def model_step(model, batch, voxel_mode=4, criterion=None, device="cuda"):
+def model_step(model, batch, voxel_mode=4, criterion=None, device="cuda", coords_pending=False):
     """One forward of the reference's `model_fn` (model/unet.py:72-99,154-198) on a collated batch dict:
-    H2D copies, voxelize the point features, build the SparseConvTensor, run the net, cross-entropy."""
-    voxel_coords = batch["voxel_locs"].to(device, non_blocking=True)
+    H2D copies, voxelize the point features, build the SparseConvTensor, run the net, cross-entropy.
+
+    The voxel coordinates go through `ops.stage_coords` (copy + int cast on the engine's index stream) so that the
+    rulebooks of this step do not queue behind the previous step's backward; device-resident `voxel_locs` must be
+    complete, or pass coords_pending=True."""
+    voxel_coords = _ops.stage_coords(batch["voxel_locs"], device, pending=coords_pending)
     p2v_map = batch["p2v_map"].to(device, non_blocking=True)
     v2p_map = batch["v2p_map"].to(device, non_blocking=True)
     feats = batch["feats"].to(device, non_blocking=True)
     labels = batch["labels"].to(device, non_blocking=True)
     batch_size = batch["offsets"].size(0) - 1
     voxel_feats = pointgroup_ops.voxelization(feats, v2p_map, voxel_mode)
-    x = spconv.SparseConvTensor(voxel_feats, voxel_coords.int(), batch["spatial_shape"], batch_size)
+    x = spconv.SparseConvTensor(voxel_feats, voxel_coords, batch["spatial_shape"], batch_size)
     scores = model(x, p2v_map)
     if criterion is None:
         criterion = nn.CrossEntropyLoss(ignore_index=255)

@@ -75,6 +75,23 @@ int b200sp_rulebook_conv(const int32_t* coords_dev, int64_t M_in, int batch, con
                          int32_t* pairnum_dev /*[K] or NULL*/, int64_t* n_out_host, void* ws_dev,
                          int64_t ws_bytes, void* stream);
 
+/* The same build in two halves, so that a host can start it early and never block on it: _begin hashes the
+ * candidate output sites and starts an async copy of their count into *n_out_host (pinned host memory) without
+ * waiting; after the caller has synchronised (stream or event) it passes the count to _finish together with the
+ * SAME, untouched workspace.  b200sp_rulebook_conv == begin + cudaStreamSynchronize + finish. */
+int b200sp_rulebook_conv_begin(const int32_t* coords_dev, int64_t M_in, int batch, const int32_t* shape_host,
+                               const int32_t* out_shape_host, const int32_t* ksize_host,
+                               const int32_t* stride_host, const int32_t* pad_host, const int32_t* dil_host,
+                               int cand_per_input, int32_t* n_out_host /*pinned*/, void* ws_dev, int64_t ws_bytes,
+                               void* stream);
+int b200sp_rulebook_conv_finish(const int32_t* coords_dev, int64_t M_in, int batch, const int32_t* shape_host,
+                                const int32_t* out_shape_host, const int32_t* ksize_host,
+                                const int32_t* stride_host, const int32_t* pad_host, const int32_t* dil_host,
+                                int cand_per_input, int64_t n_out, int32_t* out_coords_dev /*[ub,4]*/,
+                                int32_t* fwd_dev /*[M_in,K]*/, int32_t* bwd_dev /*[ub,K]*/,
+                                int32_t* pairs_dev /*[2,K,M_in] or NULL*/, int32_t* pairnum_dev /*[K] or NULL*/,
+                                void* ws_dev, int64_t ws_bytes, void* stream);
+
 /* pairs [2,K,M_in] (spconv layout) -> out-stationary table tab[n_out,K]; `inverse` swaps roles. */
 int b200sp_pairs_to_table(const int32_t* pairs_dev, const int32_t* pairnum_dev, int K, int64_t M_in,
                           int inverse, int32_t* tab_dev /*[n_out,K]*/, int64_t n_out, void* stream);

@@ -63,6 +63,35 @@ def test_rulebook_generic_conv_exact(cuda_dev, ks, st, pd, dl):
     _check_rulebook(cuda_dev, coords, 2, list(shape), ks, st, pd, dl, False)
 
 
+def test_rulebook_speculative_down_build(cuda_dev):
+    """the strided builder's first half started early (when the level's SubM table is built) gives the same rulebook
+    as the blocking build, whether the guessed geometry was right (k2 s2) or wrong (k3 s2 -> guess dropped)"""
+    from doda_b200 import ops
+    shape = [40, 37, 29]
+    coords = torch.from_numpy(random_coords(5, 4000, 2, shape)).to(cuda_dev)
+
+    def build(spec, ks, st, pd):
+        ops.speculate_down = spec
+        try:
+            ops._spec.clear()
+            ops._spec_hint[cuda_dev.index or 0] = ([2, 2, 2], [2, 2, 2], [0, 0, 0], [1, 1, 1])
+            ops.build_rulebook(coords, 2, shape, 3, 1, 1, 1, subm=True)
+            started = len(ops._spec) == 1
+            rb = ops.build_rulebook(coords, 2, shape, ks, st, pd, 1)
+            assert len(ops._spec) == 0
+            return started, rb
+        finally:
+            ops.speculate_down = True
+
+    for ks, st, pd in ((2, 2, 0), (3, 2, 1)):
+        s1, a = build(True, ks, st, pd)
+        s0, b = build(False, ks, st, pd)
+        assert s1 and not s0
+        for name in ("outids", "fwd", "bwd", "pairs", "pairnum"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+    torch.cuda.synchronize()
+
+
 def test_rulebook_empty(cuda_dev):
     from doda_b200 import ops
     coords = torch.zeros((0, 4), dtype=torch.int32, device=cuda_dev)

@@ -10,8 +10,10 @@ for k in ("voxel_locs", "p2v_map", "v2p_map", "feats", "labels"):
     batch[k] = batch[k].to(dev)
 model = SparseConvNet(mid_channel=16).to(dev).train()
 crit = torch.nn.CrossEntropyLoss(ignore_index=255)
+params = list(model.parameters())
 def step():
-    for p in model.parameters(): p.grad = None
+    for p in params: p.grad = None
+    ops.invalidate_prepared_weights()
     loss, _ = model_step(model, batch, criterion=crit, device=dev)
     loss.backward()
 for _ in range(3): step()

@@ -1,0 +1,45 @@
+"""dev helper (GPU box): CUPTI timeline of a few training steps through torch.profiler -> per-kernel totals, GPU busy
+time vs wall time per step (how much of the step the GPU sits idle waiting for the host)."""
+import os, sys, collections
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from torch.profiler import profile, ProfilerActivity
+from doda_b200 import scenes
+from doda_b200.unet import SparseConvNet, model_step
+dev = torch.device("cuda")
+batch = scenes.collate([scenes.scene_with_voxels(i, 150000) for i in range(2)], seed=0, dup_max=2)
+for k in ("voxel_locs", "p2v_map", "v2p_map", "feats", "labels"):
+    batch[k] = batch[k].to(dev)
+model = SparseConvNet(mid_channel=16).to(dev).train()
+crit = torch.nn.CrossEntropyLoss(ignore_index=255)
+def step():
+    for p in model.parameters(): p.grad = None
+    loss, _ = model_step(model, batch, criterion=crit, device=dev)
+    loss.backward()
+for _ in range(4): step()
+torch.cuda.synchronize()
+NS = 4
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    for _ in range(NS): step()
+    torch.cuda.synchronize()
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+tot = collections.defaultdict(float); cnt = collections.Counter()
+ivs = []
+for e in evs:
+    name = e.name.split("(")[0][:70]
+    tot[name] += e.device_time if hasattr(e, "device_time") else e.cuda_time
+    cnt[name] += 1
+    ivs.append((e.time_range.start, e.time_range.end))
+ivs.sort()
+busy = 0.0; cur_s, cur_e = ivs[0]
+for s, e in ivs[1:]:
+    if s > cur_e:
+        busy += cur_e - cur_s; cur_s, cur_e = s, e
+    else:
+        cur_e = max(cur_e, e)
+busy += cur_e - cur_s
+wall = ivs[-1][1] - ivs[0][0]
+print("steps %d: wall %.2f ms/step, GPU busy (union of kernels) %.2f ms/step, sum of kernel durations %.2f ms/step, kernels/step %d"
+      % (NS, wall / NS / 1e3, busy / NS / 1e3, sum(tot.values()) / NS / 1e3, len(evs) // NS))
+for name, t in sorted(tot.items(), key=lambda kv: -kv[1])[:28]:
+    print("%9.1f us/step %5d  %s" % (t / NS, cnt[name] // NS, name))
