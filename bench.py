@@ -210,7 +210,7 @@ def main():
     net = model
     if world > 1:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
-    criterion = torch.nn.CrossEntropyLoss(ignore_index=255)
+    criterion = None  # model_step's default: the engine's one-pass cross-entropy (ignore_index=255, mean)
     tensor_keys = ["voxel_locs", "p2v_map", "v2p_map", "feats", "labels"]
     host = dict(batch)
     for k in tensor_keys:

@@ -407,6 +407,10 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
                 const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out, int Cout,
                 int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st);
 int64_t conv_tc_ws_bytes(int K, int Cin, int Cout);
+bool conv_direct_covers(int K, int Cin, int Cout);
+void conv_direct_set(int on);
+int conv_direct_run(const float* in, int Cin, const float* W, int wflags, const int* tab, const int* orow,
+                    const int* rowmask, long long n_rows, int K, float* out, int Cout, int accumulate, cudaStream_t st);
 int conv_tc_prep_batch(const int64_t* desc_host, int n, void* desc_dev, int64_t desc_dev_bytes, cudaStream_t st);
 int wgrad_tc_run(const float* a, int Ca, const float* b, int Cb, const int* pa, const int* pb, const int* pairnum,
                  int64_t n_upper, int K, int64_t pstride, float* dW, cudaStream_t st);
@@ -451,7 +455,17 @@ extern "C" int b200sp_set_conv_impl(int impl) {
     return B200SP_OK;
 }
 
-extern "C" int64_t b200sp_conv_prepared_bytes(int K, int Cin, int Cout) { return b200sp::conv_tc_ws_bytes(K, Cin, Cout); }
+extern "C" int64_t b200sp_conv_prepared_bytes(int K, int Cin, int Cout) {
+    if (b200sp::conv_direct_covers(K, Cin, Cout)) return 0;  // the register-gather kernel reads the raw weights
+    return b200sp::conv_tc_ws_bytes(K, Cin, Cout);
+}
+
+extern "C" int b200sp_set_conv_direct(int on) {
+    b200sp::conv_direct_set(on);
+    return B200SP_OK;
+}
+
+extern "C" int b200sp_conv_direct_covers(int K, int Cin, int Cout) { return b200sp::conv_direct_covers(K, Cin, Cout) ? 1 : 0; }
 
 extern "C" int b200sp_prep_weights_batch(const int64_t* desc_host, int n, void* desc_dev, int64_t desc_dev_bytes,
                                          void* stream) {
@@ -476,7 +490,9 @@ extern "C" int b200sp_gather_gemm(const float* in, int64_t n_in, int Cin, const 
     cudaStream_t st = (cudaStream_t)stream;
     if (conv_impl() == 0) {
         const int Ci_w = (wflags & 1) ? Cout : Cin, Co_w = (wflags & 1) ? Cin : Cout;
-        int rc = conv_tc_run(in, Cin, W, Ci_w, Co_w, wflags, tab, orow, rowmask, nullptr, nullptr, nullptr, n_out, 0, K, out, Cout,
+        int rc = conv_direct_run(in, Cin, W, wflags, tab, orow, rowmask, n_out, K, out, Cout, accumulate, st);
+        if (rc != B200SP_EUNSUP) return rc;
+        rc = conv_tc_run(in, Cin, W, Ci_w, Co_w, wflags, tab, orow, rowmask, nullptr, nullptr, nullptr, n_out, 0, K, out, Cout,
                              accumulate, 0, ws, ws_bytes, st);
         if (rc != B200SP_EUNSUP) return rc;
     }

@@ -41,6 +41,16 @@ def set_conv_impl(name):
     global _conv_impl_name
     check(lib.b200sp_set_conv_impl({"tc": 0, "fp32": 1}[name]), "set_conv_impl")
     _conv_impl_name = name
+    _direct_cache.clear()
+    invalidate_prepared_weights()
+
+
+def set_conv_direct(on):
+    """inside the tensor path: use the register-gather kernel for the narrow layers (default) or the tcgen05 kernel
+    for everything (A/B testing)"""
+    check(lib.b200sp_set_conv_direct(1 if on else 0), "set_conv_direct")
+    _direct_cache.clear()
+    invalidate_prepared_weights()
 
 
 def launch_count():
@@ -688,6 +698,18 @@ class SparseInverseConvFunction(Function):
         return din, dW, None, None
 
 
+_direct_cache = {}
+
+
+def _direct_covers(K, Cin, Cout):
+    """does the register-gather kernel (conv_direct.cu, table mode only) take this shape?"""
+    key = (K, Cin, Cout)
+    v = _direct_cache.get(key)
+    if v is None:
+        v = _direct_cache[key] = bool(lib.b200sp_conv_direct_covers(K, Cin, Cout)) and _conv_impl_name == "tc"
+    return v
+
+
 _CONV_FN = {"subm": SubMConvFunction, "dense": DenseConvFunction, "conv": SparseConvFunction,
             "inverse": SparseInverseConvFunction}
 
@@ -705,7 +727,7 @@ def conv_forward_raw(kind, features, filters, rb, prep):
     if kind == "conv":
         return gather_gemm(features, W3, rb.bwd, rb.outids.shape[0], wimg=wf)
     n_fine = rb.indices.shape[0]  # inverse
-    if rb.nonoverlap:
+    if rb.nonoverlap and not _direct_covers(W3.shape[0], W3.shape[1], W3.shape[2]):
         return gather_gemm_pairs(features, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, n_fine, wimg=wf)
     return gather_gemm(features, W3, rb.fwd, n_fine, wimg=wf)
 
@@ -732,7 +754,7 @@ def conv_backward_raw(kind, features, filters, grad_out, rb, prep, need_din=True
             dW = wgrad(features, grad_out, None, None, None, M, 1)
     elif kind == "conv":
         if need_din:
-            if rb.nonoverlap:
+            if rb.nonoverlap and not _direct_covers(W3.shape[0], W3.shape[2], W3.shape[1]):
                 din = gather_gemm_pairs(grad_out, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, M, M, wflags=W_T, wimg=wb)
             else:
                 din = gather_gemm(grad_out, W3, rb.fwd, M, wflags=W_T, wimg=wb)
@@ -811,6 +833,63 @@ class BNReLUConvFunction(Function):
         dw = dwb[0] if bn_w is not None and ctx.needs_input_grad[1] else None
         db = dwb[1] if bn_b is not None and ctx.needs_input_grad[2] else None
         return dx, dw, db, dW, None, None, None, None, None, None, None, None
+
+
+class CrossEntropyFunction(Function):
+    """softmax cross-entropy with ignore_index / class weights, mean reduction -- what DODA's model_fn asks of
+    nn.CrossEntropyLoss (model/unet.py:168-170), in one pass over the logits per direction."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, weight, ignore_index):
+        _req_cuda(logits, labels)
+        if logits.dim() != 2 or labels.dim() != 1 or labels.shape[0] != logits.shape[0]:
+            raise ValueError("cross_entropy: logits [N, C] and labels [N] expected")
+        logits = _f32c(logits)
+        labels = labels.contiguous() if labels.dtype == torch.int64 else labels.long()
+        weight = _f32c(weight) if weight is not None else None
+        N, C = logits.shape
+        out2 = torch.empty(2, dtype=_F32, device=logits.device)
+        if N == 0:
+            out2.fill_(float("nan"))
+        else:
+            ws = _workspace(int(lib.b200sp_cross_entropy_ws_bytes()), logits.device, "ce")
+            check(lib.b200sp_cross_entropy_fwd(logits.data_ptr(), labels.data_ptr(),
+                                               weight.data_ptr() if weight is not None else None, N, C,
+                                               int(ignore_index), out2.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+                  "cross_entropy_fwd")
+        ctx.save_for_backward(logits, labels, weight, out2)
+        ctx.ignore_index = int(ignore_index)
+        return out2[0]
+
+    @staticmethod
+    def backward(ctx, dloss):
+        logits, labels, weight, out2 = ctx.saved_tensors
+        N, C = logits.shape
+        d = torch.empty_like(logits)
+        if N:
+            dloss = _f32c(dloss).reshape(1)
+            check(lib.b200sp_cross_entropy_bwd(logits.data_ptr(), labels.data_ptr(),
+                                               weight.data_ptr() if weight is not None else None, N, C, ctx.ignore_index,
+                                               out2.data_ptr(), dloss.data_ptr(), d.data_ptr(), _stream()),
+                  "cross_entropy_bwd")
+        return d, None, None, None
+
+
+def cross_entropy(logits, labels, weight=None, ignore_index=-100):
+    """F.cross_entropy(logits, labels, weight, ignore_index=..., reduction='mean') for [N, C <= 64] CUDA logits"""
+    return CrossEntropyFunction.apply(logits, labels, weight, ignore_index)
+
+
+class CrossEntropyLoss(torch.nn.Module):
+    """drop-in for nn.CrossEntropyLoss(weight=None, ignore_index=-100) (mean reduction) on [N, C] logits"""
+
+    def __init__(self, weight=None, ignore_index=-100):
+        super().__init__()
+        self.register_buffer("weight", weight)
+        self.ignore_index = ignore_index
+
+    def forward(self, logits, labels):
+        return cross_entropy(logits, labels, self.weight, self.ignore_index)
 
 
 def bn_batch_stats_args(bn):

@@ -118,7 +118,8 @@ def model_step(model, batch, voxel_mode=4, criterion=None, device="cuda", coords
     voxel_feats = pointgroup_ops.voxelization(feats, v2p_map, voxel_mode)
     x = spconv.SparseConvTensor(voxel_feats, voxel_coords, batch["spatial_shape"], batch_size)
     scores = model(x, p2v_map)
-    if criterion is None:
-        criterion = nn.CrossEntropyLoss(ignore_index=255)
-    loss = criterion(scores, labels)
+    if criterion is None:  # the engine's one-pass cross-entropy (same result as nn.CrossEntropyLoss(ignore_index=255))
+        loss = _ops.cross_entropy(scores, labels, ignore_index=255)
+    else:
+        loss = criterion(scores, labels)
     return loss, scores

@@ -133,6 +133,12 @@ int64_t b200sp_conv_ws_bytes(int K, int Cin, int Cout);
 /* 0 (default) = tcgen05 tensor-core path (3xTF32, fp32-accurate) wherever the shape is covered;
  * 1 = fp32 CUDA-core kernel only.  Also selectable with the environment variable B200SP_CONV_IMPL=fp32. */
 int b200sp_set_conv_impl(int impl);
+/* Inside the tensor path, narrow layers (Cin, Cout in {16, 32}, table mode) run the register-gather
+ * kernel (conv_direct.cu: warp-level mma.m16n8k8 3xTF32 fed straight from gathered rows, reads the raw weights);
+ * everything else runs the persistent tcgen05 kernel.  on = 0 switches the register-gather kernel off
+ * (also B200SP_DIRECT=0); _covers tells which kernel a shape would get. */
+int b200sp_set_conv_direct(int on);
+int b200sp_conv_direct_covers(int K, int Cin, int Cout);
 
 /* weight gradient: dW[k][ci][co] += sum_i a[pa[k][i]][ci] * b[pb[k][i]][co].   pa/pb NULL -> identity
  * rows (1x1 conv: n_upper rows, pairnum ignored).  dW must be zero-initialised by the caller. */
@@ -243,6 +249,20 @@ int b200sp_aggregation_fwd(int n, int nsample, int c, int w_c, const float* in_d
 int b200sp_aggregation_bwd(int n, int nsample, int c, int w_c, const float* in_dev, const float* pos_dev,
                            const float* w_dev, const int32_t* idx_dev, const float* dout_dev, float* din_dev,
                            float* dpos_dev, float* dw_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Loss epilogue: softmax cross-entropy over point logits, replaces the nn.CrossEntropyLoss call
+ * of model/unet.py:168-170 (ignore_index, optional per-class weights, mean reduction).
+ * out2[0] = loss, out2[1] = sum of the weights of the counted rows (kept for the backward).
+ * ws: b200sp_cross_entropy_ws_bytes() bytes, zero-filled once by the caller.  C <= 64.
+ * ------------------------------------------------------------------------------------------ */
+int64_t b200sp_cross_entropy_ws_bytes(void);
+int b200sp_cross_entropy_fwd(const float* logits_dev /*[N,C]*/, const int64_t* labels_dev /*[N]*/,
+                             const float* weight_dev /*[C] or NULL*/, int64_t N, int C, int64_t ignore_index,
+                             float* out2_dev /*[2]*/, void* ws_dev, int64_t ws_bytes, void* stream);
+int b200sp_cross_entropy_bwd(const float* logits_dev, const int64_t* labels_dev, const float* weight_dev, int64_t N,
+                             int C, int64_t ignore_index, const float* out2_dev, const float* dloss_dev /*[1]*/,
+                             float* dlogits_dev /*[N,C]*/, void* stream);
 
 #ifdef __cplusplus
 }

@@ -165,6 +165,46 @@ def test_conv_many_tiles_per_cta(cuda_dev, kind, Cin, Cout):
     _conv_case(cuda_dev, kind, Cin, Cout, seed=7, n=45000, shape=(96, 96, 64))
 
 
+@pytest.mark.parametrize("Cin,Cout", [(16, 16), (32, 16), (16, 32), (32, 32)])
+def test_register_gather_kernel_matches_tcgen05_and_oracle(cuda_dev, Cin, Cout):
+    """the two tensor-path kernels (conv_direct.cu for the narrow layers, conv_tc.cu for the rest) on the same
+    inputs: SubM forward + dgrad (row order and mask order), strided conv and its inverse, each against the oracle"""
+    from doda_b200 import ops
+    from oracle.conv import indice_conv_ref
+    torch.manual_seed(4)
+    shape = (26, 23, 21)
+    coords = random_coords(4, 2500, 2, shape)
+    c = torch.from_numpy(coords).to(cuda_dev)
+    n = coords.shape[0]
+    rb = ops.build_rulebook(c, 2, list(shape), 3, 1, 1, 1, subm=True)
+    rd = ops.build_rulebook(c, 2, list(shape), 2, 2, 0, 1)
+    nd = rd.outids.shape[0]
+    feat, g = torch.randn(n, Cin), torch.randn(n, Cout)
+    W3, W8 = torch.randn(27, Cin, Cout) * 0.2, torch.randn(8, Cin, Cout) * 0.3
+    fd, gd, W3d, W8d = feat.to(cuda_dev), g.to(cuda_dev), W3.to(cuda_dev), W8.to(cuda_dev)
+    _, pairs, pairnum, _ = _rb_oracle(coords, 2, list(shape), 3, 1, 1, 1, True)
+    ref_fwd = indice_conv_ref(feat.double(), W3.double(), pairs, pairnum, n, subm=True)
+    Wt = torch.flip(W3, [0]).transpose(1, 2).contiguous()
+    ref_dg = indice_conv_ref(g.double(), Wt.double(), pairs, pairnum, n, subm=True)
+    outs = {}
+    try:
+        for on in (1, 0):
+            ops.set_conv_direct(on)
+            assert ops._direct_covers(27, Cin, Cout) == bool(on)
+            outs[on] = [ops.gather_gemm(fd, W3d, rb.nbr, n),
+                        ops.gather_gemm(fd, W3d, rb.nbr_perm, n, orow=rb.order, rowmask=rb.rowmask),
+                        ops.gather_gemm(gd, W3d, rb.nbr_perm, n, wflags=ops.W_T_MIRROR, orow=rb.order, rowmask=rb.rowmask),
+                        ops.conv_forward_raw("conv", fd, W8d, rd, None)]
+            coarse = outs[on][3]
+            outs[on].append(ops.conv_forward_raw("inverse", coarse, W8d.transpose(1, 2).contiguous(), rd, None))
+            outs[on].append(ops.conv_backward_raw("conv", fd, W8d, torch.ones(nd, Cout, device=cuda_dev), rd, None, True, False)[0])
+    finally:
+        ops.set_conv_direct(1)
+    assert rel_err(outs[1][0], ref_fwd) <= TOL and rel_err(outs[1][1], ref_fwd) <= TOL and rel_err(outs[1][2], ref_dg) <= TOL
+    for a, b in zip(outs[1], outs[0]):
+        assert rel_err(a, b) <= TOL
+
+
 def test_prepared_weight_images_follow_updates(cuda_dev):
     """module path: weight images are prepared ahead (one launch for all layers) and must track in-place updates"""
     from doda_b200 import spconv, ops
@@ -173,8 +213,10 @@ def test_prepared_weight_images_follow_updates(cuda_dev):
     shape = (20, 18, 16)
     coords = random_coords(11, 900, 2, shape)
     _, pairs, pairnum, _ = _rb_oracle(coords, 2, list(shape), 3, 1, 1, 1, True)
-    conv = spconv.SubMConv3d(16, 32, 3, padding=1, bias=False, indice_key="k").to(cuda_dev)
-    other = spconv.SubMConv3d(32, 16, 3, padding=1, bias=False, indice_key="k").to(cuda_dev)
+    # 80 channels: a shape of the persistent tcgen05 kernel (the register-gather kernel of the narrow layers reads the
+    # raw weights and has no image)
+    conv = spconv.SubMConv3d(16, 80, 3, padding=1, bias=False, indice_key="k").to(cuda_dev)
+    other = spconv.SubMConv3d(80, 16, 3, padding=1, bias=False, indice_key="k").to(cuda_dev)
     feats = torch.randn(coords.shape[0], 16)
     for it in range(3):
         x = spconv.SparseConvTensor(feats.to(cuda_dev).requires_grad_(True), torch.from_numpy(coords).to(cuda_dev),
@@ -362,6 +404,32 @@ def test_fused_bn_relu_conv_matches_unfused(cuda_dev):
         assert rel_err(ga, gb) <= 1e-4
     for ba, bb in zip(a[4], b[4]):
         assert rel_err(ba.float(), bb.float()) <= 1e-6
+
+
+@pytest.mark.parametrize("C,weighted", [(11, False), (13, True), (40, False)])
+def test_cross_entropy_matches_torch(cuda_dev, C, weighted):
+    """loss epilogue (model/unet.py:168-170): value and gradient against torch's fp64 CPU cross_entropy, with
+    ignored rows and class weights; all-ignored input gives nan like torch"""
+    from doda_b200 import ops
+    torch.manual_seed(C)
+    N = 20000
+    logits = torch.randn(N, C) * 3
+    labels = torch.randint(0, C, (N,))
+    labels[torch.rand(N) < 0.07] = 255
+    w = torch.rand(C) + 0.5 if weighted else None
+    ref_in = logits.double().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(ref_in, labels, weight=w.double() if weighted else None, ignore_index=255)
+    (ref * 1.7).backward()
+    x = logits.to(cuda_dev).requires_grad_(True)
+    out = ops.cross_entropy(x, labels.to(cuda_dev), w.to(cuda_dev) if weighted else None, ignore_index=255)
+    (out * 1.7).backward()
+    assert abs(float(out) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert rel_err(x.grad, ref_in.grad) <= 1e-5
+    assert torch.all(x.grad[labels.to(cuda_dev) == 255] == 0)
+    none = ops.cross_entropy(x.detach(), torch.full((N,), 255, device=cuda_dev), None, ignore_index=255)
+    assert torch.isnan(none)
+    mod = ops.CrossEntropyLoss(ignore_index=255).to(cuda_dev)
+    assert float(mod(x.detach(), labels.to(cuda_dev))) == float(ops.cross_entropy(x.detach(), labels.to(cuda_dev), None, 255))
 
 
 def test_voxelize_and_devoxelize(cuda_dev):

@@ -14,10 +14,16 @@ model = SparseConvNet(mid_channel=16).to(dev).train()
 crit = torch.nn.CrossEntropyLoss(ignore_index=255)
 def step():
     for p in model.parameters(): p.grad = None
-    loss, _ = model_step(model, batch, criterion=crit, device=dev)
+    loss, _ = model_step(model, batch, criterion=None, device=dev)
     loss.backward()
 for _ in range(4): step()
 torch.cuda.synchronize()
+# shapes of the conv / wgrad launches of one step, in launch order (to put next to the CUPTI durations)
+from doda_b200 import ops
+ops.profile_begin(); step(); torch.cuda.synchronize(); recs = ops.profile_end()
+shapes = collections.defaultdict(list)
+for r in recs:
+    shapes[r["kernel"]].append(r)
 NS = 4
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(NS): step()
@@ -26,7 +32,7 @@ evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CU
 tot = collections.defaultdict(float); cnt = collections.Counter()
 ivs = []
 for e in evs:
-    name = e.name.split("(")[0][:70]
+    name = e.name.replace("(anonymous namespace)::", "").split("(")[0][:70]
     tot[name] += e.device_time if hasattr(e, "device_time") else e.cuda_time
     cnt[name] += 1
     ivs.append((e.time_range.start, e.time_range.end))
@@ -43,3 +49,27 @@ print("steps %d: wall %.2f ms/step, GPU busy (union of kernels) %.2f ms/step, su
       % (NS, wall / NS / 1e3, busy / NS / 1e3, sum(tot.values()) / NS / 1e3, len(evs) // NS))
 for name, t in sorted(tot.items(), key=lambda kv: -kv[1])[:28]:
     print("%9.1f us/step %5d  %s" % (t / NS, cnt[name] // NS, name))
+
+per = collections.defaultdict(list)
+for e in sorted(evs, key=lambda e: e.time_range.start):
+    n = e.name.replace("(anonymous namespace)::", "")
+    key = "wgrad" if "k_wgrad" in n else "conv" if "k_conv_tc" in n or "k_conv_direct" in n or "k_gather_gemm" in n else "bn" if "k_bn_" in n or "k_affine" in n else None
+    if key:
+        per[key].append((n.split("(")[0][-28:], e.time_range.end - e.time_range.start))
+L = per["bn"]; n1 = len(L) // NS
+rk = [r for r in recs if r["kernel"] in ("bn_fwd", "bn_bwd")]
+print("== bn: %d launches/step, %d bn calls recorded" % (n1, len(rk)))
+i = 0
+for r in rk:
+    nk = 2
+    names = [L[n1 + i + q] for q in range(nk)]
+    print("  %-7s M %6d C %3d : %s" % (r["kernel"], r["M"], r["C"], "  ".join("%s %.1f us" % (n[-22:], d) for n, d in names)))
+    i += nk
+for key in ("conv", "wgrad"):
+    L = per[key]; n1 = len(L) // NS
+    print("== %s: %d launches/step; per-launch us (step 2 of the capture), with the recorded shapes" % (key, n1))
+    rk = [r for r in recs if (r["kernel"] in ("k_gather_gemm",) and key == "conv") or (r["kernel"] == "k_wgrad" and key == "wgrad")]
+    for i in range(n1):
+        name, d = L[n1 + i]
+        r = rk[i] if i < len(rk) else {}
+        print("  %3d %-28s %8.1f us  %s" % (i, name, d, {k: v for k, v in r.items() if k not in ("kernel", "ms")}))
