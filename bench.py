@@ -59,9 +59,16 @@ class ClockSampler(threading.Thread):
     through NVML (nvidia_ml_py).  An `nvidia-smi -lms` subprocess was used first: its queries stalled the CUDA
     process for 40-100 ms at a time (visible as outlier steps); it remains the fallback when NVML is unavailable."""
 
-    def __init__(self, index, period=0.2):
+    def __init__(self, index, period=1.0):
         super().__init__(daemon=True)
         self.index, self.rows, self._stop_evt, self.proc, self.period = index, [], threading.Event(), None, period
+        self._kick = threading.Event()
+
+    def kick(self):
+        """take a sample now (the timed loops call this at their middle step: an NVML query holds a driver lock for
+        several ms and delays the launches of the step it lands in, so the sampler is kept to one query per timed
+        loop plus a slow periodic one instead of a fast poll)"""
+        self._kick.set()
 
     def _run_nvml(self):
         import pynvml as nv
@@ -77,7 +84,8 @@ class ClockSampler(threading.Thread):
             sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
             r = int(get_reasons(h))
             self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
-            self._stop_evt.wait(self.period)
+            self._kick.wait(self.period)
+            self._kick.clear()
 
     def _run_smi(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -101,6 +109,7 @@ class ClockSampler(threading.Thread):
 
     def stop(self):
         self._stop_evt.set()
+        self._kick.set()
         if self.proc is not None:
             try:
                 self.proc.terminate()
@@ -255,6 +264,8 @@ def main():
             flush.zero_()  # L2 flush between timed iterations (not timed)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
+            if sampler is not None and i == nsteps // 2:
+                sampler.kick()
             loss = step(b)
             if read_loss:
                 loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)  # device -> host, every step

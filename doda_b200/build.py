@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200sparse.so")
-SOURCES = ["core.cu", "rulebook.cu", "conv.cu", "conv_tc.cu", "conv_direct.cu", "wgrad_tc.cu", "elementwise.cu", "loss.cu", "pgops.cu", "pointops.cu"]
+SOURCES = ["core.cu", "rulebook.cu", "conv.cu", "conv_tc.cu", "conv_direct.cu", "wgrad_tc.cu", "wgrad_direct.cu", "elementwise.cu", "loss.cu", "pgops.cu", "pointops.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", 
          "-Xcompiler", "-fPIC", "-DB200SP_BUILD"]

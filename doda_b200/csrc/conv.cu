@@ -412,6 +412,9 @@ void conv_direct_set(int on);
 int conv_direct_run(const float* in, int Cin, const float* W, int wflags, const int* tab, const int* orow,
                     const int* rowmask, long long n_rows, int K, float* out, int Cout, int accumulate, cudaStream_t st);
 int conv_tc_prep_batch(const int64_t* desc_host, int n, void* desc_dev, int64_t desc_dev_bytes, cudaStream_t st);
+bool wgrad_direct_covers(int K, int Ca, int Cb);
+int wgrad_direct_run(const float* a, int Ca, const float* g, int Cb, const int* tab, const int* orow, const int* rowmask,
+                     long long n_rows, int K, float* dW, cudaStream_t st);
 int wgrad_tc_run(const float* a, int Ca, const float* b, int Cb, const int* pa, const int* pb, const int* pairnum,
                  int64_t n_upper, int K, int64_t pstride, float* dW, cudaStream_t st);
 
@@ -556,6 +559,18 @@ extern "C" int b200sp_wgrad(const float* a, int Ca, const float* b, int Cb, cons
     k_wgrad<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     B200SP_LAUNCH_CHECK();
     return B200SP_OK;
+}
+
+extern "C" int b200sp_wgrad_table_covers(int K, int Ca, int Cb) {
+    return (conv_impl() == 0 && b200sp::wgrad_direct_covers(K, Ca, Cb)) ? 1 : 0;
+}
+
+extern "C" int b200sp_wgrad_table(const float* a, int Ca, const float* g, int Cb, const int32_t* tab, const int32_t* orow,
+                                  const int32_t* rowmask, int64_t n_rows, int K, float* dW, void* stream) {
+    B200SP_CHECK_ARG(Ca >= 1 && Cb >= 1 && K >= 1 && n_rows >= 0, "wgrad_table: bad sizes");
+    B200SP_CHECK_ARG(tab || K == 1, "wgrad_table: tab == NULL requires K == 1");
+    B200SP_CHECK_ARG(b200sp_wgrad_table_covers(K, Ca, Cb), "wgrad_table: shape K=%d %dx%d is not covered (ask b200sp_wgrad_table_covers; use b200sp_wgrad)", K, Ca, Cb);
+    return wgrad_direct_run(a, Ca, g, Cb, tab, orow, rowmask, n_rows, K, dW, (cudaStream_t)stream);
 }
 
 extern "C" int b200sp_weight_transpose(const float* W, int K, int Cin, int Cout, int mirror, float* out,

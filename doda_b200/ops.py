@@ -42,6 +42,7 @@ def set_conv_impl(name):
     check(lib.b200sp_set_conv_impl({"tc": 0, "fp32": 1}[name]), "set_conv_impl")
     _conv_impl_name = name
     _direct_cache.clear()
+    _wgt_cache.clear()
     invalidate_prepared_weights()
 
 
@@ -50,6 +51,7 @@ def set_conv_direct(on):
     for everything (A/B testing)"""
     check(lib.b200sp_set_conv_direct(1 if on else 0), "set_conv_direct")
     _direct_cache.clear()
+    _wgt_cache.clear()
     invalidate_prepared_weights()
 
 
@@ -563,6 +565,29 @@ def wgrad(a, b, pa, pb, pairnum, n_upper, K):
     return dW
 
 
+_wgt_cache = {}
+
+
+def _wgrad_table_covers(K, Ca, Cb):
+    key = (K, Ca, Cb)
+    v = _wgt_cache.get(key)
+    if v is None:
+        v = _wgt_cache[key] = bool(lib.b200sp_wgrad_table_covers(K, Ca, Cb))
+    return v
+
+
+def wgrad_table(a, g, tab, n_rows, K, orow=None, rowmask=None):
+    """dW[k] = sum_r a[tab[r][k]]^T g[orow[r]]  -> [K, Ca, Cb]  (out-stationary form, shapes of _wgrad_table_covers)"""
+    Ca, Cb = a.shape[1], g.shape[1]
+    dW = _dw_arena.take((K, Ca, Cb), a.device)
+    with _Timed(kernel="k_wgrad", n_rows=a.shape[0], Ca=Ca, Cb=Cb, K=K, n_upper=n_rows):
+        check(lib.b200sp_wgrad_table(a.data_ptr(), Ca, g.data_ptr(), Cb, tab.data_ptr() if tab is not None else None,
+                                     orow.data_ptr() if orow is not None else None,
+                                     rowmask.data_ptr() if rowmask is not None else None, n_rows, K, dW.data_ptr(),
+                                     _stream()), "wgrad_table")
+    return dW
+
+
 def weight_transpose(W3, mirror):
     K, Cin, Cout = W3.shape
     out = torch.empty((K, Cout, Cin), dtype=_F32, device=W3.device)
@@ -746,12 +771,18 @@ def conv_backward_raw(kind, features, filters, grad_out, rb, prep, need_din=True
             else:
                 din = gather_gemm(grad_out, W3, rb.nbr, M, wflags=W_T_MIRROR, wimg=wb)
         if need_dw:
-            dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K)
+            if rb.nbr_perm is not None and _wgrad_table_covers(rb.K, features.shape[1], grad_out.shape[1]):
+                dW = wgrad_table(features, grad_out, rb.nbr_perm, M, rb.K, orow=rb.order, rowmask=rb.rowmask)
+            else:
+                dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K)
     elif kind == "dense":
         if need_din:
             din = gather_gemm(grad_out, W3, None, M, wflags=W_T, wimg=wb)
         if need_dw:
-            dW = wgrad(features, grad_out, None, None, None, M, 1)
+            if _wgrad_table_covers(1, features.shape[1], grad_out.shape[1]):
+                dW = wgrad_table(features, grad_out, None, M, 1)
+            else:
+                dW = wgrad(features, grad_out, None, None, None, M, 1)
     elif kind == "conv":
         if need_din:
             if rb.nonoverlap and not _direct_covers(W3.shape[0], W3.shape[2], W3.shape[1]):
@@ -759,13 +790,19 @@ def conv_backward_raw(kind, features, filters, grad_out, rb, prep, need_din=True
             else:
                 din = gather_gemm(grad_out, W3, rb.fwd, M, wflags=W_T, wimg=wb)
         if need_dw:
-            dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K)
+            if _wgrad_table_covers(rb.K, features.shape[1], grad_out.shape[1]):
+                dW = wgrad_table(features, grad_out, rb.bwd, grad_out.shape[0], rb.K)
+            else:
+                dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K)
     else:  # inverse
         n_fine = rb.indices.shape[0]
         if need_din:
             din = gather_gemm(grad_out, W3, rb.bwd, M, wflags=W_T, wimg=wb)
         if need_dw:
-            dW = wgrad(features, grad_out, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, rb.K)
+            if _wgrad_table_covers(rb.K, features.shape[1], grad_out.shape[1]):
+                dW = wgrad_table(features, grad_out, rb.fwd, n_fine, rb.K)
+            else:
+                dW = wgrad(features, grad_out, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, rb.K)
     return din, (dW.view(filters.shape) if dW is not None else None)
 
 

@@ -146,6 +146,15 @@ int b200sp_wgrad(const float* a_dev, int Ca, const float* b_dev, int Cb, const i
                  const int32_t* pairnum_dev, int64_t n_upper, int K, int64_t pair_stride, float* dW_dev /*[K,Ca,Cb]*/,
                  void* stream);
 
+/* Weight gradient in TABLE form (out-stationary, wgrad_direct.cu), for the shapes _covers reports (Ca, Cb in
+ * {16, 32}):  dW[k][ca][cb] += sum_r a[tab[r][k]][ca] * g[orow[r]][cb],  tab/orow/rowmask as in b200sp_gather_gemm
+ * (SubM: nbr_perm/order/rowmask of b200sp_rulebook_subm; strided conv: bwd table, a = input, g = output gradient;
+ * inverse conv: fwd table).  g is read once per row instead of once per pair.  dW must be zeroed by the caller. */
+int b200sp_wgrad_table_covers(int K, int Ca, int Cb);
+int b200sp_wgrad_table(const float* a_dev, int Ca, const float* g_dev, int Cb, const int32_t* tab_dev,
+                       const int32_t* orow_dev, const int32_t* rowmask_dev, int64_t n_rows, int K, float* dW_dev,
+                       void* stream);
+
 /* out[k'][co][ci] = W[k][ci][co], k' = mirror ? K-1-k : k   (weights for dgrad) */
 int b200sp_weight_transpose(const float* W_dev, int K, int Cin, int Cout, int mirror, float* out_dev, void* stream);
 

@@ -198,11 +198,21 @@ def test_register_gather_kernel_matches_tcgen05_and_oracle(cuda_dev, Cin, Cout):
             coarse = outs[on][3]
             outs[on].append(ops.conv_forward_raw("inverse", coarse, W8d.transpose(1, 2).contiguous(), rd, None))
             outs[on].append(ops.conv_backward_raw("conv", fd, W8d, torch.ones(nd, Cout, device=cuda_dev), rd, None, True, False)[0])
+            # weight gradients: table form (wgrad_direct.cu) vs pair lists, all four conv kinds
+            gcoarse = torch.sin(torch.arange(nd * Cout, device=cuda_dev, dtype=torch.float32)).view(nd, Cout)
+            outs[on].append(ops.conv_backward_raw("subm", fd, W3d, gd, rb, None, False, True)[1].clone())
+            outs[on].append(ops.conv_backward_raw("conv", fd, W8d, gcoarse, rd, None, False, True)[1].clone())
+            outs[on].append(ops.conv_backward_raw("inverse", gcoarse, W8d.transpose(1, 2).contiguous(), fd, rd, None, False, True)[1].clone())
+            outs[on].append(ops.conv_backward_raw("dense", fd, W3d[:1], gd, None, None, False, True)[1].clone())
     finally:
         ops.set_conv_direct(1)
     assert rel_err(outs[1][0], ref_fwd) <= TOL and rel_err(outs[1][1], ref_fwd) <= TOL and rel_err(outs[1][2], ref_dg) <= TOL
-    for a, b in zip(outs[1], outs[0]):
-        assert rel_err(a, b) <= TOL
+    from oracle.conv import indice_conv_backward_ref
+    _, ref_dw = indice_conv_backward_ref(feat.double(), W3.double(), g.double(), pairs, pairnum, subm=True)
+    assert rel_err(outs[1][6], ref_dw.view(27, Cin, Cout)) <= TOL
+    assert rel_err(outs[1][9].view(Cin, Cout), feat.double().t() @ g.double()) <= TOL
+    for i, (a, b) in enumerate(zip(outs[1], outs[0])):
+        assert rel_err(a, b) <= TOL, i
 
 
 def test_prepared_weight_images_follow_updates(cuda_dev):
