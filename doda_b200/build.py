@@ -7,6 +7,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200sparse.so")
+FAST_SRC = os.path.join(CSRC, "fastcall.c")
+FAST_OUT = os.path.join(HERE, "_b200fast.so")  # CPython module doda_b200._b200fast (fast-call binding of the hot entry points)
 SOURCES = ["core.cu", "rulebook.cu", "conv.cu", "conv_tc.cu", "conv_direct.cu", "wgrad_tc.cu", "wgrad_direct.cu", "elementwise.cu", "loss.cu", "pgops.cu", "pointops.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", 
@@ -23,7 +25,26 @@ def _deps_mtime():
     return m
 
 
+def build_fast(force=False):
+    """gcc: csrc/fastcall.c -> _b200fast.so, linked against libb200sparse.so next to it (rpath $ORIGIN)"""
+    import sysconfig
+    if not force and os.path.exists(FAST_OUT) and os.path.getmtime(FAST_OUT) >= max(_deps_mtime(), os.path.getmtime(OUT)):
+        return FAST_OUT
+    cmd = [os.environ.get("CC", "gcc"), "-O2", "-shared", "-fPIC", "-I" + sysconfig.get_paths()["include"], FAST_SRC,
+           "-o", FAST_OUT, "-L" + HERE, "-lb200sparse", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("gcc failed for fastcall.c:\n%s\n%s" % (r.stdout, r.stderr))
+    return FAST_OUT
+
+
 def build(force=False, verbose=False):
+    out = _build_lib(force, verbose)
+    build_fast(force)
+    return out
+
+
+def _build_lib(force=False, verbose=False):
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     if not force and os.path.exists(OUT) and os.path.getmtime(OUT) >= _deps_mtime():
         return OUT

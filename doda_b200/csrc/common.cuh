@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <stdarg.h>
 #include "../../include/b200sparse.h"
 
@@ -35,6 +36,14 @@ void add_launches(int n);
         B200SP_CUDA(cudaGetLastError());    \
     } while (0)
 #define B200SP_LAUNCH_CHECK() B200SP_LAUNCH_CHECK_N(1)
+
+// developer knobs are read from the environment ONCE per call site (getenv walks the whole environment; the conv
+// launch path used to do that seven times per launch)
+#define B200SP_ENV_INT(var, name, dflt)                  \
+    static const int var = [] {                          \
+        const char* e__ = getenv(name);                  \
+        return e__ ? atoi(e__) : (dflt);                 \
+    }()
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -627,9 +627,9 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
     int smax = 4;
     uint32_t two_cta_budget = 110u * 1024u;
     {
-        const char* e = getenv("B200SP_TC_SLOTS");  // dev knob: > 4 trades the second CTA per SM for a deeper ring
-        if (e && atoi(e) >= 2) {
-            smax = atoi(e);
+        B200SP_ENV_INT(env_slots, "B200SP_TC_SLOTS", 0);  // dev knob: > 4 trades the second CTA per SM for a deeper ring
+        if (env_slots >= 2) {
+            smax = env_slots;
             if (smax > 4) two_cta_budget = 0;
         }
     }
@@ -649,16 +649,16 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
     {
         const uint32_t used = (uint32_t)best * a_bytes + fixed;
         int mult = 4;
-        const char* e = getenv("B200SP_TC_BMULT");
-        if (e && atoi(e) >= 1) mult = atoi(e);
+        B200SP_ENV_INT(env_bmult, "B200SP_TC_BMULT", 0);
+        if (env_bmult >= 1) mult = env_bmult;
         while (mult > 1 && used + (uint32_t)(best * mult) * (pl.stageB + 16u) > budget) --mult;
         pl.nslots_b = best * mult;
     }
     // issuer warps: each smem slot must belong to exactly ONE issuer (its mbarrier waits are parity waits, an issuer
     // running a fill ahead of a slot it shares would alias phases), so ni divides nslots; two accumulator sets
     {
-        const char* e = getenv("B200SP_TC_ISSUERS");
-        const int want = std::max(1, std::min(e ? atoi(e) : TC_MAX_ISSUERS, TC_MAX_ISSUERS));
+        B200SP_ENV_INT(env_issuers, "B200SP_TC_ISSUERS", TC_MAX_ISSUERS);
+        const int want = std::max(1, std::min(env_issuers, TC_MAX_ISSUERS));
         pl.ni = 0;
         for (int ni = want; ni >= 1; --ni)
             if (best % ni == 0 && TC_NBUF * ni * pl.Cout_pad <= 512) {
@@ -719,16 +719,16 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
     p.nchunks = pl.nchunks; p.Cout_pad = pl.Cout_pad; p.accumulate = accumulate; p.pairs_mode = pairs_mode;
     p.nslots = pl.nslots; p.nslots_b = pl.nslots_b; p.stageB_bytes = pl.stageB; p.tmem_cols = pl.tmem_cols; p.ni = pl.ni;
     {
-        const char* e = getenv("B200SP_TC_DEBUG");
-        p.dbg = e ? atoi(e) : 0;
+        B200SP_ENV_INT(env_dbg, "B200SP_TC_DEBUG", 0);
+        p.dbg = env_dbg;
     }
     p.row_tiles = (int)cdiv(n_rows, TC_BM);
     // few row tiles (deep U-Net levels): deal each tile's active offsets to nsplit CTAs so the machine is not idle
     // behind two or three serial tiles; the partial sums meet in the output through float4 atomics
     p.nsplit = 1;
     if (!pairs_mode && tab && K > 1 && p.row_tiles * 2 <= num_sms()) {
-        const char* e = getenv("B200SP_TC_NOSPLIT");
-        if (!(e && atoi(e))) p.nsplit = std::max(1, std::min(K, 2 * num_sms() / p.row_tiles));
+        B200SP_ENV_INT(env_nosplit, "B200SP_TC_NOSPLIT", 0);
+        if (!env_nosplit) p.nsplit = std::max(1, std::min(K, 2 * num_sms() / p.row_tiles));
     }
     if (p.nsplit > 1 && !accumulate) B200SP_CUDA(cudaMemsetAsync(out, 0, (size_t)n_rows * Cout * sizeof(float), st));
     p.total_tiles = p.row_tiles * (pairs_mode ? K : p.nsplit);

@@ -70,29 +70,43 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restric
         }
     }
     if (active) {
-        for (int64_t r = (int64_t)blockIdx.x * rpb + rl; r < M; r += (int64_t)gridDim.x * rpb) {
-            float xv[VEC], gv[VEC];
-            if (VEC == 4) {
-                float4 t = __ldg(reinterpret_cast<const float4*>(x + r * C) + cg);
-                xv[0] = t.x; xv[1] = t.y; xv[2] = t.z; xv[3] = t.w;
-                if (MODE == 1) {
-                    float4 g = __ldg(reinterpret_cast<const float4*>(dy + r * C) + cg);
-                    gv[0] = g.x; gv[1] = g.y; gv[2] = g.z; gv[3] = g.w;
+        // UNR rows per trip with all loads issued before the first use: a block is ~8 warps and the grid ~2 blocks
+        // per SM, so memory-level parallelism has to come from inside the thread
+        constexpr int UNR = 4;
+        const int64_t stride = (int64_t)gridDim.x * rpb;
+        for (int64_t r0 = (int64_t)blockIdx.x * rpb + rl; r0 < M; r0 += UNR * stride) {
+            float xv[UNR][VEC], gv[UNR][VEC];
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int64_t r = r0 + u * stride;
+                if (r < M) {
+                    if (VEC == 4) {
+                        float4 t = __ldg(reinterpret_cast<const float4*>(x + r * C) + cg);
+                        xv[u][0] = t.x; xv[u][1] = t.y; xv[u][2] = t.z; xv[u][3] = t.w;
+                        if (MODE == 1) {
+                            float4 g = __ldg(reinterpret_cast<const float4*>(dy + r * C) + cg);
+                            gv[u][0] = g.x; gv[u][1] = g.y; gv[u][2] = g.z; gv[u][3] = g.w;
+                        }
+                    } else {
+                        xv[u][0] = __ldg(x + r * C + cg);
+                        if (MODE == 1) gv[u][0] = __ldg(dy + r * C + cg);
+                    }
                 }
-            } else {
-                xv[0] = __ldg(x + r * C + cg);
-                if (MODE == 1) gv[0] = __ldg(dy + r * C + cg);
             }
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) {
-                if (MODE == 0) {
-                    a0[v] += xv[v];
-                    a1[v] = fmaf(xv[v], xv[v], a1[v]);
-                } else {
-                    float g = gv[v];
-                    if (relu && fmaf(xv[v], sc[v], sh[v]) <= 0.f) g = 0.f;
-                    a0[v] += g;
-                    a1[v] = fmaf(g, (xv[v] - mu[v]) * is[v], a1[v]);
+            for (int u = 0; u < UNR; ++u) {
+                if (r0 + u * stride >= M) break;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) {
+                    if (MODE == 0) {
+                        a0[v] += xv[u][v];
+                        a1[v] = fmaf(xv[u][v], xv[u][v], a1[v]);
+                    } else {
+                        float g = gv[u][v];
+                        if (relu && fmaf(xv[u][v], sc[v], sh[v]) <= 0.f) g = 0.f;
+                        a0[v] += g;
+                        a1[v] = fmaf(g, (xv[u][v] - mu[v]) * is[v], a1[v]);
+                    }
                 }
             }
         }
@@ -124,14 +138,19 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restric
     const int SL = E >= BN_THREADS ? 1 : BN_THREADS / E;
     for (int i = tid; i < E * SL; i += BN_THREADS) {
         const int sl = i / E, e = i - sl * E;
-        double a = 0.0, b2 = 0.0;
+        // eight loads in flight per thread: with two, a 96-entry layer walked 74 dependent L2 round trips here and the
+        // fold, not the reduction, set the kernel's duration (25 us for 27 k rows x 48 channels)
+        double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         int g = sl;
-        for (; g + SL < G; g += 2 * SL) {  // two independent chains keep loads in flight
-            a += (double)__ldcg(&partial[(int64_t)g * E + e]);
-            b2 += (double)__ldcg(&partial[(int64_t)(g + SL) * E + e]);
+        for (; g + 7 * SL < G; g += 8 * SL) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(&partial[(int64_t)(g + u * SL) * E + e]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] += (double)v[u];
         }
-        if (g < G) a += (double)__ldcg(&partial[(int64_t)g * E + e]);
-        s_fold[i] = a + b2;
+        for (; g < G; g += SL) a[0] += (double)__ldcg(&partial[(int64_t)g * E + e]);
+        s_fold[i] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     }
     __syncthreads();
     for (int c = tid; c < C; c += BN_THREADS) {
@@ -335,7 +354,7 @@ extern "C" int64_t b200sp_bn_ws_bytes(int64_t M, int C) {
 static int bn_grid(int64_t M, int C, int VEC) {
     int CG = C / VEC;
     int rpb = BN_THREADS / CG;
-    int64_t g = cdiv(M, (int64_t)rpb * 4);
+    int64_t g = cdiv(M, (int64_t)rpb * 16);  // >= 16 rows per thread: fewer partial rows for the last block to fold
     if (g < 1) g = 1;
     if (g > BN_MAXGRID) g = BN_MAXGRID;
     return (int)g;

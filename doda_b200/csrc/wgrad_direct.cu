@@ -199,8 +199,12 @@ int launch(const WDParams& p0, cudaStream_t st) {
 bool conv_direct_enabled();
 
 bool wgrad_direct_covers(int K, int Ca, int Cb) {
+    // 32 x 32 is built but not used: 48 MMAs per 16-row tile-offset and 116 registers (two blocks per SM) make it
+    // 205 us inside the U-Net step on 118 k rows against 182 us for the tcgen05 pair-list kernel; 16 x 16 is 86 vs
+    // 200 us, 32 x 16 160 vs 290 us, 16 x 32 70 vs 140 us (tools/gpu_timeline.py, tools/dev_wgrad_direct.py)
+    B200SP_ENV_INT(env_all, "B200SP_WGRAD_DIRECT_ALL", 0);
     auto ok = [](int c) { return c == 16 || c == 32; };
-    return conv_direct_enabled() && K >= 1 && K <= 32 && ok(Ca) && ok(Cb);
+    return conv_direct_enabled() && K >= 1 && K <= 32 && ok(Ca) && ok(Cb) && (env_all || Ca == 16 || Cb == 16);
 }
 
 int wgrad_direct_run(const float* a, int Ca, const float* g, int Cb, const int* tab, const int* orow, const int* rowmask,

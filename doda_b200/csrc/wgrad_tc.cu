@@ -313,8 +313,8 @@ int wgrad_tc_run(const float* a, int Ca, const float* b, int Cb, const int* pa, 
     p.Npad = (Cb + 15) / 16 * 16;
     if (p.MB * p.Npad > 512 || p.MB > 4) return B200SP_EUNSUP;
     {
-        const char* e = getenv("B200SP_WG_DEBUG");
-        p.dbg = e ? atoi(e) : 0;
+        B200SP_ENV_INT(env_dbg, "B200SP_WG_DEBUG", 0);
+        p.dbg = env_dbg;
     }
     p.magicA = p.cprA == 1 ? 0u : (uint32_t)(((1ull << 32) + p.cprA - 1) / p.cprA);
     p.magicB = p.cprB == 1 ? 0u : (uint32_t)(((1ull << 32) + p.cprB - 1) / p.cprB);
@@ -322,8 +322,8 @@ int wgrad_tc_run(const float* a, int Ca, const float* b, int Cb, const int* pa, 
     const int slots = 4;
     int PS = 128;
     {
-        const char* e = getenv("B200SP_WG_PS");  // dev knob: cap on pairs per stage
-        if (e && atoi(e) >= 16) PS = atoi(e);
+        B200SP_ENV_INT(env_ps, "B200SP_WG_PS", 0);  // dev knob: cap on pairs per stage
+        if (env_ps >= 16) PS = env_ps;
     }
     uint32_t slot = 0;
     for (; PS >= 16; PS >>= 1) {
@@ -342,8 +342,8 @@ int wgrad_tc_run(const float* a, int Ca, const float* b, int Cb, const int* pa, 
     // issuer warps: each smem slot belongs to exactly one issuer (parity waits must not run a fill ahead of a shared
     // slot), so nacc divides nslots; one accumulator set (MB x Npad columns) per issuer
     {
-        const char* e = getenv("B200SP_WG_NACC");
-        const int want = std::max(1, std::min(e ? atoi(e) : WG_MAX_ISSUERS, WG_MAX_ISSUERS));
+        B200SP_ENV_INT(env_nacc, "B200SP_WG_NACC", WG_MAX_ISSUERS);
+        const int want = std::max(1, std::min(env_nacc, WG_MAX_ISSUERS));
         p.nacc = 1;
         for (int ni = want; ni >= 1; --ni)
             if (slots % ni == 0 && ni * p.MB * p.Npad <= 512) {
@@ -359,8 +359,8 @@ int wgrad_tc_run(const float* a, int Ca, const float* b, int Cb, const int* pa, 
     // pairs per block: enough CTAs to fill the machine, few enough that the final atomics stay cheap
     int64_t ppb = 4096;
     {
-        const char* e = getenv("B200SP_WG_PPB");  // dev knob: cap on pairs per CTA
-        if (e && atoi(e) >= 256) ppb = atoi(e);
+        B200SP_ENV_INT(env_ppb, "B200SP_WG_PPB", 0);  // dev knob: cap on pairs per CTA
+        if (env_ppb >= 256) ppb = env_ppb;
     }
     while (ppb > 2 * PS && ppb > 256 && cdiv(n_upper, ppb) * K < 3 * 148) ppb >>= 1;
     if (ppb < PS) ppb = PS;

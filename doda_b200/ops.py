@@ -23,6 +23,12 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+try:  # fast-call binding of the per-layer entry points (csrc/fastcall.c); same exported functions as `lib`
+    from . import _b200fast as _fast
+except ImportError as _e:  # no silent fallback: the build makes both shared objects
+    raise ImportError("doda_b200/_b200fast.so is missing -- build it with `python -m doda_b200.build` (%s)" % _e)
+
+
 def _req_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -407,11 +413,13 @@ def gather_gemm(feat, W3, tab, n_out, out=None, accumulate=False, wflags=W_FWD, 
         ws = _workspace(_conv_ws_bytes(K, Cin, Cout), feat.device, "conv")
         wptr, wfl, wsp, wsn = W3.data_ptr(), wflags, ws.data_ptr(), ws.numel()
     if _prof is None:
-        check(lib.b200sp_gather_gemm(feat.data_ptr(), feat.shape[0], Cin, wptr, wfl,
-                                     tab.data_ptr() if tab is not None else None,
-                                     orow.data_ptr() if orow is not None else None,
-                                     rowmask.data_ptr() if rowmask is not None else None, K, out.data_ptr(), n_out, Cout,
-                                     1 if accumulate else 0, wsp, wsn, _stream()), "gather_gemm")
+        rc = _fast.gather_gemm(feat.data_ptr(), feat.shape[0], Cin, wptr, wfl,
+                               tab.data_ptr() if tab is not None else None,
+                               orow.data_ptr() if orow is not None else None,
+                               rowmask.data_ptr() if rowmask is not None else None, K, out.data_ptr(), n_out, Cout,
+                               1 if accumulate else 0, wsp, wsn, _stream())
+        if rc:
+            check(rc, "gather_gemm")
         return out
     pairs = int((tab >= 0).sum()) if tab is not None else int(n_out)  # profile pass only (host sync)
     with _Timed(kernel="k_gather_gemm", n_in=feat.shape[0], n_out=n_out, Cin=Cin, Cout=Cout, K=K,
@@ -552,10 +560,12 @@ def wgrad(a, b, pa, pb, pairnum, n_upper, K):
     Ca, Cb = a.shape[1], b.shape[1]
     dW = _dw_arena.take((K, Ca, Cb), a.device)
     if _prof is None:
-        check(lib.b200sp_wgrad(a.data_ptr(), Ca, b.data_ptr(), Cb, pa.data_ptr() if pa is not None else None,
-                               pb.data_ptr() if pb is not None else None,
-                               pairnum.data_ptr() if pairnum is not None else None, n_upper, K,
-                               pa.stride(0) if pa is not None else 0, dW.data_ptr(), _stream()), "wgrad")
+        rc = _fast.wgrad(a.data_ptr(), Ca, b.data_ptr(), Cb, pa.data_ptr() if pa is not None else None,
+                         pb.data_ptr() if pb is not None else None,
+                         pairnum.data_ptr() if pairnum is not None else None, n_upper, K,
+                         pa.stride(0) if pa is not None else 0, dW.data_ptr(), _stream())
+        if rc:
+            check(rc, "wgrad")
         return dW
     with _Timed(kernel="k_wgrad", n_rows=a.shape[0], Ca=Ca, Cb=Cb, K=K, n_upper=n_upper):
         check(lib.b200sp_wgrad(a.data_ptr(), Ca, b.data_ptr(), Cb, pa.data_ptr() if pa is not None else None,
@@ -580,6 +590,13 @@ def wgrad_table(a, g, tab, n_rows, K, orow=None, rowmask=None):
     """dW[k] = sum_r a[tab[r][k]]^T g[orow[r]]  -> [K, Ca, Cb]  (out-stationary form, shapes of _wgrad_table_covers)"""
     Ca, Cb = a.shape[1], g.shape[1]
     dW = _dw_arena.take((K, Ca, Cb), a.device)
+    if _prof is None:
+        rc = _fast.wgrad_table(a.data_ptr(), Ca, g.data_ptr(), Cb, tab.data_ptr() if tab is not None else None,
+                               orow.data_ptr() if orow is not None else None,
+                               rowmask.data_ptr() if rowmask is not None else None, n_rows, K, dW.data_ptr(), _stream())
+        if rc:
+            check(rc, "wgrad_table")
+        return dW
     with _Timed(kernel="k_wgrad", n_rows=a.shape[0], Ca=Ca, Cb=Cb, K=K, n_upper=n_rows):
         check(lib.b200sp_wgrad_table(a.data_ptr(), Ca, g.data_ptr(), Cb, tab.data_ptr() if tab is not None else None,
                                      orow.data_ptr() if orow is not None else None,
@@ -812,10 +829,22 @@ def _bn_forward_raw(x, weight, bias, running_mean, running_var, nbt, momentum, e
     y = torch.empty_like(x)
     stats = torch.empty((2, C), dtype=_F32, device=dev)
     ws = _workspace(_bn_ws_bytes(C), dev, "bn")
+    sp = stats.data_ptr()
+    if _prof is None:
+        rc = _fast.bn_fwd_train(x.data_ptr(), M, C, weight.data_ptr() if weight is not None else None,
+                                bias.data_ptr() if bias is not None else None, float(eps), 1 if relu else 0,
+                                y.data_ptr(), sp, sp + 4 * C,
+                                running_mean.data_ptr() if running_mean is not None else None,
+                                running_var.data_ptr() if running_var is not None else None,
+                                float(momentum), nbt.data_ptr() if nbt is not None else None, ws.data_ptr(),
+                                ws.numel(), _stream())
+        if rc:
+            check(rc, "bn_fwd_train")
+        return y, stats
     with _Timed(kernel="bn_fwd", M=M, C=C):
         check(lib.b200sp_bn_fwd_train(x.data_ptr(), M, C, weight.data_ptr() if weight is not None else None,
                                       bias.data_ptr() if bias is not None else None, float(eps), 1 if relu else 0,
-                                      y.data_ptr(), stats[0].data_ptr(), stats[1].data_ptr(),
+                                      y.data_ptr(), sp, sp + 4 * C,
                                       running_mean.data_ptr() if running_mean is not None else None,
                                       running_var.data_ptr() if running_var is not None else None,
                                       float(momentum), nbt.data_ptr() if nbt is not None else None, ws.data_ptr(),
@@ -829,12 +858,19 @@ def _bn_backward_raw(x, dy, weight, bias, stats, relu):
     dx = torch.empty_like(x)
     dwb = torch.empty((2, C), dtype=_F32, device=dev)
     ws = _workspace(_bn_ws_bytes(C), dev, "bn")
+    sp, gp = stats.data_ptr(), dwb.data_ptr()
+    if _prof is None:
+        rc = _fast.bn_bwd(x.data_ptr(), dy.data_ptr(), M, C, weight.data_ptr() if weight is not None else None,
+                          bias.data_ptr() if bias is not None else None, sp, sp + 4 * C, 1 if relu else 0,
+                          dx.data_ptr(), gp, gp + 4 * C, ws.data_ptr(), ws.numel(), _stream())
+        if rc:
+            check(rc, "bn_bwd")
+        return dx, dwb
     with _Timed(kernel="bn_bwd", M=M, C=C):
         check(lib.b200sp_bn_bwd(x.data_ptr(), dy.data_ptr(), M, C,
                                 weight.data_ptr() if weight is not None else None,
-                                bias.data_ptr() if bias is not None else None, stats[0].data_ptr(),
-                                stats[1].data_ptr(), 1 if relu else 0, dx.data_ptr(), dwb[0].data_ptr(),
-                                dwb[1].data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "bn_bwd")
+                                bias.data_ptr() if bias is not None else None, sp, sp + 4 * C, 1 if relu else 0,
+                                dx.data_ptr(), gp, gp + 4 * C, ws.data_ptr(), ws.numel(), _stream()), "bn_bwd")
     return dx, dwb
 
 

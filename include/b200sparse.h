@@ -147,7 +147,7 @@ int b200sp_wgrad(const float* a_dev, int Ca, const float* b_dev, int Cb, const i
                  void* stream);
 
 /* Weight gradient in TABLE form (out-stationary, wgrad_direct.cu), for the shapes _covers reports (Ca, Cb in
- * {16, 32}):  dW[k][ca][cb] += sum_r a[tab[r][k]][ca] * g[orow[r]][cb],  tab/orow/rowmask as in b200sp_gather_gemm
+ * {16, 32}, not both 32):  dW[k][ca][cb] += sum_r a[tab[r][k]][ca] * g[orow[r]][cb],  tab/orow/rowmask as in b200sp_gather_gemm
  * (SubM: nbr_perm/order/rowmask of b200sp_rulebook_subm; strided conv: bwd table, a = input, g = output gradient;
  * inverse conv: fwd table).  g is read once per row instead of once per pair.  dW must be zeroed by the caller. */
 int b200sp_wgrad_table_covers(int K, int Ca, int Cb);

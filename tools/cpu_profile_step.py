@@ -30,5 +30,5 @@ for _ in range(3): step()
 pr.disable()
 torch.cuda.synchronize()
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("cumtime").print_stats(60)
-print(s.getvalue()[:12000])
+pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(45)
+print(s.getvalue()[:14000])
