@@ -327,9 +327,10 @@ def main():
             recs = []
         gg = [r for r in recs if r["kernel"] == "k_gather_gemm"]
         if gg:
-            # dominant kernel = k_conv_tc (tcgen05 gather-GEMM, fwd + dgrad); dominant LAUNCH SHAPE = the group of
-            # identical launches with the largest total time.  achieved = algorithmic bytes of one such launch
-            # (SURVEY.md 8(d) / DESIGN.md 3) / its average CUDA-event duration (events on the launch stream).
+            # dominant kernel = the conv gather-GEMM (fwd + dgrad; k_conv_direct on the 16/32-channel layers,
+            # k_conv_tc elsewhere); dominant LAUNCH SHAPE = the group of identical launches with the largest total
+            # time.  achieved = algorithmic bytes of one such launch (SURVEY.md 8(d) / DESIGN.md 3) / its average
+            # CUDA-event duration (events on the launch stream).
             groups = {}
             for r in gg:
                 groups.setdefault((r["n_out"], r["Cin"], r["Cout"], r["K"], r.get("pairs_mode", 0)), []).append(r)
@@ -343,12 +344,13 @@ def main():
             peak, how = peaks()
             ach = g_bytes / (g_ms * 1e-3) / 1e9
             traffic = None
+            kname = "k_conv_direct" if (not key[4] and ops._direct_covers(key[3], key[1], key[2])) else "k_conv_tc"
             tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from `ncu --set full`
             if os.path.exists(tpath):
-                for t in json.load(open(tpath)).get("k_conv_tc", []):
+                for t in json.load(open(tpath)).get(kname, []):
                     if (t["Cin"], t["Cout"], t["K"]) == key[1:4] and abs(t["n_out"] - key[0]) <= 0.1 * key[0]:
                         traffic = t["dram_bytes"]
-            roof = {"bound": "hbm", "kernel": "k_conv_tc", "achieved": ach, "peak": peak, "unit": "GB/s",
+            roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": traffic, "peak_source": how,
                     "launch_shape": {"rows": key[0], "Cin": key[1], "Cout": key[2], "K": key[3], "pairs_mode": key[4],
                                      "launches_per_step": len(grp), "avg_launch_ms": g_ms,

@@ -19,6 +19,9 @@ g = torch.randn(n, Cout, device=dev)
 ops.set_conv_impl(impl)
 for _ in range(reps):
     out = ops.gather_gemm(feat, W3, rb.nbr_perm, n, orow=rb.order, rowmask=rb.rowmask)
+    din = ops.gather_gemm(g, W3, rb.nbr_perm, n, wflags=ops.W_T_MIRROR, orow=rb.order, rowmask=rb.rowmask)
     dW = ops.wgrad(feat, g, rb.pairs[0], rb.pairs[1], rb.pairnum, n, 27)
+    if ops._wgrad_table_covers(27, Cin, Cout):
+        dW = ops.wgrad_table(feat, g, rb.nbr_perm, n, 27, orow=rb.order, rowmask=rb.rowmask)
 torch.cuda.synchronize()
 print("done", out.shape, dW.shape)
