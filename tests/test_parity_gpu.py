@@ -242,6 +242,57 @@ def test_prepared_weight_images_follow_updates(cuda_dev):
     assert ops.prepared_weights(conv) is not None
 
 
+def _encoder_decoder(planes, with_bn):
+    """BASELINE configs[3]: the k2 s2 SparseConv3d / SparseInverseConv3d encoder-decoder of UBlock
+    (model/unet_block.py:67-79) without the SubM blocks: 6 down + 6 up"""
+    from doda_b200 import spconv
+    mods = []
+    for l in range(len(planes) - 1):
+        if with_bn:
+            mods += [torch.nn.BatchNorm1d(planes[l], eps=1e-4, momentum=0.1), torch.nn.ReLU()]
+        mods.append(spconv.SparseConv3d(planes[l], planes[l + 1], 2, stride=2, bias=False, indice_key="spconv%d" % l))
+    for l in reversed(range(len(planes) - 1)):
+        if with_bn:
+            mods += [torch.nn.BatchNorm1d(planes[l + 1], eps=1e-4, momentum=0.1), torch.nn.ReLU()]
+        mods.append(spconv.SparseInverseConv3d(planes[l + 1], planes[l], 2, bias=False, indice_key="spconv%d" % l))
+    return spconv.SparseSequential(*mods)
+
+
+def test_cfg4_encoder_decoder_400k(cuda_dev):
+    """BASELINE configs[3] size (one 400 k-voxel scene, stride-2 encoder-decoder, 1 x B200), properties that need no CPU
+    oracle: the inverse convs restore the input's active set; the net without BN is linear in x and in each layer's
+    weight, so <g, y> = <dL/dx, x> = <dL/dW_l, W_l> for every layer (forward, dgrad and wgrad of the strided and the
+    inverse conv are mutually adjoint, table-form and pair-list kernels alike); with BN+ReLU it runs and is finite."""
+    from doda_b200 import spconv
+    torch.manual_seed(5)
+    coords, shape = surface_coords(7, 400000, 1)
+    c = torch.from_numpy(coords).to(cuda_dev)
+    n = c.shape[0]
+    assert n == 400000
+    planes = [16 * i for i in range(1, 8)]
+    net = _encoder_decoder(planes, with_bn=False).to(cuda_dev)
+    x = torch.randn(n, planes[0], device=cuda_dev, requires_grad=True)
+    t = spconv.SparseConvTensor(x, c, shape, 1)
+    y = net(t)
+    assert y.indices is c or torch.equal(y.indices, c)
+    assert y.features.shape == (n, planes[0])
+    levels = [t.indice_dict["spconv%d" % l].outids.shape[0] for l in range(6)]
+    assert all(a > b > 0 for a, b in zip([n] + levels, levels))  # each level strictly coarser, none empty
+    g = torch.randn_like(y.features)
+    s = (g * y.features).sum()
+    s.backward()
+    ref = float(s.detach())
+    assert abs(float((x.grad * x.detach()).sum()) - ref) <= 2e-4 * abs(ref)
+    for name, p in net.named_parameters():
+        assert abs(float((p.grad * p.detach()).sum()) - ref) <= 2e-4 * abs(ref), name
+    net_bn = _encoder_decoder(planes, with_bn=True).to(cuda_dev).train()
+    xb = torch.randn(n, planes[0], device=cuda_dev, requires_grad=True)
+    yb = net_bn(spconv.SparseConvTensor(xb, c, shape, 1))
+    yb.features.square().mean().backward()
+    assert torch.isfinite(yb.features).all() and torch.isfinite(xb.grad).all()
+    assert all(torch.isfinite(p.grad).all() for p in net_bn.parameters())
+
+
 def test_full_size_adjoint_and_linearity(cuda_dev):
     """BASELINE configs[1] size (2 x 150 k voxels): properties that need no CPU oracle.
     <g, conv(x)> = <dgrad(g), x> = <W, wgrad(x, g)> (the three kernels are mutually adjoint), linearity in x, and
