@@ -40,6 +40,7 @@ def parse():
     ap.add_argument("--voxels", type=int, default=150000)
     ap.add_argument("--bs", type=int, default=2, help="scenes per GPU")
     ap.add_argument("--mid", type=int, default=16, help="MODEL.BACKBONE.mid_channel (16 as shipped)")
+    ap.add_argument("--ddp", action="store_true", help="N>1: torch DistributedDataParallel instead of parallel.allreduce_grads")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--detail", default="", help="write per-kernel detail JSON here")
@@ -217,7 +218,7 @@ def main():
     batch = make_batch(rank, args.bs, args.voxels)
     model = SparseConvNet(mid_channel=args.mid).to(dev).train()
     net = model
-    if world > 1:
+    if world > 1 and args.ddp:  # A/B: torch's DistributedDataParallel instead of the engine's in-place gradient mean
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
     criterion = None  # model_step's default: the engine's one-pass cross-entropy (ignore_index=255, mean)
     tensor_keys = ["voxel_locs", "p2v_map", "v2p_map", "feats", "labels"]
@@ -232,6 +233,7 @@ def main():
 
     params = [p for p in model.parameters()]
     from doda_b200 import ops as _engine_ops
+    from doda_b200 import parallel
 
     def step(b):
         for p in params:  # what optimizer.zero_grad(set_to_none=True) does
@@ -241,6 +243,8 @@ def main():
         _engine_ops.invalidate_prepared_weights()
         loss, _ = model_step(net, b, criterion=criterion, device=dev)
         loss.backward()
+        if world > 1 and not args.ddp:
+            parallel.allreduce_grads(params, world)  # the path's only collective: gradient mean over ranks (NCCL)
         return loss
 
     def barrier():
@@ -380,8 +384,8 @@ def main():
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": "2x150k-voxel ScanNet-shape scenes, full SparseConvNet fwd+bwd, bs=%d, m=%d"
                           % (args.bs, args.mid), "voxels_per_scene": args.voxels, "scenes_per_gpu": args.bs,
-                          "mid_channel": args.mid, "parallelism": "dp%d (whole scenes per rank, DDP grad all-reduce)"
-                          % world, "l2": "256 MB flush between timed steps",
+                          "mid_channel": args.mid, "parallelism": "dp%d (whole scenes per rank, %s)"
+                          % (world, "DDP grad all-reduce" if args.ddp else "one in-place NCCL gradient mean after backward"), "l2": "256 MB flush between timed steps",
                           "settle": "%d further untimed steps through the timing harness before each timed loop"
                           % SETTLE},
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

@@ -115,6 +115,24 @@ for p in params[:2]:
 parallel.allreduce_grads(params, world)
 assert all(torch.allclose(p.grad, r, atol=1e-6) for p, r in zip(params[:2], ref))
 assert params[2].grad is None
+# gradients that are slices of one big zero-filled block (how the engine hands out conv weight gradients): reduced
+# in place over the span they cover, one collective, neighbours in the block untouched
+block = torch.zeros(1 << 19)  # 2 MB
+big = [torch.nn.Parameter(torch.zeros(27, 16, 16)), torch.nn.Parameter(torch.zeros(8, 16, 32)), torch.nn.Parameter(torch.zeros(3))]
+off = 1024
+for p in big[:2]:
+    p.grad = block[off:off + p.numel()].view_as(p)
+    p.grad.copy_(torch.randn_like(p))
+    off += (p.numel() + 63) // 64 * 64
+big[2].grad = torch.randn(3)
+sentinel = block[off + 64:off + 128].fill_(7.0)
+ref = []
+for p in big:
+    g = p.grad.clone(); dist.all_reduce(g); ref.append(g / world)
+parallel.allreduce_grads(big, world)
+assert all(torch.allclose(p.grad, r, atol=1e-6) for p, r in zip(big, ref))
+assert big[0].grad.untyped_storage().data_ptr() == block.untyped_storage().data_ptr()  # still the arena slice
+assert bool((sentinel == 7.0).all()) and float(block[:1024].abs().sum()) == 0.0
 # max-over-ranks timing reduction
 t = parallel.max_over_ranks(float(rank + 1), torch.device("cpu"))
 assert t == float(world)
