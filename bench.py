@@ -55,67 +55,48 @@ def peaks():
     return 6650.0, "fallback"
 
 
-class ClockSampler(threading.Thread):
+class ClockSampler(object):
     """SM clock / throttle-reason samples during the timed region (B200_PROFILING.md recipe), taken in-process
-    through NVML (nvidia_ml_py).  An `nvidia-smi -lms` subprocess was used first: its queries stalled the CUDA
-    process for 40-100 ms at a time (visible as outlier steps); it remains the fallback when NVML is unavailable."""
+    through NVML (nvidia_ml_py; a one-shot `nvidia-smi` query is the fallback).
 
-    def __init__(self, index, period=1.0):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt, self.proc, self.period = index, [], threading.Event(), None, period
-        self._kick = threading.Event()
+    An NVML query holds a driver lock: CUDA launches of this process stall for 10-110 ms while it runs (first seen
+    with an `nvidia-smi -lms` subprocess, then with a sampling thread: one or two outlier steps per timed loop).
+    So there is no polling: the timed loops call sample() once, at their middle step, BETWEEN two steps (where the L2
+    flush already sits, outside the per-step event intervals) while the GPU is still executing the steps queued
+    before it -- the clocks are read under load, and the query's stall is not booked on a step."""
 
-    def kick(self):
-        """take a sample now (the timed loops call this at their middle step: an NVML query holds a driver lock for
-        several ms and delays the launches of the step it lands in, so the sampler is kept to one query per timed
-        loop plus a slow periodic one instead of a fast poll)"""
-        self._kick.set()
-
-    def _run_nvml(self):
-        import pynvml as nv
-        nv.nvmlInit()
-        h = nv.nvmlDeviceGetHandleByIndex(self.index)
-        mx = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
-        bits = [("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8))),
-                ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40))),
-                ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20))),
-                ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))]
-        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
-        while not self._stop_evt.is_set():
-            sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-            r = int(get_reasons(h))
-            self.rows.append([str(sm), str(mx)] + ["Active" if r & b else "Not Active" for _, b in bits])
-            self._kick.wait(self.period)
-            self._kick.clear()
-
-    def _run_smi(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits", "-lms", "500"],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-            if self._stop_evt.is_set():
-                break
-
-    def run(self):
+    def __init__(self, index):
+        self.index, self.rows, self.nv, self.h, self.mx = index, [], None, None, None
         try:
-            self._run_nvml()
+            import pynvml as nv
+            nv.nvmlInit()
+            self.h = nv.nvmlDeviceGetHandleByIndex(index)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.bits = [("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8))),
+                         ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40))),
+                         ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20))),
+                         ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))]
+            self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.nv = nv
         except Exception:
-            try:
-                self._run_smi()
-            except Exception:
-                pass
+            self.nv = None
 
-    def stop(self):
-        self._stop_evt.set()
-        self._kick.set()
-        if self.proc is not None:
-            try:
-                self.proc.terminate()
-            except Exception:
-                pass
+    def sample(self):
+        try:
+            if self.nv is not None:
+                sm = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                r = int(self.get_reasons(self.h))
+                self.rows.append([str(sm), str(self.mx)] + ["Active" if r & b else "Not Active" for _, b in self.bits])
+            else:
+                q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                     "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=20).stdout
+                for line in out.splitlines():
+                    if line.strip():
+                        self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
 
     def summary(self):
         sm, mx, reasons = [], [], set()
@@ -230,6 +211,16 @@ def main():
         resident[k] = batch[k].to(dev)
     h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in tensor_keys)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    # grow the caching allocator's pool once (the step's live set is ~2 GB, more with the host a step ahead): a
+    # cudaMalloc inside a timed step is a 20-100 ms stall; the JSON line reports how many happened anyway
+    # (the caching allocator keeps one pool per stream: rulebook tensors live in the index stream's pool and, being
+    # handed to the main stream, are only reusable once the GPU has finished the step that used them)
+    grow = [torch.empty(1 << 30, dtype=torch.uint8, device=dev) for _ in range(6)]
+    grow += [torch.empty(1 << 20, dtype=torch.uint8, device=dev) for _ in range(256)]  # small pool (<= 1 MB requests)
+    with torch.cuda.stream(ops.index_stream_for(dev)):
+        grow += [torch.empty(1 << 30, dtype=torch.uint8, device=dev) for _ in range(4)]
+        grow += [torch.empty(1 << 20, dtype=torch.uint8, device=dev) for _ in range(128)]
+    del grow
 
     params = [p for p in model.parameters()]
     from doda_b200 import ops as _engine_ops
@@ -261,15 +252,17 @@ def main():
         the host is not parked on the GPU once per step (a training loop that logs its loss one step late)."""
         import gc
         evs, copied = [], []
+        st0 = torch.cuda.memory_stats(dev)
+        mallocs0 = st0.get("num_device_alloc", 0)
         gc.collect()
         gc.disable()  # a gen-2 collection inside the loop shows up as a 50-100 ms outlier step
         barrier()
         for i in range(nsteps):
             flush.zero_()  # L2 flush between timed iterations (not timed)
+            if sampler is not None and i == nsteps // 2:
+                sampler.sample()  # between two steps, GPU busy with the steps queued so far (see ClockSampler)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            if sampler is not None and i == nsteps // 2:
-                sampler.kick()
             loss = step(b)
             if read_loss:
                 loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)  # device -> host, every step
@@ -286,17 +279,20 @@ def main():
         gc.enable()
         per_step = [s.elapsed_time(e) for s, e in evs]
         timed.last_steps = per_step
+        st1 = torch.cuda.memory_stats(dev)
+        timed.last_mallocs = st1.get("num_device_alloc", 0) - mallocs0
+        if rank == 0 and timed.last_mallocs:
+            sys.stderr.write("[bench] cudaMalloc in timed loop: %s\n" % {k: st1[k] - st0.get(k, 0) for k in (
+                "segment.small_pool.allocated", "segment.large_pool.allocated", "reserved_bytes.all.allocated",
+                "reserved_bytes.small_pool.allocated", "reserved_bytes.large_pool.allocated") if k in st1})
         tot = sum(per_step)
         t = torch.tensor([tot], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # the clock sampler is an nvidia-smi subprocess: its start-up (fork + NVML init) stalls driver calls for up to a
-    # second, so it is started BEFORE the warm-up and must have delivered a sample before anything is timed
+    # NVML is initialised BEFORE the warm-up (its start-up stalls driver calls for up to a second)
     sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
     for _ in range(max(args.warmup, 3)):
         step(resident)
     # untimed passes through the timing harness itself: with the host running ahead of the GPU the caching allocator
@@ -304,17 +300,13 @@ def main():
     timed(resident, SETTLE, False)
     timed(host, SETTLE, True)
     if sampler:
-        t_wait = time.time()
-        while not sampler.rows and time.time() - t_wait < 10.0:
-            time.sleep(0.05)
         sampler.rows.clear()  # keep only samples taken during the timed regions
     calls0 = ops.launch_count()
     ms_total = timed(resident, args.steps, False)
     steps_ms = [round(v, 3) for v in timed.last_steps]
+    mallocs = timed.last_mallocs
     launches = ops.launch_count() - calls0
     ms_e2e = timed(host, args.steps, True)
-    if sampler:
-        sampler.stop()
     scenes_per_step = args.bs * world
     value = scenes_per_step * args.steps / (ms_total / 1e3)
     e2e_val = scenes_per_step * args.steps / (ms_e2e / 1e3)
@@ -394,7 +386,7 @@ def main():
                                     "during step i and the last one before the closing sync (all K inside the timed "
                                     "region)"},
                "gpu_launches": launches, "clocks": sampler.summary() if sampler else None,
-               "step_ms_rank0": steps_ms}
+               "step_ms_rank0": steps_ms, "cuda_mallocs_in_timed_steps": mallocs}
         if roof:
             out["roofline"] = roof
         if cpu_base:

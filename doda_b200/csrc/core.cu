@@ -56,6 +56,29 @@ extern "C" const char* b200sp_last_error(void) { return g_err; }
 extern "C" int b200sp_version(void) { return 100; }
 extern "C" int64_t b200sp_launch_count(void) { return (int64_t)b200sp::get_launches(); }
 
+// Fork / join of a side stream around independent kernels of one layer (the weight gradient next to dgrad + BN
+// backward): side waits for everything queued on main so far / main waits for everything queued on side so far.
+// The event handle belongs to the caller (one per direction is enough: a wait captures the record it follows).
+extern "C" int b200sp_event_create(void** event_out) {
+    B200SP_CHECK_ARG(event_out, "event_create: null");
+    cudaEvent_t ev;
+    B200SP_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    *event_out = (void*)ev;
+    return B200SP_OK;
+}
+extern "C" int b200sp_stream_fork(void* main_stream, void* side_stream, void* event) {
+    B200SP_CHECK_ARG(event, "stream_fork: null event");
+    B200SP_CUDA(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)main_stream));
+    B200SP_CUDA(cudaStreamWaitEvent((cudaStream_t)side_stream, (cudaEvent_t)event, 0));
+    return B200SP_OK;
+}
+extern "C" int b200sp_stream_join(void* main_stream, void* side_stream, void* event) {
+    B200SP_CHECK_ARG(event, "stream_join: null event");
+    B200SP_CUDA(cudaEventRecord((cudaEvent_t)event, (cudaStream_t)side_stream));
+    B200SP_CUDA(cudaStreamWaitEvent((cudaStream_t)main_stream, (cudaEvent_t)event, 0));
+    return B200SP_OK;
+}
+
 // Semantics follow lib/pointgroup_ops/src/voxelize/voxelize.cpp:62-155 (first-touch voxel ids while scanning
 // points in order; per-batch maps; output_map rows = [count, pt..., -1 pad]; coords of the first point) and
 // voxelize_outputmap 35-52.  Modes: 0 unique, 1 first point, 2 last point, 3 sum, 4 mean (the code, not the

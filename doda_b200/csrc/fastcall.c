@@ -80,7 +80,21 @@ static PyObject* f_bn_bwd(PyObject* self, PyObject* const* a, Py_ssize_t nargs) 
     CHECKED(b200sp_bn_bwd(x, dy, M, C, w, b, mean, invstd, relu, dx, dw, db, ws, ws_bytes, stream))
 }
 
+/* b200sp_stream_fork / b200sp_stream_join (main_stream, side_stream, event) */
+static PyObject* f_fork(PyObject* self, PyObject* const* a, Py_ssize_t nargs) {
+    NARGS(3)
+    void* m = P(a[0]); void* s = P(a[1]); void* e = P(a[2]);
+    CHECKED(b200sp_stream_fork(m, s, e))
+}
+static PyObject* f_join(PyObject* self, PyObject* const* a, Py_ssize_t nargs) {
+    NARGS(3)
+    void* m = P(a[0]); void* s = P(a[1]); void* e = P(a[2]);
+    CHECKED(b200sp_stream_join(m, s, e))
+}
+
 static PyMethodDef methods[] = {
+    {"fork", (PyCFunction)(void (*)(void))f_fork, METH_FASTCALL, "b200sp_stream_fork"},
+    {"join", (PyCFunction)(void (*)(void))f_join, METH_FASTCALL, "b200sp_stream_join"},
     {"gather_gemm", (PyCFunction)(void (*)(void))f_gather_gemm, METH_FASTCALL, "b200sp_gather_gemm"},
     {"gather_gemm_pairs", (PyCFunction)(void (*)(void))f_gather_gemm_pairs, METH_FASTCALL, "b200sp_gather_gemm_pairs"},
     {"wgrad", (PyCFunction)(void (*)(void))f_wgrad, METH_FASTCALL, "b200sp_wgrad"},

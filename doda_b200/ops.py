@@ -4,6 +4,8 @@ and the autograd functions of `spconv.functional`.
 
 No CPU path: every function requires CUDA tensors and raises otherwise.
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -213,6 +215,16 @@ def build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding=
     main.wait_event(ev)
     rb.outids._b200sp_idx_stream = True
     return rb
+
+
+def index_stream_for(device):
+    """the engine's index stream on `device` (created on first use)"""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    side = _idx_streams.get(idx)
+    if side is None:
+        side = _idx_streams[idx] = torch.cuda.Stream(torch.device("cuda", idx))
+    return side
 
 
 def stage_coords(voxel_locs, device, pending=False):
@@ -555,15 +567,19 @@ class _ZeroArena(object):
 _dw_arena = _ZeroArena()
 
 
-def wgrad(a, b, pa, pb, pairnum, n_upper, K):
-    """dW[k] = sum_i a[pa[k][i]]^T b[pb[k][i]]  -> [K, Ca, Cb]"""
+_wg_stream = None  # raw handle of the side stream the weight gradient is launched on while a backward node has forked
+
+
+def wgrad(a, b, pa, pb, pairnum, n_upper, K, out=None):
+    """dW[k] = sum_i a[pa[k][i]]^T b[pb[k][i]]  -> [K, Ca, Cb] (accumulated into `out`, which must be zero-filled)"""
     Ca, Cb = a.shape[1], b.shape[1]
-    dW = _dw_arena.take((K, Ca, Cb), a.device)
+    dW = out if out is not None else _dw_arena.take((K, Ca, Cb), a.device)
     if _prof is None:
         rc = _fast.wgrad(a.data_ptr(), Ca, b.data_ptr(), Cb, pa.data_ptr() if pa is not None else None,
                          pb.data_ptr() if pb is not None else None,
                          pairnum.data_ptr() if pairnum is not None else None, n_upper, K,
-                         pa.stride(0) if pa is not None else 0, dW.data_ptr(), _stream())
+                         pa.stride(0) if pa is not None else 0, dW.data_ptr(),
+                         _wg_stream if _wg_stream is not None else _stream())
         if rc:
             check(rc, "wgrad")
         return dW
@@ -586,14 +602,15 @@ def _wgrad_table_covers(K, Ca, Cb):
     return v
 
 
-def wgrad_table(a, g, tab, n_rows, K, orow=None, rowmask=None):
+def wgrad_table(a, g, tab, n_rows, K, orow=None, rowmask=None, out=None):
     """dW[k] = sum_r a[tab[r][k]]^T g[orow[r]]  -> [K, Ca, Cb]  (out-stationary form, shapes of _wgrad_table_covers)"""
     Ca, Cb = a.shape[1], g.shape[1]
-    dW = _dw_arena.take((K, Ca, Cb), a.device)
+    dW = out if out is not None else _dw_arena.take((K, Ca, Cb), a.device)
     if _prof is None:
         rc = _fast.wgrad_table(a.data_ptr(), Ca, g.data_ptr(), Cb, tab.data_ptr() if tab is not None else None,
                                orow.data_ptr() if orow is not None else None,
-                               rowmask.data_ptr() if rowmask is not None else None, n_rows, K, dW.data_ptr(), _stream())
+                               rowmask.data_ptr() if rowmask is not None else None, n_rows, K, dW.data_ptr(),
+                               _wg_stream if _wg_stream is not None else _stream())
         if rc:
             check(rc, "wgrad_table")
         return dW
@@ -620,124 +637,77 @@ def _w3(filters):
     return f.view(-1, Cin, Cout)
 
 
-class SubMConvFunction(Function):
+class _ConvFunctionBase(Function):
+    """forward / backward of one sparse conv through conv_forward_raw / conv_backward_raw (one dispatch for every
+    kernel choice: register-gather vs tcgen05, table vs pair lists, side-stream wgrad)"""
+    KIND = None
+
+    @classmethod
+    def _fwd(cls, ctx, features, filters, rb, prep):
+        _req_cuda(features, filters)
+        features = _f32c(features)
+        ctx.rb, ctx.prep = rb, prep
+        ctx.save_for_backward(features, filters)
+        return conv_forward_raw(cls.KIND, features, filters, rb, prep)
+
+    @classmethod
+    def _bwd(cls, ctx, grad_out):
+        features, filters = ctx.saved_tensors
+        grad_out = _f32c(grad_out)  # the llijiang fork's `.contiguous()` (docs/INSTALL.md:25)
+        return conv_backward_raw(cls.KIND, features, filters, grad_out, ctx.rb, ctx.prep, ctx.needs_input_grad[0],
+                                 ctx.needs_input_grad[1])
+
+
+class SubMConvFunction(_ConvFunctionBase):
     """spconv.functional.indice_subm_conv: out[q] = sum_k W[k] . in[q + k - centre] on the input's own sites."""
+    KIND = "subm"
 
     @staticmethod
     def forward(ctx, features, filters, rb, prep=None):
-        _req_cuda(features, filters)
-        features = _f32c(features)
-        W3 = _w3(filters)
-        ctx.rb, ctx.prep = rb, prep
-        ctx.save_for_backward(features, filters)
-        tab, orow = (rb.nbr_perm, rb.order) if rb.nbr_perm is not None else (rb.nbr, None)
-        return gather_gemm(features, W3, tab, features.shape[0], orow=orow, wimg=prep[0] if prep else None,
-                           rowmask=rb.rowmask if rb.nbr_perm is not None else None)
+        return SubMConvFunction._fwd(ctx, features, filters, rb, prep)
 
     @staticmethod
     def backward(ctx, grad_out):
-        features, filters = ctx.saved_tensors
-        rb = ctx.rb
-        grad_out = _f32c(grad_out)  # the llijiang fork's `.contiguous()` (docs/INSTALL.md:25)
-        W3 = _w3(filters)
-        M = features.shape[0]
-        din = dW = None
-        if ctx.needs_input_grad[0]:
-            tab, orow = (rb.nbr_perm, rb.order) if rb.nbr_perm is not None else (rb.nbr, None)
-            din = gather_gemm(grad_out, W3, tab, M, wflags=W_T_MIRROR, orow=orow,
-                              wimg=ctx.prep[1] if ctx.prep else None,
-                              rowmask=rb.rowmask if rb.nbr_perm is not None else None)
-        if ctx.needs_input_grad[1]:
-            dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K).view(filters.shape)
-        return din, dW, None, None
+        return SubMConvFunction._bwd(ctx, grad_out) + (None, None)
 
 
-class DenseConvFunction(Function):
+class DenseConvFunction(_ConvFunctionBase):
     """kernel_size == 1: features @ W.view(Cin, Cout) (spconv SparseConvolution.forward)."""
+    KIND = "dense"
 
     @staticmethod
     def forward(ctx, features, filters, prep=None):
-        _req_cuda(features, filters)
-        features = _f32c(features)
-        ctx.prep = prep
-        ctx.save_for_backward(features, filters)
-        return gather_gemm(features, _w3(filters), None, features.shape[0], wimg=prep[0] if prep else None)
+        return DenseConvFunction._fwd(ctx, features, filters, None, prep)
 
     @staticmethod
     def backward(ctx, grad_out):
-        features, filters = ctx.saved_tensors
-        grad_out = _f32c(grad_out)
-        W3 = _w3(filters)
-        M = features.shape[0]
-        din = dW = None
-        if ctx.needs_input_grad[0]:
-            din = gather_gemm(grad_out, W3, None, M, wflags=W_T, wimg=ctx.prep[1] if ctx.prep else None)
-        if ctx.needs_input_grad[1]:
-            dW = wgrad(features, grad_out, None, None, None, M, 1).view(filters.shape)
-        return din, dW, None
+        return DenseConvFunction._bwd(ctx, grad_out) + (None,)
 
 
-class SparseConvFunction(Function):
+class SparseConvFunction(_ConvFunctionBase):
     """spconv.functional.indice_conv (regular / strided sparse conv)."""
+    KIND = "conv"
 
     @staticmethod
     def forward(ctx, features, filters, rb, prep=None):
-        _req_cuda(features, filters)
-        features = _f32c(features)
-        ctx.rb, ctx.prep = rb, prep
-        ctx.save_for_backward(features, filters)
-        return gather_gemm(features, _w3(filters), rb.bwd, rb.outids.shape[0], wimg=prep[0] if prep else None)
+        return SparseConvFunction._fwd(ctx, features, filters, rb, prep)
 
     @staticmethod
     def backward(ctx, grad_out):
-        features, filters = ctx.saved_tensors
-        rb = ctx.rb
-        grad_out = _f32c(grad_out)
-        W3 = _w3(filters)
-        M_in = features.shape[0]
-        din = dW = None
-        if ctx.needs_input_grad[0]:
-            wb = ctx.prep[1] if ctx.prep else None
-            if rb.nonoverlap:  # every input has at most one (output, offset): pair-grouped, no accumulation
-                din = gather_gemm_pairs(grad_out, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, M_in, M_in, wflags=W_T,
-                                        wimg=wb)
-            else:
-                din = gather_gemm(grad_out, W3, rb.fwd, M_in, wflags=W_T, wimg=wb)
-        if ctx.needs_input_grad[1]:
-            dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M_in, rb.K).view(filters.shape)
-        return din, dW, None, None
+        return SparseConvFunction._bwd(ctx, grad_out) + (None, None)
 
 
-class SparseInverseConvFunction(Function):
+class SparseInverseConvFunction(_ConvFunctionBase):
     """spconv.functional.indice_inverse_conv: reuses the strided conv's rulebook with roles swapped."""
+    KIND = "inverse"
 
     @staticmethod
     def forward(ctx, features, filters, rb, prep=None):
-        _req_cuda(features, filters)
-        features = _f32c(features)
-        ctx.rb, ctx.prep = rb, prep
-        ctx.save_for_backward(features, filters)
-        W3 = _w3(filters)
-        n_fine = rb.indices.shape[0]
-        wf = prep[0] if prep else None
-        if rb.nonoverlap:
-            return gather_gemm_pairs(features, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, n_fine, wimg=wf)
-        return gather_gemm(features, W3, rb.fwd, n_fine, wimg=wf)
+        return SparseInverseConvFunction._fwd(ctx, features, filters, rb, prep)
 
     @staticmethod
     def backward(ctx, grad_out):
-        features, filters = ctx.saved_tensors
-        rb = ctx.rb
-        grad_out = _f32c(grad_out)
-        W3 = _w3(filters)
-        n_fine = rb.indices.shape[0]
-        din = dW = None
-        if ctx.needs_input_grad[0]:
-            din = gather_gemm(grad_out, W3, rb.bwd, features.shape[0], wflags=W_T,
-                              wimg=ctx.prep[1] if ctx.prep else None)
-        if ctx.needs_input_grad[1]:
-            dW = wgrad(features, grad_out, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, rb.K).view(filters.shape)
-        return din, dW, None, None
+        return SparseInverseConvFunction._bwd(ctx, grad_out) + (None, None)
 
 
 _direct_cache = {}
@@ -774,52 +744,107 @@ def conv_forward_raw(kind, features, filters, rb, prep):
     return gather_gemm(features, W3, rb.fwd, n_fine, wimg=wf)
 
 
-def conv_backward_raw(kind, features, filters, grad_out, rb, prep, need_din=True, need_dw=True):
-    """-> (din, dW) of one sparse conv"""
+# The weight gradient of a layer is independent of its dgrad and BN backward, and most of these kernels are latency-
+# bound (deep levels: a few CTAs) -- the backward node forks a side stream for the wgrad kernel and joins it before it
+# returns, so everything autograd / DDP does with dW afterwards is ordered as before.
+async_wgrad = os.environ.get("B200SP_ASYNC_WGRAD", "1") != "0"
+_wg_side = {}        # device index -> (torch side stream, its raw handle, fork event, join event)
+_pending_join = None
+
+
+def _fork_side(dev):
+    st = _wg_side.get(dev.index)
+    if st is None:
+        import ctypes
+        side = torch.cuda.Stream(dev)
+        evs = []
+        for _ in range(2):
+            h = ctypes.c_void_p()
+            check(lib.b200sp_event_create(ctypes.byref(h)), "event_create")
+            evs.append(h.value)
+        st = _wg_side[dev.index] = (side, side.cuda_stream, evs[0], evs[1])
+    main = _stream()
+    rc = _fast.fork(main, st[1], st[2])
+    if rc:
+        check(rc, "stream_fork")
+    return (main, st[1], st[3])
+
+
+def _join_side(fk):
+    rc = _fast.join(fk[0], fk[1], fk[2])
+    if rc:
+        check(rc, "stream_join")
+
+
+def join_pending_wgrad():
+    """main stream waits for the weight-gradient kernel a conv_backward_raw(defer_join=True) left on the side stream"""
+    global _pending_join
+    if _pending_join is not None:
+        _join_side(_pending_join)
+        _pending_join = None
+
+
+def _conv_wgrad(kind, features, grad_out, rb, out):
+    M = features.shape[0]
+    Ca, Cb = features.shape[1], grad_out.shape[1]
+    if kind == "subm":
+        if rb.nbr_perm is not None and _wgrad_table_covers(rb.K, Ca, Cb):
+            return wgrad_table(features, grad_out, rb.nbr_perm, M, rb.K, orow=rb.order, rowmask=rb.rowmask, out=out)
+        return wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K, out=out)
+    if kind == "dense":
+        if _wgrad_table_covers(1, Ca, Cb):
+            return wgrad_table(features, grad_out, None, M, 1, out=out)
+        return wgrad(features, grad_out, None, None, None, M, 1, out=out)
+    if kind == "conv":
+        if _wgrad_table_covers(rb.K, Ca, Cb):
+            return wgrad_table(features, grad_out, rb.bwd, grad_out.shape[0], rb.K, out=out)
+        return wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K, out=out)
+    n_fine = rb.indices.shape[0]  # inverse
+    if _wgrad_table_covers(rb.K, Ca, Cb):
+        return wgrad_table(features, grad_out, rb.fwd, n_fine, rb.K, out=out)
+    return wgrad(features, grad_out, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, rb.K, out=out)
+
+
+def _conv_dgrad(kind, W3, grad_out, rb, wb, M):
+    if kind == "subm":
+        if rb.nbr_perm is not None:
+            return gather_gemm(grad_out, W3, rb.nbr_perm, M, wflags=W_T_MIRROR, orow=rb.order, wimg=wb, rowmask=rb.rowmask)
+        return gather_gemm(grad_out, W3, rb.nbr, M, wflags=W_T_MIRROR, wimg=wb)
+    if kind == "dense":
+        return gather_gemm(grad_out, W3, None, M, wflags=W_T, wimg=wb)
+    if kind == "conv":
+        if rb.nonoverlap and not _direct_covers(W3.shape[0], W3.shape[2], W3.shape[1]):
+            return gather_gemm_pairs(grad_out, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, M, M, wflags=W_T, wimg=wb)
+        return gather_gemm(grad_out, W3, rb.fwd, M, wflags=W_T, wimg=wb)
+    return gather_gemm(grad_out, W3, rb.bwd, M, wflags=W_T, wimg=wb)  # inverse
+
+
+def conv_backward_raw(kind, features, filters, grad_out, rb, prep, need_din=True, need_dw=True, defer_join=False):
+    """-> (din, dW) of one sparse conv.  With both requested the weight gradient runs on a side stream next to dgrad;
+    the streams are joined before returning, or by the caller's join_pending_wgrad() when defer_join is set (the fused
+    BN node joins after it has queued its BN backward too)."""
+    global _wg_stream, _pending_join
     W3 = _w3(filters)
     wb = prep[1] if prep else None
     M = features.shape[0]
     din = dW = None
-    if kind == "subm":
-        if need_din:
-            if rb.nbr_perm is not None:
-                din = gather_gemm(grad_out, W3, rb.nbr_perm, M, wflags=W_T_MIRROR, orow=rb.order, wimg=wb,
-                                  rowmask=rb.rowmask)
-            else:
-                din = gather_gemm(grad_out, W3, rb.nbr, M, wflags=W_T_MIRROR, wimg=wb)
-        if need_dw:
-            if rb.nbr_perm is not None and _wgrad_table_covers(rb.K, features.shape[1], grad_out.shape[1]):
-                dW = wgrad_table(features, grad_out, rb.nbr_perm, M, rb.K, orow=rb.order, rowmask=rb.rowmask)
-            else:
-                dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K)
-    elif kind == "dense":
-        if need_din:
-            din = gather_gemm(grad_out, W3, None, M, wflags=W_T, wimg=wb)
-        if need_dw:
-            if _wgrad_table_covers(1, features.shape[1], grad_out.shape[1]):
-                dW = wgrad_table(features, grad_out, None, M, 1)
-            else:
-                dW = wgrad(features, grad_out, None, None, None, M, 1)
-    elif kind == "conv":
-        if need_din:
-            if rb.nonoverlap and not _direct_covers(W3.shape[0], W3.shape[2], W3.shape[1]):
-                din = gather_gemm_pairs(grad_out, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, M, M, wflags=W_T, wimg=wb)
-            else:
-                din = gather_gemm(grad_out, W3, rb.fwd, M, wflags=W_T, wimg=wb)
-        if need_dw:
-            if _wgrad_table_covers(rb.K, features.shape[1], grad_out.shape[1]):
-                dW = wgrad_table(features, grad_out, rb.bwd, grad_out.shape[0], rb.K)
-            else:
-                dW = wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K)
-    else:  # inverse
-        n_fine = rb.indices.shape[0]
-        if need_din:
-            din = gather_gemm(grad_out, W3, rb.bwd, M, wflags=W_T, wimg=wb)
-        if need_dw:
-            if _wgrad_table_covers(rb.K, features.shape[1], grad_out.shape[1]):
-                dW = wgrad_table(features, grad_out, rb.fwd, n_fine, rb.K)
-            else:
-                dW = wgrad(features, grad_out, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, rb.K)
+    fk = None
+    if need_dw:
+        buf = _dw_arena.take(tuple(W3.shape), features.device)  # before the fork: a fresh arena block is zeroed on main
+        if need_din and async_wgrad and _prof is None:
+            fk = _fork_side(features.device)
+            _wg_stream = fk[1]
+        try:
+            dW = _conv_wgrad(kind, features, grad_out, rb, buf)
+        finally:
+            _wg_stream = None
+    if need_din:
+        din = _conv_dgrad(kind, W3, grad_out, rb, wb, M)
+    if fk is not None:
+        if defer_join:
+            _pending_join = fk
+        else:
+            _join_side(fk)
     return din, (dW.view(filters.shape) if dW is not None else None)
 
 
@@ -897,12 +922,15 @@ class BNReLUConvFunction(Function):
         dy = dW = None
         if grad_out is not None:
             grad_out = _f32c(grad_out)
-            dy, dW = conv_backward_raw(ctx.kind, y, filters, grad_out, ctx.rb, ctx.prep, True, ctx.needs_input_grad[3])
+            dy, dW = conv_backward_raw(ctx.kind, y, filters, grad_out, ctx.rb, ctx.prep, True, ctx.needs_input_grad[3],
+                                       defer_join=True)
         if grad_y is not None:
             dy = grad_y if dy is None else dy + grad_y
         if dy is None:
+            join_pending_wgrad()
             return (None,) * 12
         dx, dwb = _bn_backward_raw(x, _f32c(dy), bn_w, bn_b, stats, True)
+        join_pending_wgrad()  # the wgrad kernel ran on the side stream next to dgrad and the BN backward
         dw = dwb[0] if bn_w is not None and ctx.needs_input_grad[1] else None
         db = dwb[1] if bn_b is not None and ctx.needs_input_grad[2] else None
         return dx, dw, db, dW, None, None, None, None, None, None, None, None

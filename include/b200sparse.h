@@ -33,6 +33,11 @@ const char* b200sp_last_error(void);
 int b200sp_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */
 int64_t b200sp_launch_count(void);
+/* fork / join of a side stream (cudaEventRecord + cudaStreamWaitEvent in one call): the host runs a layer's weight
+ * gradient on a side stream next to its dgrad + BN backward.  Events are created once and reused. */
+int b200sp_event_create(void** event_out);
+int b200sp_stream_fork(void* main_stream, void* side_stream, void* event);
+int b200sp_stream_join(void* main_stream, void* side_stream, void* event);
 
 /* ------------------------------------------------------------------------------------------
  * Rulebook builder.  Replaces spconv v1.2 `ops.get_indice_pairs` (called from
