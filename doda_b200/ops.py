@@ -406,8 +406,14 @@ W_FWD, W_T, W_T_MIRROR = 0, 1, 3  # wflags of the C ABI: bit0 = use W[k]^T (dgra
 W_PREP = 4  # bit2: the weight pointer is an image made by b200sp_prep_weights_batch
 
 
+def _kcc(W):
+    """(K, Ci_w, Co_w) of a weight tensor [..., Ci_w, Co_w] (no view is made: the kernels only need the pointer)"""
+    Ci_w, Co_w = W.shape[-2], W.shape[-1]
+    return W.numel() // (Ci_w * Co_w), Ci_w, Co_w
+
+
 def _conv_dims(W3, wflags):
-    K, Ci_w, Co_w = W3.shape
+    K, Ci_w, Co_w = _kcc(W3)
     return (K, Co_w, Ci_w) if (wflags & 1) else (K, Ci_w, Co_w)
 
 
@@ -631,10 +637,9 @@ def weight_transpose(W3, mirror):
 
 
 def _w3(filters):
-    """[k,k,k,Cin,Cout] (or any leading kernel dims) -> contiguous [K,Cin,Cout] view"""
-    Cin, Cout = filters.shape[-2], filters.shape[-1]
-    f = filters if filters.is_contiguous() else filters.contiguous()
-    return f.view(-1, Cin, Cout)
+    """[k,k,k,Cin,Cout] (or any leading kernel dims) -> the same tensor, contiguous; the conv primitives read its
+    (K, Cin, Cout) through _kcc, so no 3-D view object is created per call"""
+    return filters if filters.is_contiguous() else filters.contiguous()
 
 
 class _ConvFunctionBase(Function):
@@ -739,7 +744,7 @@ def conv_forward_raw(kind, features, filters, rb, prep):
     if kind == "conv":
         return gather_gemm(features, W3, rb.bwd, rb.outids.shape[0], wimg=wf)
     n_fine = rb.indices.shape[0]  # inverse
-    if rb.nonoverlap and not _direct_covers(W3.shape[0], W3.shape[1], W3.shape[2]):
+    if rb.nonoverlap and not _direct_covers(*_kcc(W3)):
         return gather_gemm_pairs(features, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, n_fine, wimg=wf)
     return gather_gemm(features, W3, rb.fwd, n_fine, wimg=wf)
 
@@ -748,6 +753,7 @@ def conv_forward_raw(kind, features, filters, rb, prep):
 # bound (deep levels: a few CTAs) -- the backward node forks a side stream for the wgrad kernel and joins it before it
 # returns, so everything autograd / DDP does with dW afterwards is ordered as before.
 async_wgrad = os.environ.get("B200SP_ASYNC_WGRAD", "1") != "0"
+async_wgrad_max_rows = 65536  # above this both kernels fill the machine and the fork/join only costs host time
 _wg_side = {}        # device index -> (torch side stream, its raw handle, fork event, join event)
 _pending_join = None
 
@@ -813,7 +819,7 @@ def _conv_dgrad(kind, W3, grad_out, rb, wb, M):
     if kind == "dense":
         return gather_gemm(grad_out, W3, None, M, wflags=W_T, wimg=wb)
     if kind == "conv":
-        if rb.nonoverlap and not _direct_covers(W3.shape[0], W3.shape[2], W3.shape[1]):
+        if rb.nonoverlap and not _direct_covers(_kcc(W3)[0], W3.shape[-1], W3.shape[-2]):
             return gather_gemm_pairs(grad_out, W3, rb.pairs[1], rb.pairs[0], rb.pairnum, M, M, wflags=W_T, wimg=wb)
         return gather_gemm(grad_out, W3, rb.fwd, M, wflags=W_T, wimg=wb)
     return gather_gemm(grad_out, W3, rb.bwd, M, wflags=W_T, wimg=wb)  # inverse
@@ -830,8 +836,8 @@ def conv_backward_raw(kind, features, filters, grad_out, rb, prep, need_din=True
     din = dW = None
     fk = None
     if need_dw:
-        buf = _dw_arena.take(tuple(W3.shape), features.device)  # before the fork: a fresh arena block is zeroed on main
-        if need_din and async_wgrad and _prof is None:
+        buf = _dw_arena.take(filters.shape, features.device)  # before the fork: a fresh arena block is zeroed on main
+        if need_din and async_wgrad and _prof is None and M <= async_wgrad_max_rows:
             fk = _fork_side(features.device)
             _wg_stream = fk[1]
         try:
@@ -845,7 +851,7 @@ def conv_backward_raw(kind, features, filters, grad_out, rb, prep, need_din=True
             _pending_join = fk
         else:
             _join_side(fk)
-    return din, (dW.view(filters.shape) if dW is not None else None)
+    return din, dW
 
 
 def _bn_forward_raw(x, weight, bias, running_mean, running_var, nbt, momentum, eps, relu):
@@ -1027,7 +1033,7 @@ def indice_conv_backward(features, filters, out_bp, indice_pairs, indice_pair_nu
     features, out_bp = _f32c(features), _f32c(out_bp)
     pairs, pairnum = indice_pairs.contiguous(), indice_pair_num.contiguous()
     W3 = _w3(filters)
-    K = W3.shape[0]
+    K = _kcc(W3)[0]
     n_in = features.shape[0]
     tab = pairs_to_table(pairs, pairnum, n_in, not inverse)  # in-row -> out-row per offset
     din = gather_gemm(out_bp, W3, tab, n_in, wflags=W_T)
