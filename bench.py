@@ -148,7 +148,7 @@ def run_reference(args):
             v.grad = None
         loss, _ = model_step_ref(sd, batch, training=True)
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
 
     steps = max(1, min(args.steps, 5))  # each step is the FULL workload (~5 s of CPU work); bounded to stay in minutes
     warm = max(1, min(args.warmup, 1))
