@@ -357,7 +357,7 @@ def main():
                                           "share_of_engine_kernel_time": tot_ms / max(all_ms, 1e-9)}}
             detail = recs
     cpu_base = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N=1 only (rank 0, the box's host cores)
         from oracle.unet_ref import model_step_ref
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
