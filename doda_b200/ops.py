@@ -227,6 +227,33 @@ def index_stream_for(device):
     return side
 
 
+def stage_batch(batch, device, keys=("voxel_locs", "p2v_map", "v2p_map", "feats", "labels")):
+    """Start the host -> device copies of a collated batch on the engine's index stream and return a batch dict of
+    device tensors (the other entries are passed through).  Meant to be called for batch i+1 before step i runs, from
+    pinned host memory: the copies then overlap step i's kernels instead of sitting at the head of step i+1 on the
+    compute stream (24 MB per step at 2 x 150 k voxels).  `model_step` makes the compute stream wait for them."""
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("doda_b200: stage_batch needs a CUDA device (no CPU fallback)")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    main = torch.cuda.current_stream(dev)
+    side = index_stream_for(dev)
+    out = dict(batch)
+    with torch.cuda.stream(side):
+        for k in keys:
+            t = batch[k].to(dev, non_blocking=True)
+            if k == "voxel_locs":
+                t = (t if t.dtype == _I32 else t.int()).contiguous()
+            out[k] = t
+        ev = side.record_event()
+    for k in keys:
+        out[k].record_stream(main)
+    out["voxel_locs"]._b200sp_idx_stream = True
+    out["_staged_event"] = ev
+    return out
+
+
 def stage_coords(voxel_locs, device, pending=False):
     """[M,4] voxel coordinates (host or device; int64 as the reference's collate makes them, or int32) -> int32
     device tensor, produced on the engine's index stream.
@@ -235,6 +262,9 @@ def stage_coords(voxel_locs, device, pending=False):
     backward on the caller's stream -- if they do, every rulebook of the new step (and the host read of the strided
     builder) waits for that backward and the host can never run ahead of the GPU.  `pending=True` is for coordinates
     some kernel on the caller's stream is still writing: the index stream then waits for the caller's stream first."""
+    if voxel_locs.is_cuda and voxel_locs.dtype == _I32 and getattr(voxel_locs, "_b200sp_idx_stream", False) \
+            and voxel_locs.is_contiguous():
+        return voxel_locs  # already staged (stage_batch)
     dev = torch.device(device)
     if dev.type != "cuda":
         raise RuntimeError("doda_b200: stage_coords needs a CUDA device (no CPU fallback)")

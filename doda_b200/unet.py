@@ -109,6 +109,9 @@ def model_step(model, batch, voxel_mode=4, criterion=None, device="cuda", coords
     The voxel coordinates go through `ops.stage_coords` (copy + int cast on the engine's index stream) so that the
     rulebooks of this step do not queue behind the previous step's backward; device-resident `voxel_locs` must be
     complete, or pass coords_pending=True."""
+    staged = batch.get("_staged_event")
+    if staged is not None:  # ops.stage_batch started the copies on the index stream
+        torch.cuda.current_stream().wait_event(staged)
     voxel_coords = _ops.stage_coords(batch["voxel_locs"], device, pending=coords_pending)
     p2v_map = batch["p2v_map"].to(device, non_blocking=True)
     v2p_map = batch["v2p_map"].to(device, non_blocking=True)

@@ -570,6 +570,26 @@ def _unet_parity(cuda_dev, target, mid, tol_scores, tol_grad):
     assert report["l2"] <= max(2.0 * tol_grad, 40.0 * report["f32_median"]), report
 
 
+def test_staged_batch_and_host_batch_give_the_same_step(cuda_dev):
+    """ops.stage_batch (H2D copies + coordinate cast on the index stream, ahead of the step) feeds model_step the
+    same values as the plain host batch: identical loss and scores, two steps in a row (event hand-off both ways)"""
+    from doda_b200 import scenes, ops
+    from doda_b200.unet import SparseConvNet, model_step
+    torch.manual_seed(0)
+    batch = scenes.collate([scenes.scene_with_voxels(3, 6000), scenes.scene_with_voxels(4, 5000)], dup_max=2)
+    pinned = dict(batch)
+    for k in ("voxel_locs", "p2v_map", "v2p_map", "feats", "labels"):
+        pinned[k] = batch[k].pin_memory()
+    model = SparseConvNet(mid_channel=16).to(cuda_dev).eval()  # eval: no running-stat updates between the passes
+    with torch.no_grad():
+        ref_loss, ref_scores = model_step(model, batch, device=cuda_dev)
+        for _ in range(2):
+            staged = ops.stage_batch(pinned, cuda_dev)
+            assert staged["voxel_locs"].dtype == torch.int32 and staged["feats"].is_cuda
+            loss, scores = model_step(model, staged, device=cuda_dev)
+            assert torch.equal(scores, ref_scores) and float(loss) == float(ref_loss)
+
+
 def test_unet_fwd_bwd_small_scene(cuda_dev):
     # whole-net check: 71 convs + 65 BN deep, so the per-op 1e-4 bound compounds; 1e-3 on logits / grads
     _unet_parity(cuda_dev, 20000, 16, 1e-3, 5e-3)
