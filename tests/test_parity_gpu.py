@@ -587,7 +587,8 @@ def test_staged_batch_and_host_batch_give_the_same_step(cuda_dev):
             staged = ops.stage_batch(pinned, cuda_dev)
             assert staged["voxel_locs"].dtype == torch.int32 and staged["feats"].is_cuda
             loss, scores = model_step(model, staged, device=cuda_dev)
-            assert torch.equal(scores, ref_scores) and float(loss) == float(ref_loss)
+            # split-K layers add partial sums with atomics: equal up to summation order
+            assert rel_err(scores, ref_scores) <= 1e-5 and abs(float(loss) - float(ref_loss)) <= 1e-5
 
 
 def test_unet_fwd_bwd_small_scene(cuda_dev):
