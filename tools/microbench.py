@@ -28,7 +28,9 @@ def timeit(fn, n=5):
 
 print("# Microbench sweep (round 1): SubM 3x3x3 rulebook build and fused conv kernels, L2 flushed between launches\n")
 print("peak = " + ("%.1f" % peak) + " GB/s (MEASURED_PEAKS.json, of measured).  Algorithmic bytes: rulebook 16M + 8P + 4K + 8MK (two tables); "
-      "conv 4(M Cin + M Cout) + 4 K Cin Cout + 8 P; wgrad P(8 + 4Cin + 4Cout) + 4 K Cin Cout.\n")
+      "conv 4(M Cin + M Cout) + 4 K Cin Cout + 8 P; wgrad P(8 + 4Cin + 4Cout) + 4 K Cin Cout.  Kernels as the engine "
+      "dispatches them: C = 16, 32 register-gather conv (conv_direct.cu), C = 16 table-form wgrad (wgrad_direct.cu), "
+      "the rest tcgen05 (conv_tc.cu, wgrad_tc.cu).\n")
 print("| scene | M | P/M | rulebook ms | GB/s | frac | C | fwd ms | GB/s | frac | dgrad ms | wgrad ms | GB/s | frac |")
 print("|---|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|---:|")
 cases = [("uniform %.1f%%" % (100 * occ), M, occ) for M in (10000, 100000, 1000000) for occ in (0.005, 0.02, 0.05)]
@@ -50,7 +52,8 @@ for name, M, occ in cases:
         W3 = torch.randn(27, C, C, device=dev) * 0.1
         t_f = timeit(lambda: ops.gather_gemm(x, W3, rb.nbr_perm, n, orow=rb.order, rowmask=rb.rowmask))
         t_d = timeit(lambda: ops.gather_gemm(g, W3, rb.nbr_perm, n, orow=rb.order, wflags=ops.W_T_MIRROR, rowmask=rb.rowmask))
-        t_w = timeit(lambda: ops.wgrad(x, g, rb.pairs[0], rb.pairs[1], rb.pairnum, n, 27))
+        # the engine's own dispatch: table form (wgrad_direct.cu) where it is used, pair lists (wgrad_tc.cu) elsewhere
+        t_w = timeit(lambda: ops.conv_backward_raw("subm", x, W3, g, rb, None, False, True))
         b_c = 4 * (2 * n * C) + 4 * 27 * C * C + 8 * P
         b_w = P * (8 + 8 * C) + 4 * 27 * C * C
         gf, gw = b_c / t_f / 1e6, b_w / t_w / 1e6
