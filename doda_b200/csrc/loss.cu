@@ -156,3 +156,66 @@ extern "C" int b200sp_cross_entropy_bwd(const float* logits, const int64_t* labe
     B200SP_LAUNCH_CHECK();
     return B200SP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Metric epilogue: per-class intersection / union / target counts of util/common_utils.py:233-247
+// (intersectionAndUnionGPU: three torch.histc calls on CPU copies = three device->host syncs per iteration,
+// tool/train.py:113-118).  One pass over (prediction, label), block-private histograms in shared memory, integer
+// atomics to a [3][K] device buffer, counts returned as float like histc does.  Rows whose label is ignore_index are
+// skipped entirely; predictions / labels outside [0, K) fall outside the histogram range, as with histc.
+// ---------------------------------------------------------------------------------------------------------------
+namespace b200sp {
+namespace {
+constexpr int IOU_MAXK = 1024;
+
+__global__ void __launch_bounds__(256) k_iou_hist(const long long* __restrict__ pred, const long long* __restrict__ label,
+                                                  long long N, int K, long long ignore_index, int* __restrict__ acc) {
+    extern __shared__ int s_h[];  // [3][K]: intersection, prediction, target
+    for (int i = threadIdx.x; i < 3 * K; i += blockDim.x) s_h[i] = 0;
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < N; i += (long long)gridDim.x * blockDim.x) {
+        const long long t = label[i];
+        if (t == ignore_index) continue;
+        const long long o = pred[i];
+        if (o >= 0 && o < K) atomicAdd(&s_h[K + (int)o], 1);
+        if (t >= 0 && t < K) {
+            atomicAdd(&s_h[2 * K + (int)t], 1);
+            if (o == t) atomicAdd(&s_h[(int)t], 1);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * K; i += blockDim.x)
+        if (s_h[i]) atomicAdd(&acc[i], s_h[i]);
+}
+
+// out[0] = intersection, out[1] = union = prediction + target - intersection, out[2] = target
+__global__ void k_iou_finish(const int* __restrict__ acc, int K, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= K) return;
+    const int inter = acc[c], po = acc[K + c], ta = acc[2 * K + c];
+    out[c] = (float)inter;
+    out[K + c] = (float)(po + ta - inter);
+    out[2 * K + c] = (float)ta;
+}
+}  // namespace
+}  // namespace b200sp
+
+extern "C" int b200sp_intersection_union(const int64_t* pred, const int64_t* label, int64_t N, int K, int64_t ignore_index,
+                                         float* out3k, void* ws, int64_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B200SP_CHECK_ARG(N >= 0 && K >= 1 && K <= IOU_MAXK, "intersection_union: need N >= 0 and 1 <= K <= %d", IOU_MAXK);
+    B200SP_CHECK_ARG(out3k && ws && ws_bytes >= (int64_t)3 * K * 4, "intersection_union: null output or workspace < 12 K bytes");
+    B200SP_CHECK_ARG(N == 0 || (pred && label), "intersection_union: null input");
+    int* acc = (int*)ws;
+    B200SP_CUDA(cudaMemsetAsync(acc, 0, (size_t)3 * K * 4, st));
+    if (N > 0) {
+        long long g = cdiv(N, 256 * 8);
+        if (g > 296) g = 296;
+        k_iou_hist<<<(unsigned)g, 256, (size_t)3 * K * sizeof(int), st>>>((const long long*)pred, (const long long*)label, N, K,
+                                                                        ignore_index, acc);
+        B200SP_LAUNCH_CHECK();
+    }
+    k_iou_finish<<<(unsigned)cdiv(K, 128), 128, 0, st>>>(acc, K, out3k);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}

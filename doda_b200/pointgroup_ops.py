@@ -9,6 +9,7 @@ import torch
 from torch.autograd import Function
 
 from . import pg_op as PG_OP
+from ._lib import lib, check
 
 
 def voxelization_idx(coords, batchsize, mode=4):
@@ -21,6 +22,44 @@ def voxelization_idx(coords, batchsize, mode=4):
     output_map = torch.zeros(0, dtype=torch.int32)
     PG_OP.voxelize_idx(coords, output_coords, input_map, output_map, batchsize, mode)
     return output_coords, input_map, output_map
+
+
+_vox_pinned = [None, 0]
+
+
+def voxelization_idx_gpu(coords, batchsize, mode=4):
+    """`voxelization_idx` on the device: coords int64 [N, 3 or 4] CUDA ->
+    (output_coords int64 [M, ncol], input_index int32 [N], output_index int32 [M, 1 + maxActive]), all CUDA and
+    bit-identical to the CPU / reference result (first-touch voxel order, ascending points per voxel).
+    One host sync (M and maxActive size the outputs); run it on a side stream a batch ahead to hide it."""
+    from . import ops as _ops
+    if not coords.is_cuda:
+        raise RuntimeError("voxelization_idx_gpu needs a CUDA tensor (the CPU entry point is voxelization_idx)")
+    assert coords.dtype == torch.int64 and coords.dim() == 2 and coords.is_contiguous()
+    N, ncol = coords.shape
+    dev = coords.device
+    input_map = torch.empty(N, dtype=torch.int32, device=dev)
+    ws = _ops._workspace(int(lib.b200sp_voxelize_idx_gpu_ws_bytes(N)), dev, "vox")
+    if _vox_pinned[0] is None:
+        _vox_pinned[0] = torch.zeros(64, 4, dtype=torch.int32).pin_memory()
+    _vox_pinned[1] = (_vox_pinned[1] + 1) % 64
+    info = _vox_pinned[0][_vox_pinned[1]]
+    st = _ops._stream()
+    check(lib.b200sp_voxelize_idx_gpu_begin(coords.data_ptr(), N, ncol, int(mode), input_map.data_ptr(), info.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), st), "voxelize_idx_gpu_begin")
+    torch.cuda.current_stream(dev).synchronize()
+    M, A, bad, dup = [int(v) for v in info.tolist()]
+    if bad:
+        raise RuntimeError("voxelization_idx_gpu: coordinates must satisfy 0 <= batch < 15 and 0 <= x, y, z < 2^20")
+    if int(mode) == 0 and dup:
+        raise RuntimeError("libb200sparse voxelize_idx failed: mode 0 requires unique coordinates")
+    A = A if int(mode) in (3, 4) else 1
+    out_coords = torch.empty((M, ncol), dtype=torch.int64, device=dev)
+    output_map = torch.empty((M, A + 1), dtype=torch.int32, device=dev)
+    check(lib.b200sp_voxelize_idx_gpu_finish(coords.data_ptr(), N, ncol, int(mode), M, A, out_coords.data_ptr(),
+                                             output_map.data_ptr(), ws.data_ptr(), ws.numel(), st),
+          "voxelize_idx_gpu_finish")
+    return out_coords, input_map, output_map
 
 
 class Voxelization(Function):

@@ -222,6 +222,19 @@ int64_t b200sp_ballquery_ws_bytes(int n);
 int b200sp_ballquery_batch_p(const float* xyz_dev, const int32_t* batch_idxs_dev, const int32_t* batch_offsets_dev,
                              int32_t* idx_dev, int32_t* start_len_dev, int n, int mean_active, float radius,
                              void* ws_dev, int64_t ws_bytes, int32_t* n_active_host, void* stream);
+/* The same on the device (batch assembly without the serial CPU hash map), bit-identical results
+ * (first-touch voxel order, ascending points per voxel).  coords: int64 [N, ncol] on the device, 0 <= batch < 15,
+ * 0 <= x, y, z < 2^20.  Two calls: _begin writes input_map [N] and starts an async copy of
+ * info[4] = {M, maxActive (modes 3/4), bad-coordinate flag, duplicate flag} to pinned host memory; after a stream
+ * sync the caller sizes out_coords [M, ncol] / output_map [M, 1 + maxActive] (maxActive = 1 for modes 0-2) and calls
+ * _finish with the SAME workspace (b200sp_voxelize_idx_gpu_ws_bytes(N) bytes). */
+int64_t b200sp_voxelize_idx_gpu_ws_bytes(int64_t N);
+int b200sp_voxelize_idx_gpu_begin(const int64_t* coords_dev, int64_t N, int ncol, int mode, int32_t* input_map_dev,
+                                  int32_t* info_host /*[4] pinned*/, void* ws_dev, int64_t ws_bytes, void* stream);
+int b200sp_voxelize_idx_gpu_finish(const int64_t* coords_dev, int64_t N, int ncol, int mode, int64_t M,
+                                   int max_active, int64_t* out_coords_dev, int32_t* output_map_dev, void* ws_dev,
+                                   int64_t ws_bytes, void* stream);
+
 /* bfs_cluster.cpp:28-111 — CPU BFS connected components. Two-call protocol like voxelize_idx. */
 int b200sp_bfs_cluster_cpu(const int32_t* sem_host, const int32_t* idx_host, const int32_t* start_len_host, int N,
                            int threshold, int32_t* cluster_idxs_host /*[sum,2]*/, int32_t* cluster_offsets_host,
@@ -277,6 +290,13 @@ int b200sp_cross_entropy_fwd(const float* logits_dev /*[N,C]*/, const int64_t* l
 int b200sp_cross_entropy_bwd(const float* logits_dev, const int64_t* labels_dev, const float* weight_dev, int64_t N,
                              int C, int64_t ignore_index, const float* out2_dev, const float* dloss_dev /*[1]*/,
                              float* dlogits_dev /*[N,C]*/, void* stream);
+
+/* Metric epilogue, replaces util/common_utils.py:233-247 (intersectionAndUnionGPU: three torch.histc calls on CPU
+ * copies, i.e. three device->host syncs per iteration at tool/train.py:113-118).  pred / label: int64 [N];
+ * out3k: float [3][K] = per-class intersection, union, target counts (float, as histc returns them), on the device,
+ * no host sync.  ws: >= 12 K bytes of device scratch.  K <= 1024. */
+int b200sp_intersection_union(const int64_t* pred_dev, const int64_t* label_dev, int64_t N, int K,
+                              int64_t ignore_index, float* out3k_dev, void* ws_dev, int64_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -493,6 +493,69 @@ def test_cross_entropy_matches_torch(cuda_dev, C, weighted):
     assert float(mod(x.detach(), labels.to(cuda_dev))) == float(ops.cross_entropy(x.detach(), labels.to(cuda_dev), None, 255))
 
 
+@pytest.mark.parametrize("K,shape", [(11, (50000,)), (13, (300, 40)), (20, (7, 9, 11)), (11, (0,))])
+def test_intersection_and_union_matches_reference_formula(cuda_dev, K, shape):
+    """metric epilogue (util/common_utils.py:233-247): per-class intersection / union / target counts, exact, with
+    ignored labels, out-of-range predictions and an empty input"""
+    from doda_b200 import metrics
+    g = torch.Generator().manual_seed(K)
+    pred = torch.randint(0, K + 2, shape, generator=g)  # K, K+1: out of the histogram range
+    lab = torch.randint(0, K, shape, generator=g)
+    if pred.numel():
+        lab.view(-1)[torch.rand(lab.numel(), generator=g) < 0.1] = 255
+        same = torch.rand(shape, generator=g) < 0.5
+        pred = torch.where(same & (lab != 255), lab, pred)
+    ri, ru, rt = metrics.intersection_and_union_ref(pred, lab, K, 255)
+    for dtype in (torch.int64, torch.int32):
+        i, u, t = metrics.intersectionAndUnionGPU(pred.to(cuda_dev, dtype), lab.to(cuda_dev, dtype), K, 255)
+        assert i.is_cuda and i.dtype == torch.float32 and i.shape == (K,)
+        assert torch.equal(i.cpu(), ri) and torch.equal(u.cpu(), ru) and torch.equal(t.cpu(), rt)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_voxelize_idx_gpu_is_bit_identical_to_cpu(cuda_dev, mode):
+    """device voxelizer against the CPU entry point, which is pinned to the reference's compiled
+    code by the golden vectors: voxel order, p2v and v2p maps identical, for every mode, 3- and 4-column coordinates,
+    heavy duplication, and the 6-point known answer"""
+    from doda_b200 import pointgroup_ops
+    rng = np.random.RandomState(10 + mode)
+    cases = []
+    if mode == 0:  # unique coordinates only
+        cases.append(np.stack(np.unravel_index(rng.permutation(4096)[:3000], (16, 16, 16)), 1))
+        cases.append(np.concatenate([rng.randint(0, 3, (3000, 1)), cases[0]], 1))
+    else:
+        for n, side, ncol in ((5000, 12, 4), (3000, 40, 3), (20000, 6, 4), (1, 3, 4), (257, 2, 4)):
+            c = rng.randint(0, side, size=(n, 3))
+            if ncol == 4:
+                c = np.concatenate([np.sort(rng.randint(0, 3, size=(n, 1)), 0), c], 1)
+            cases.append(c)
+        cases.append(np.array([[0, 1, 1, 1], [0, 1, 1, 1], [0, 2, 2, 2], [1, 1, 1, 1], [0, 2, 2, 2], [0, 1, 1, 1]]))
+    for c in cases:
+        c = torch.from_numpy(np.ascontiguousarray(c.astype(np.int64)))
+        oc, im, om = pointgroup_ops.voxelization_idx(c, 3, mode)
+        goc, gim, gom = pointgroup_ops.voxelization_idx_gpu(c.to(cuda_dev), 3, mode)
+        assert goc.is_cuda and gim.dtype == torch.int32 and gom.dtype == torch.int32
+        assert torch.equal(goc.cpu(), oc) and torch.equal(gim.cpu(), im) and torch.equal(gom.cpu(), om), (mode, tuple(c.shape))
+
+
+def test_voxelize_idx_gpu_full_size_and_errors(cuda_dev):
+    from doda_b200 import pointgroup_ops, scenes
+    batch = scenes.collate([scenes.scene_with_voxels(i, 150000) for i in range(2)], seed=0, dup_max=2)
+    locs = batch["locs"].contiguous() if "locs" in batch else None
+    if locs is None:  # rebuild point coordinates from the maps: every point carries its voxel's coordinates
+        locs = batch["voxel_locs"][batch["p2v_map"].long()].contiguous()
+    oc, im, om = pointgroup_ops.voxelization_idx(locs, 2, 4)
+    goc, gim, gom = pointgroup_ops.voxelization_idx_gpu(locs.to(cuda_dev), 2, 4)
+    assert oc.shape[0] == 300000
+    assert torch.equal(goc.cpu(), oc) and torch.equal(gim.cpu(), im) and torch.equal(gom.cpu(), om)
+    e = pointgroup_ops.voxelization_idx_gpu(torch.zeros((0, 4), dtype=torch.int64, device=cuda_dev), 1, 4)
+    assert e[0].shape == (0, 4) and e[1].numel() == 0 and e[2].shape[0] == 0
+    with pytest.raises(RuntimeError):
+        pointgroup_ops.voxelization_idx_gpu(torch.tensor([[0, -1, 0, 0]], device=cuda_dev), 1, 4)
+    with pytest.raises(RuntimeError):
+        pointgroup_ops.voxelization_idx_gpu(torch.tensor([[0, 1, 1, 1], [0, 1, 1, 1]], device=cuda_dev), 1, 0)
+
+
 def test_voxelize_and_devoxelize(cuda_dev):
     from doda_b200 import pointgroup_ops, ops
     from oracle.unet_ref import voxelize_mean_ref
