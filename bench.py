@@ -3,14 +3,16 @@
 (BASELINE.json configs[1]: 2 x 150k-voxel scenes, full unet.py fwd+bwd, bs=2 per GPU).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-  torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU, NCCL; whole scenes are sharded,
-                                                          gradients all-reduced by DDP: "scaling": "weak")
+  torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU, NCCL; whole scenes are sharded, the
+                                                          gradient mean after backward is the only collective:
+                                                          parallel.allreduce_grads, or DDP with --ddp; "scaling": "weak")
 
 Prints ONE JSON line (rank 0).  `value` = scenes/s with the collated batch already resident in HBM;
-`e2e` = the same step through the public API from pinned HOST buffers (H2D of the batch + D2H of the loss inside
-the timed region); `roofline` = the dominant kernel (k_gather_gemm, the sparse-conv gather-GEMM) timed live with
-CUDA events; `cpu_baseline` = the CPU oracle (restatement of spconv v1.2's native algorithm) on the host cores.
-`--impl reference` times that CPU implementation as the reference arm.
+`e2e` = the same step through the public API from pinned HOST buffers (H2D of every step's batch, staged one step
+ahead on the index stream, + an async D2H of every step's loss read one step late, all inside the timed region);
+`roofline` = the conv launch shape with the largest total time (k_conv_direct / k_conv_tc) timed live with CUDA
+events against the measured HBM peak; `cpu_baseline` (N = 1) = the CPU oracle (restatement of spconv v1.2's native
+algorithm) on the host cores.  `--impl reference` times that CPU implementation as the reference arm.
 """
 import argparse
 import json
