@@ -79,52 +79,9 @@ extern "C" int b200sp_stream_join(void* main_stream, void* side_stream, void* ev
     return B200SP_OK;
 }
 
-// Semantics follow lib/pointgroup_ops/src/voxelize/voxelize.cpp:62-155 (first-touch voxel ids while scanning
-// points in order; per-batch maps; output_map rows = [count, pt..., -1 pad]; coords of the first point) and
-// voxelize_outputmap 35-52.  Modes: 0 unique, 1 first point, 2 last point, 3 sum, 4 mean (the code, not the
-// swapped comment at voxelize.cpp:54).  Note the reference zero-fills output_map before writing and pads with -1
-// only up to maxActive (voxelize.cpp:20-21,36-41).
-extern "C" int b200sp_voxelize_idx_cpu(const int64_t* coords, int64_t N, int ncol, int batch_size, int mode,
-                                       int64_t* out_coords, int32_t* input_map, int32_t* output_map, int64_t* M_out,
-                                       int32_t* max_active_out) {
-    (void)batch_size;
-    B200SP_CHECK_ARG(ncol == 3 || ncol == 4, "voxelize_idx: coords must have 3 or 4 columns (got %d)", ncol);
-    B200SP_CHECK_ARG(mode >= 0 && mode <= 4, "voxelize_idx: mode %d not in 0..4", mode);
-    B200SP_CHECK_ARG(N >= 0 && M_out && max_active_out, "voxelize_idx: bad arguments");
-    std::unordered_map<Key4, int32_t, Key4Hash> mp;
-    mp.reserve((size_t)N);
-    std::vector<int32_t> p2v((size_t)N);
-    std::vector<int32_t> count;
-    for (int64_t i = 0; i < N; ++i) {
-        const int64_t* c = coords + i * ncol;
-        Key4 k = ncol == 4 ? Key4{c[0], c[1], c[2], c[3]} : Key4{0, c[0], c[1], c[2]};
-        auto it = mp.find(k);
-        int32_t v;
-        if (it == mp.end()) {
-            v = (int32_t)count.size();
-            mp.emplace(k, v);
-            count.push_back(0);
-        } else {
-            v = it->second;
-        }
-        count[v]++;
-        p2v[i] = v;
-    }
-    const int64_t M = (int64_t)count.size();
-    int32_t maxActive = 1;
-    if (mode == 3 || mode == 4)
-        for (int32_t c : count) maxActive = c > maxActive ? c : maxActive;
-    if (mode == 0) {
-        for (int32_t c : count)
-            if (c != 1) {
-                set_error("voxelize_idx: mode 0 requires unique coordinates");
-                return B200SP_EINVAL;
-            }
-    }
-    *M_out = M;
-    *max_active_out = maxActive;
-    if (!out_coords && !input_map && !output_map) return B200SP_OK;  // size query
-    B200SP_CHECK_ARG(out_coords && input_map && output_map, "voxelize_idx: all three outputs are required");
+// output_map rows [count, points ..., -1 pad] and the voxel coordinates from the point -> voxel map
+static void vox_fill_cpu(const int64_t* coords, int64_t N, int ncol, int mode, const int32_t* p2v, int64_t M, int maxActive,
+                         int64_t* out_coords, int32_t* output_map) {
     const int W = maxActive + 1;
     for (int64_t v = 0; v < M; ++v) {
         int32_t* r = output_map + v * W;
@@ -132,9 +89,7 @@ extern "C" int b200sp_voxelize_idx_cpu(const int64_t* coords, int64_t N, int nco
         for (int j = 1; j < W; ++j) r[j] = -1;
     }
     for (int64_t i = 0; i < N; ++i) {
-        int32_t v = p2v[i];
-        input_map[i] = v;
-        int32_t* r = output_map + (int64_t)v * W;
+        int32_t* r = output_map + (int64_t)p2v[i] * W;
         if (mode == 3 || mode == 4) {
             r[++r[0]] = (int32_t)i;
         } else if (mode == 2) {  // back(): last point wins
@@ -151,6 +106,114 @@ extern "C" int b200sp_voxelize_idx_cpu(const int64_t* coords, int64_t N, int nco
         const int64_t* c = coords + (int64_t)output_map[v * W + 1] * ncol;
         for (int j = 0; j < ncol; ++j) out_coords[v * ncol + j] = c[j];
     }
+}
+
+// Semantics follow lib/pointgroup_ops/src/voxelize/voxelize.cpp:62-155 (first-touch voxel ids while scanning
+// points in order; per-batch maps; output_map rows = [count, pt..., -1 pad]; coords of the first point) and
+// voxelize_outputmap 35-52.  Modes: 0 unique, 1 first point, 2 last point, 3 sum, 4 mean (the code, not the
+// swapped comment at voxelize.cpp:54).  Note the reference zero-fills output_map before writing and pads with -1
+// only up to maxActive (voxelize.cpp:20-21,36-41).
+extern "C" int b200sp_voxelize_idx_cpu(const int64_t* coords, int64_t N, int ncol, int batch_size, int mode,
+                                       int64_t* out_coords, int32_t* input_map, int32_t* output_map, int64_t* M_out,
+                                       int32_t* max_active_out) {
+    (void)batch_size;
+    B200SP_CHECK_ARG(ncol == 3 || ncol == 4, "voxelize_idx: coords must have 3 or 4 columns (got %d)", ncol);
+    B200SP_CHECK_ARG(mode >= 0 && mode <= 4, "voxelize_idx: mode %d not in 0..4", mode);
+    B200SP_CHECK_ARG(N >= 0 && M_out && max_active_out, "voxelize_idx: bad arguments");
+    std::vector<int32_t> p2v((size_t)N);
+    std::vector<int32_t> count;
+    // Fast path (what DODA feeds: batch < 2^15, voxel coordinates < 2^16): the four columns pack into one 64-bit key
+    // and go through a flat open-addressing table (linear probing, load <= 0.5) -- ~15x faster than a node-based
+    // map at 450 k points.  Anything else (negative or huge coordinates) takes the general map below.
+    bool packable = true;
+    for (int64_t i = 0; i < N && packable; ++i) {
+        const int64_t* c = coords + i * ncol;
+        for (int j = 0; j < ncol; ++j)
+            if (c[j] < 0 || c[j] >= (ncol == 4 && j == 0 ? (1 << 15) : (1 << 16))) packable = false;
+    }
+    if (packable) {
+        uint64_t cap = 1024;
+        while (cap < (uint64_t)N * 2) cap <<= 1;
+        const uint64_t mask = cap - 1, kEmpty = ~0ull;
+        std::vector<uint64_t> keys((size_t)cap, kEmpty);
+        std::vector<int32_t> vals((size_t)cap);
+        count.reserve((size_t)N / 2 + 16);
+        for (int64_t i = 0; i < N; ++i) {
+            const int64_t* c = coords + i * ncol;
+            const uint64_t key = ncol == 4 ? ((uint64_t)c[0] << 48) | ((uint64_t)c[1] << 32) | ((uint64_t)c[2] << 16) | (uint64_t)c[3]
+                                           : ((uint64_t)c[0] << 32) | ((uint64_t)c[1] << 16) | (uint64_t)c[2];
+            uint64_t h = key;
+            h ^= h >> 33; h *= 0xff51afd7ed558ccdull; h ^= h >> 33; h *= 0xc4ceb9fe1a85ec53ull; h ^= h >> 33;
+            uint64_t s = h & mask;
+            int32_t v;
+            while (true) {
+                if (keys[s] == key) { v = vals[s]; break; }
+                if (keys[s] == kEmpty) {
+                    v = (int32_t)count.size();
+                    keys[s] = key; vals[s] = v;
+                    count.push_back(0);
+                    break;
+                }
+                s = (s + 1) & mask;
+            }
+            count[v]++;
+            p2v[i] = v;
+        }
+    } else {
+        std::unordered_map<Key4, int32_t, Key4Hash> mp;
+        mp.reserve((size_t)N);
+        for (int64_t i = 0; i < N; ++i) {
+            const int64_t* c = coords + i * ncol;
+            Key4 k = ncol == 4 ? Key4{c[0], c[1], c[2], c[3]} : Key4{0, c[0], c[1], c[2]};
+            auto it = mp.find(k);
+            int32_t v;
+            if (it == mp.end()) {
+                v = (int32_t)count.size();
+                mp.emplace(k, v);
+                count.push_back(0);
+            } else {
+                v = it->second;
+            }
+            count[v]++;
+            p2v[i] = v;
+        }
+    }
+    const int64_t M = (int64_t)count.size();
+    int32_t maxActive = 1;
+    if (mode == 3 || mode == 4)
+        for (int32_t c : count) maxActive = c > maxActive ? c : maxActive;
+    if (mode == 0) {
+        for (int32_t c : count)
+            if (c != 1) {
+                set_error("voxelize_idx: mode 0 requires unique coordinates");
+                return B200SP_EINVAL;
+            }
+    }
+    *M_out = M;
+    *max_active_out = maxActive;
+    if (!out_coords && !output_map) {  // size query; with input_map given it also returns the point -> voxel map,
+        if (input_map)                 // and b200sp_voxelize_idx_cpu_fill finishes without hashing again
+            for (int64_t i = 0; i < N; ++i) input_map[i] = p2v[i];
+        return B200SP_OK;
+    }
+    B200SP_CHECK_ARG(out_coords && input_map && output_map, "voxelize_idx: all three outputs are required");
+    for (int64_t i = 0; i < N; ++i) input_map[i] = p2v[i];
+    vox_fill_cpu(coords, N, ncol, mode, input_map, M, maxActive, out_coords, output_map);
+    return B200SP_OK;
+}
+
+// second half of the two-call protocol when the first call was given input_map: builds output_map / out_coords from
+// the point -> voxel map alone (counting, no hash)
+extern "C" int b200sp_voxelize_idx_cpu_fill(const int64_t* coords, int64_t N, int ncol, int mode, const int32_t* input_map,
+                                            int64_t M, int32_t max_active, int64_t* out_coords, int32_t* output_map) {
+    B200SP_CHECK_ARG(ncol == 3 || ncol == 4, "voxelize_idx: coords must have 3 or 4 columns (got %d)", ncol);
+    B200SP_CHECK_ARG(mode >= 0 && mode <= 4, "voxelize_idx: mode %d not in 0..4", mode);
+    B200SP_CHECK_ARG(N >= 0 && M >= 0 && M <= N && max_active >= 1, "voxelize_idx_fill: bad sizes");
+    if (N == 0) return B200SP_OK;
+    B200SP_CHECK_ARG(coords && input_map && out_coords && output_map, "voxelize_idx_fill: null pointer");
+    for (int64_t i = 0; i < N; ++i)
+        B200SP_CHECK_ARG(input_map[i] >= 0 && input_map[i] < M, "voxelize_idx_fill: input_map[%lld] out of range", (long long)i);
+    vox_fill_cpu(coords, N, ncol, mode, input_map, M, max_active, out_coords, output_map);
     return B200SP_OK;
 }
 

@@ -36,13 +36,13 @@ def voxelize_idx(coords, output_coords, input_map, output_map, batchSize, mode):
     N, ncol = coords.shape
     M = ctypes.c_int64(0)
     A = ctypes.c_int32(0)
-    check(lib.b200sp_voxelize_idx_cpu(coords.data_ptr(), N, ncol, int(batchSize), int(mode), None, None, None,
-                                      ctypes.byref(M), ctypes.byref(A)), "voxelize_idx(size)")
+    # one hashing pass: the size query also writes the point -> voxel map, _fill builds the rest from it
+    check(lib.b200sp_voxelize_idx_cpu(coords.data_ptr(), N, ncol, int(batchSize), int(mode), None,
+                                      input_map.data_ptr(), None, ctypes.byref(M), ctypes.byref(A)), "voxelize_idx(size)")
     output_coords.resize_(M.value, ncol)
     output_map.resize_(M.value, A.value + 1)
-    check(lib.b200sp_voxelize_idx_cpu(coords.data_ptr(), N, ncol, int(batchSize), int(mode),
-                                      output_coords.data_ptr(), input_map.data_ptr(), output_map.data_ptr(),
-                                      ctypes.byref(M), ctypes.byref(A)), "voxelize_idx")
+    check(lib.b200sp_voxelize_idx_cpu_fill(coords.data_ptr(), N, ncol, int(mode), input_map.data_ptr(), M.value, A.value,
+                                           output_coords.data_ptr(), output_map.data_ptr()), "voxelize_idx(fill)")
 
 
 def voxelize_fp(feats, output_feats, output_map, mode, nActive, maxActive, nPlane):

@@ -222,6 +222,11 @@ int64_t b200sp_ballquery_ws_bytes(int n);
 int b200sp_ballquery_batch_p(const float* xyz_dev, const int32_t* batch_idxs_dev, const int32_t* batch_offsets_dev,
                              int32_t* idx_dev, int32_t* start_len_dev, int n, int mean_active, float radius,
                              void* ws_dev, int64_t ws_bytes, int32_t* n_active_host, void* stream);
+/* Faster two-call form: give the size query input_map (out_coords = output_map = NULL) and it also returns the
+ * point -> voxel map; _fill then builds out_coords / output_map from that map without hashing a second time. */
+int b200sp_voxelize_idx_cpu_fill(const int64_t* coords_host, int64_t N, int ncol, int mode,
+                                 const int32_t* input_map_host /*[N], from the first call*/, int64_t M,
+                                 int32_t max_active, int64_t* out_coords_host, int32_t* output_map_host);
 /* The same on the device (batch assembly without the serial CPU hash map), bit-identical results
  * (first-touch voxel order, ascending points per voxel).  coords: int64 [N, ncol] on the device, 0 <= batch < 15,
  * 0 <= x, y, z < 2^20.  Two calls: _begin writes input_map [N] and starts an async copy of
