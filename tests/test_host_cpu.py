@@ -150,3 +150,49 @@ def test_data_parallel_plumbing_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=300) for p in procs]
     for p, (o, e) in zip(procs, outs):
         assert p.returncode == 0 and "ok" in o, e
+
+
+def test_bn_batch_stats_args_follow_torch_and_dsnorm_rules():
+    """host logic of the fused [BN, ReLU, conv] node: which statistics a BatchNorm-like module normalises with
+    (torch.nn.BatchNorm1d.forward rules; DSNorm's per-domain running statistics, model/dsnorm.py:63-84)"""
+    from doda_b200 import ops
+    bn = torch.nn.BatchNorm1d(8, eps=1e-4, momentum=0.1).train()
+    rm, rv, nbt, mom = ops.bn_batch_stats_args(bn)
+    assert rm is bn.running_mean and rv is bn.running_var and nbt is bn.num_batches_tracked and mom == 0.1
+    assert ops.bn_batch_stats_args(bn.eval()) is None                       # eval: fixed statistics, not this path
+    cma = torch.nn.BatchNorm1d(8, momentum=None).train()                    # cumulative moving average
+    cma.num_batches_tracked.fill_(3)
+    assert ops.bn_batch_stats_args(cma)[3] == 0.25
+    nostats = torch.nn.BatchNorm1d(8, track_running_stats=False).eval()     # always batch statistics, nothing to update
+    assert ops.bn_batch_stats_args(nostats) == (None, None, None, 0.1)
+
+    class DS(torch.nn.Module):  # the attributes DODA's DSNorm carries
+        def __init__(self):
+            super().__init__()
+            self.register_buffer("running_mean_source", torch.zeros(8))
+            self.register_buffer("running_var_source", torch.ones(8))
+            self.register_buffer("running_mean_target", torch.zeros(8))
+            self.register_buffer("running_var_target", torch.ones(8))
+            self.register_buffer("num_batches_tracked", torch.tensor(0))
+            self.momentum, self.track_running_stats, self.domain_label, self.eps = 0.1, True, 0, 1e-4
+
+    ds = DS().train()
+    assert ops.bn_batch_stats_args(ds)[0] is ds.running_mean_source
+    ds.domain_label = 1
+    assert ops.bn_batch_stats_args(ds)[0] is ds.running_mean_target and ops.bn_batch_stats_args(ds)[1] is ds.running_var_target
+
+
+def test_staging_and_metrics_refuse_cpu_devices():
+    """no CPU fallback for the device-side helpers either"""
+    from doda_b200 import ops, metrics, pointgroup_ops
+    with pytest.raises(RuntimeError):
+        ops.stage_coords(torch.zeros(4, 4, dtype=torch.int64), "cpu")
+    with pytest.raises(RuntimeError):
+        ops.stage_batch({"voxel_locs": torch.zeros(4, 4, dtype=torch.int64)}, "cpu", keys=("voxel_locs",))
+    with pytest.raises(RuntimeError):
+        metrics.intersectionAndUnionGPU(torch.zeros(4, dtype=torch.int64), torch.zeros(4, dtype=torch.int64), 3)
+    with pytest.raises(RuntimeError):
+        pointgroup_ops.voxelization_idx_gpu(torch.zeros(4, 4, dtype=torch.int64), 1, 4)
+    ri, ru, rt = metrics.intersection_and_union_ref(torch.tensor([0, 1, 2, 3, 4, 6, 1, 1]),
+                                                    torch.tensor([0, 1, 1, 255, 4, 2, 255, 0]), 5)
+    assert ri.tolist() == [1, 1, 0, 0, 1] and ru.tolist() == [2, 3, 2, 0, 1] and rt.tolist() == [2, 2, 1, 0, 1]
