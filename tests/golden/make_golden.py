@@ -2,8 +2,10 @@
   * the reference PG_OP extension compiled unmodified from /root/reference/lib/pointgroup_ops (oracle/build_ref.py)
     for the CPU entry points voxelize_idx (voxelize.cpp:11-155) and bfs_cluster (bfs_cluster.cpp:28-111);
   * the reference model/unet.py + model/unet_block.py imported from /root/reference on top of the compat/ shims
-    (spconv, PG_OP, pointops2_cuda), for the state_dict key names / shapes a checkpoint must match.
-Run:  python tests/golden/make_golden.py      (needs /root/reference; the fixtures it writes are committed)
+    (spconv, PG_OP, pointops2_cuda), for the state_dict key names / shapes a checkpoint must match;
+  * the reference's metric epilogue `intersectionAndUnionGPU` (util/common_utils.py:233-247), imported from the
+    reference file itself (open3d / SharedArray stubbed, `.cuda()` made a no-op: its histc path runs on CPU).
+Run:  python tests/golden/make_golden.py [--only metrics]   (needs /root/reference; the fixtures are committed)
 """
 import json
 import os
@@ -39,7 +41,40 @@ def voxelize_cases():
     return cases
 
 
+def metric_fixtures():
+    """inputs + outputs of the reference's intersectionAndUnionGPU, run here from /root/reference/util/common_utils.py"""
+    import importlib.util
+    for name in ("open3d", "SharedArray"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    spec = importlib.util.spec_from_file_location("ref_common_utils", "/root/reference/util/common_utils.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    out = {}
+    try:
+        rng = np.random.RandomState(5)
+        for i, (K, shape) in enumerate([(11, (20000,)), (13, (200, 30)), (20, (6, 8, 10)), (5, (64,))]):
+            pred = rng.randint(0, K + 2, size=shape)           # K, K+1: outside the histogram range
+            lab = rng.randint(0, K, size=shape)
+            same = rng.rand(*shape) < 0.5
+            pred = np.where(same, lab, pred)
+            lab = np.where(rng.rand(*shape) < 0.1, 255, lab)
+            ai, au, at = ref.intersectionAndUnionGPU(torch.from_numpy(pred), torch.from_numpy(lab), K, 255)
+            out["c%d/pred" % i], out["c%d/label" % i] = pred.astype(np.int64), lab.astype(np.int64)
+            out["c%d/K" % i] = np.array([K], dtype=np.int64)
+            out["c%d/intersection" % i], out["c%d/union" % i], out["c%d/target" % i] = ai.numpy(), au.numpy(), at.numpy()
+    finally:
+        torch.Tensor.cuda = real_cuda
+    np.savez_compressed(os.path.join(HERE, "iou_metrics.npz"), **out)
+
+
 def main():
+    if "--only" in sys.argv and sys.argv[sys.argv.index("--only") + 1] == "metrics":
+        metric_fixtures()
+        print("iou_metrics.npz written to", HERE)
+        return
+    metric_fixtures()
     build_ref.build_all()
     ref = build_ref.load("PG_OP")
     out = {}

@@ -155,3 +155,21 @@ def test_unet_oracle_runs_and_is_deterministic():
     b64 = dict(batch); b64["feats"] = batch["feats"].double()
     l64, s64 = model_step_ref(sd64, b64, training=True)
     assert rel_err(s1, s64) < 1e-3
+
+
+def test_metric_restatement_matches_reference_golden():
+    """tests/golden/iou_metrics.npz holds inputs and outputs of the reference's own intersectionAndUnionGPU
+    (util/common_utils.py:233-247, run from the reference file by tests/golden/make_golden.py); the restatement the
+    GPU parity test compares against must reproduce them exactly"""
+    import os
+    import numpy as np
+    import torch
+    from doda_b200 import metrics
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "iou_metrics.npz"))
+    n = len({k.split("/")[0] for k in z.files})
+    assert n == 4
+    for i in range(n):
+        K = int(z["c%d/K" % i][0])
+        ai, au, at = metrics.intersection_and_union_ref(torch.from_numpy(z["c%d/pred" % i]), torch.from_numpy(z["c%d/label" % i]), K, 255)
+        assert np.array_equal(ai.numpy(), z["c%d/intersection" % i])
+        assert np.array_equal(au.numpy(), z["c%d/union" % i]) and np.array_equal(at.numpy(), z["c%d/target" % i])

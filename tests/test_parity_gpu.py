@@ -513,6 +513,20 @@ def test_intersection_and_union_matches_reference_formula(cuda_dev, K, shape):
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+def test_intersection_and_union_matches_reference_golden(cuda_dev):
+    """device metric epilogue against outputs of the reference's own intersectionAndUnionGPU (golden fixture)"""
+    import os
+    from doda_b200 import metrics
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "iou_metrics.npz"))
+    for i in range(4):
+        K = int(z["c%d/K" % i][0])
+        a = metrics.intersectionAndUnionGPU(torch.from_numpy(z["c%d/pred" % i]).to(cuda_dev),
+                                            torch.from_numpy(z["c%d/label" % i]).to(cuda_dev), K, 255)
+        for got, name in zip(a, ("intersection", "union", "target")):
+            assert np.array_equal(got.cpu().numpy(), z["c%d/%s" % (i, name)]), (i, name)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 def test_voxelize_idx_gpu_is_bit_identical_to_cpu(cuda_dev, mode):
     """device voxelizer against the CPU entry point, which is pinned to the reference's compiled
     code by the golden vectors: voxel order, p2v and v2p maps identical, for every mode, 3- and 4-column coordinates,
