@@ -10,9 +10,15 @@
 Prints ONE JSON line (rank 0).  `value` = scenes/s with the collated batch already resident in HBM;
 `e2e` = the same step through the public API from pinned HOST buffers (H2D of every step's batch, staged one step
 ahead on the index stream, + an async D2H of every step's loss read one step late, all inside the timed region);
-`roofline` = the conv launch shape with the largest total time (k_conv_direct / k_conv_tc) timed live with CUDA
-events against the measured HBM peak; `cpu_baseline` (N = 1) = the CPU oracle (restatement of spconv v1.2's native
-algorithm) on the host cores.  `--impl reference` times that CPU implementation as the reference arm.
+`roofline` = the kernel with the largest total time of the step over ALL families (conv fwd/dgrad, weight gradient,
+BatchNorm), its dominant launch shape timed live with CUDA events against the measured HBM peak, plus one row per
+family in `roofline.families`; `baseline_gpu_native` / `vs_gpu_native` = spconv v1.2's native algorithm with stock
+torch ops on the same GPU (baseline/gpu_native.py: the stand-in for reference spconv-CUDA); `m32` = the same step
+at mid_channel 32; `cpu_baseline` (N = 1) = the CPU oracle (restatement of spconv v1.2's native algorithm) on the host
+cores, with `parity_full_size` = the engine's loss / per-point scores against it at the full size.
+`--impl reference` times that CPU implementation as the reference arm (no product code on that path).
+`--model reference` runs the reference's UNCHANGED model/unet.py + unet_block.py + model_fn (staged copy under
+oracle/_ref/src, through compat/) instead of the mirror doda_b200/unet.py.
 """
 import argparse
 import json
@@ -29,6 +35,7 @@ METRIC = "scenes/sec fwd+bwd Sparse U-Net @150k voxels"
 UNIT = "scenes/s"
 
 
+WORKLOAD = "2x150k-voxel ScanNet-shape scenes, full SparseConvNet fwd+bwd, bs=%d, m=%d"
 SETTLE = 6  # extra untimed steps per timed loop (see main); reported in the JSON line's config
 
 
@@ -42,6 +49,10 @@ def parse():
     ap.add_argument("--bs", type=int, default=2, help="scenes per GPU")
     ap.add_argument("--mid", type=int, default=16, help="MODEL.BACKBONE.mid_channel (16 as shipped)")
     ap.add_argument("--ddp", action="store_true", help="N>1: torch DistributedDataParallel instead of parallel.allreduce_grads")
+    ap.add_argument("--model", default="mirror", choices=["mirror", "reference"],
+                    help="mirror: doda_b200/unet.py; reference: the reference's own model/unet.py, unchanged, via compat/")
+    ap.add_argument("--no-gpu-native", action="store_true")
+    ap.add_argument("--no-m32", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--detail", default="", help="write per-kernel detail JSON here")
@@ -129,20 +140,192 @@ def conv_layer_bytes(rec):
         + 8 * rec["pairs"]
 
 
-def run_reference(args):
-    """Reference arm: the CPU restatement of the reference's (spconv v1.2 native) algorithm on the host cores."""
+def wgrad_bytes(rec):
+    """compulsory bytes of one weight-gradient launch: both operands once, dW once, the pair list:
+    4*(M_a*Ca + M_g*Cb) + 4*K*Ca*Cb + 8*P"""
+    return 4 * (rec["n_rows"] * rec["Ca"] + rec.get("n_b", rec["n_rows"]) * rec["Cb"]) + 4 * rec["K"] * rec["Ca"] * rec["Cb"] \
+        + 8 * rec["pairs"]
+
+
+def record_bytes(rec):
+    k = rec["kernel"]
+    if k == "k_gather_gemm":
+        return conv_layer_bytes(rec)
+    if k == "k_wgrad":
+        return wgrad_bytes(rec)
+    if k == "bn_fwd":
+        return 12 * rec["M"] * rec["C"]   # read for the statistics, read + write for the apply (SURVEY.md 8d)
+    if k == "bn_bwd":
+        return 20 * rec["M"] * rec["C"]   # reduce reads x, dy; apply reads x, dy, writes dx
+    return 0
+
+
+def record_name(rec):
+    if rec["kernel"] in ("k_gather_gemm", "k_wgrad"):
+        return rec.get("name") or rec["kernel"]
+    return {"bn_fwd": "k_bn_reduce<.,0> + k_affine_relu", "bn_bwd": "k_bn_reduce<.,1> + k_bn_bwd_apply"}.get(rec["kernel"], rec["kernel"])
+
+
+def record_shape(rec):
+    k = rec["kernel"]
+    if k == "k_gather_gemm":
+        return ("rows", rec["n_out"], "Cin", rec["Cin"], "Cout", rec["Cout"], "K", rec["K"], "pairs_mode", rec.get("pairs_mode", 0))
+    if k == "k_wgrad":
+        return ("rows", rec["n_rows"], "Ca", rec["Ca"], "Cb", rec["Cb"], "K", rec["K"])
+    return ("rows", rec["M"], "C", rec["C"])
+
+
+def roofline_from_records(recs, peak, how):
+    """One row per kernel family of the step (CUDA-event time per launch on the launch stream, algorithmic bytes of
+    SURVEY.md 8(d) / DESIGN.md 3); `roofline` itself describes the family with the LARGEST total time -- the step's
+    dominant kernel, whatever it is -- through its dominant launch shape."""
+    if not recs:
+        return None
+    fams = {}
+    for r in recs:
+        fams.setdefault(record_name(r), []).append(r)
+    all_ms = sum(r["ms"] for r in recs)
+    rows = []
+    for name, rs in fams.items():
+        ms = sum(r["ms"] for r in rs)
+        by = sum(record_bytes(r) for r in rs)
+        rows.append({"kernel": name, "launches_per_step": len(rs), "ms_per_step": ms, "algorithmic_bytes": by,
+                     "algorithmic_GBs": by / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                     "frac": by / (ms * 1e-3) / 1e9 / peak if ms > 0 else None,
+                     "share_of_engine_kernel_time": ms / max(all_ms, 1e-9)})
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    top = rows[0]["kernel"]
+    groups = {}
+    for r in fams[top]:
+        groups.setdefault(record_shape(r), []).append(r)
+    key, grp = max(groups.items(), key=lambda kv: sum(r["ms"] for r in kv[1]))
+    g_ms = sum(r["ms"] for r in grp) / len(grp)
+    g_bytes = record_bytes(grp[0])
+    ach = g_bytes / (g_ms * 1e-3) / 1e9
+    shape = dict(zip(key[0::2], key[1::2]))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from `ncu --set full` captures
+    if os.path.exists(tpath):
+        for t in json.load(open(tpath)).get(top.split(" ")[0], []):
+            same = all(t.get(k) == v for k, v in shape.items() if k not in ("rows", "pairs_mode"))
+            rows_t = t.get("rows", t.get("n_out", 0))
+            if same and abs(rows_t - shape["rows"]) <= 0.1 * shape["rows"]:
+                traffic = t["dram_bytes"]
+    gg = [r for r in recs if r["kernel"] == "k_gather_gemm"]
+    conv_ms = sum(r["ms"] for r in gg)
+    return {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": traffic, "peak_source": how,
+            "launch_shape": dict(shape, launches_per_step=len(grp), avg_launch_ms=g_ms, algorithmic_bytes=g_bytes),
+            "families": rows,
+            "all_conv_launches": {"launches_per_step": len(gg), "total_ms": conv_ms,
+                                  "algorithmic_GBs": sum(conv_layer_bytes(r) for r in gg) / (conv_ms * 1e-3) / 1e9 if gg else None,
+                                  "useful_dense_tflops": sum(2.0 * r["pairs"] * r["Cin"] * r["Cout"] for r in gg) / (conv_ms * 1e-3) / 1e12 if gg else None,
+                                  "share_of_engine_kernel_time": conv_ms / max(all_ms, 1e-9)}}
+
+
+def pairs_per_level(model, resident, dev, is_ref):
+    """rows and rulebook pairs per U-Net level of THIS batch (P/M says how heavy the synthetic scenes are next to
+    SURVEY.md Appendix B's 7.9-13.6)"""
     import torch
-    from doda_b200.unet import SparseConvNet
+    from doda_b200 import spconv, pointgroup_ops
+    with torch.no_grad():
+        vf = pointgroup_ops.voxelization(resident["feats"], resident["v2p_map"], 4)
+        x = spconv.SparseConvTensor(vf, resident["voxel_locs"].int(), resident["spatial_shape"],
+                                    resident["offsets"].size(0) - 1)
+        model(x, resident["p2v_map"])
+        out = []
+        for l in range(1, 8):
+            rb = x.indice_dict.get("subm%d" % l)
+            if rb is None or rb.pairnum is None:
+                continue
+            M = int(rb.indices.shape[0])
+            P = int(rb.pairnum.sum())
+            out.append({"level": l, "rows": M, "pairs": P, "P_over_M": round(P / max(M, 1), 2)})
+    return out
+
+
+def run_gpu_native(model, batch, dev, value_ms, bs):
+    """spconv v1.2's native algorithm with stock torch ops on this GPU (baseline/gpu_native.py), same weights, same
+    batch.  vs_gpu_native = its best time (CUDA-graph replay + eager rulebooks when the capture works, else eager) /
+    the engine's ms_per_step."""
+    import torch
+    from baseline import gpu_native
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    try:
+        r = gpu_native.measure(sd, batch, dev, steps=3, warmup=1, graph=True)
+    except Exception as e:
+        return {"error": repr(e)[:300], "vs_gpu_native": None}
+    finally:
+        torch.cuda.empty_cache()
+    best = min(v for v in (r["ms_eager"], r["ms_graph"]) if v is not None)
+    return {"algorithm": "per offset index_select -> torch.mm (fp32, TF32 off) -> index_add_, torch BN/ReLU/CE; rulebooks by "
+                         "sort + searchsorted (torch ops)", "ms_per_step_eager": r["ms_eager"],
+            "ms_per_step_cuda_graph": r["ms_graph"], "ms_rulebooks": r["ms_rulebooks"],
+            "graph_error": r.get("graph_error"),
+            "scenes_per_s": bs / (best * 1e-3), "vs_gpu_native": best / value_ms,
+            "note": "stand-in for reference spconv-CUDA (spconv v1.2 cannot be built offline against torch 2.11); "
+                    "vs_gpu_native uses the baseline's FASTER reading"}
+
+
+def run_other_width(mid, batch, dev, model_step, SparseConvNet, ops, flush, steps=8):
+    """the same fwd+bwd step at another mid_channel ("also report m=32")"""
+    import torch
+    model = SparseConvNet(mid_channel=mid).to(dev).train()
+    params = list(model.parameters())
+    res = {k: (v.to(dev) if hasattr(v, "to") and k in ("voxel_locs", "p2v_map", "v2p_map", "feats", "labels") else v)
+           for k, v in batch.items()}
+
+    def step():
+        for p in params:
+            p.grad = None
+        ops.invalidate_prepared_weights()
+        loss, _ = model_step(model, res, device=dev)
+        loss.backward()
+
+    for _ in range(5):
+        step()
+    torch.cuda.synchronize()
+    evs = []
+    for _ in range(steps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        step()
+        e.record()
+        evs.append((s, e))
+    torch.cuda.synchronize()
+    ms = sum(s.elapsed_time(e) for s, e in evs) / steps
+    bs = int(batch["offsets"].shape[0] - 1)
+    del model, params
+    torch.cuda.empty_cache()
+    return {"mid_channel": mid, "ms_per_step": ms, "value": bs / (ms * 1e-3), "unit": UNIT, "steps": steps}
+
+
+def _oracle_batch(bs, voxels, rank=0):
+    """the same collated batch as make_batch(), built WITHOUT the product library: scene generator (pure numpy) +
+    the oracle's numpy voxelizer"""
+    from doda_b200 import scenes  # numpy only: loads no native code
+    from oracle.voxelize import voxelize_idx_ref
+    return scenes.collate([scenes.scene_with_voxels(1000 * rank + i, voxels) for i in range(bs)], seed=rank, dup_max=2,
+                          voxelize=voxelize_idx_ref)
+
+
+def run_reference(args):
+    """Reference arm: the CPU restatement of the reference's (spconv v1.2 native) algorithm on the host cores, the
+    full workload every step.  Nothing of the product runs here: scenes are numpy, the collate uses the oracle's
+    voxelizer, the weights are initialised from the reference model's state_dict layout (tests/golden)."""
+    import torch
     from oracle.unet_ref import model_step_ref
+    from oracle.voxelize import init_state_dict
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    torch.manual_seed(0)
-    batch = make_batch(0, args.bs, args.voxels)
-    model = SparseConvNet(mid_channel=args.mid)
-    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point) for k, v in model.state_dict().items()}
+    batch = _oracle_batch(args.bs, args.voxels)
+    shapes = json.load(open(os.path.join(ROOT, "tests", "golden", "unet_state_dict.json")))["m%d" % args.mid]
+    sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v)
+          for k, v in init_state_dict(shapes, seed=0).items()}
 
     def step():
         for v in sd.values():
@@ -151,8 +334,7 @@ def run_reference(args):
         loss.backward()
         return float(loss.detach())
 
-    steps = max(1, min(args.steps, 5))  # each step is the FULL workload (~5 s of CPU work); bounded to stay in minutes
-    warm = max(1, min(args.warmup, 1))
+    steps, warm = max(1, args.steps), max(1, args.warmup)  # same K / W as the engine's arm (~4 s of CPU work per step)
     for _ in range(warm):
         step()
     t0 = time.perf_counter()
@@ -164,9 +346,9 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "2x150k-voxel ScanNet-shape scenes, full SparseConvNet fwd+bwd, bs=%d, m=%d"
-                      % (args.bs, args.mid), "voxels_per_scene": args.voxels, "scenes_per_gpu": args.bs,
-                      "mid_channel": args.mid, "device": "host CPU (oracle port of spconv v1.2 native algorithm)"},
+           "config": {"workload": WORKLOAD % (args.bs, args.mid), "voxels_per_scene": args.voxels,
+                      "scenes_per_gpu": args.bs, "mid_channel": args.mid,
+                      "device": "host CPU, rank 0 only (oracle port of spconv v1.2's native algorithm; no GPU work)"},
            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                             "sample": sample},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -198,7 +380,18 @@ def main():
 
     torch.manual_seed(0)
     batch = make_batch(rank, args.bs, args.voxels)
-    model = SparseConvNet(mid_channel=args.mid).to(dev).train()
+    ref_model_fn = None
+    if args.model == "reference":
+        # the reference's own files, unchanged (oracle/_ref/src staged by oracle/stage_ref.py), on compat/
+        from oracle import stage_ref
+        if stage_ref.activate() is None:
+            raise SystemExit("--model reference: reference model files are not staged (python -m oracle.stage_ref)")
+        from model.unet import SparseConvNet as RefNet, model_fn_decorator
+        cfg = stage_ref.make_cfg(mid_channel=args.mid)
+        model = RefNet(cfg).to(dev).train()
+        ref_model_fn = model_fn_decorator(cfg, args.bs)
+    else:
+        model = SparseConvNet(mid_channel=args.mid).to(dev).train()
     net = model
     if world > 1 and args.ddp:  # A/B: torch's DistributedDataParallel instead of the engine's in-place gradient mean
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
@@ -233,7 +426,10 @@ def main():
         # the metric is fwd+bwd (no optimizer step), so the weights never change here; in training they change every
         # step and the engine re-prepares its weight images once per step -- charge that launch to every timed step
         _engine_ops.invalidate_prepared_weights()
-        loss, _ = model_step(net, b, criterion=criterion, device=dev)
+        if ref_model_fn is not None:  # ref: model/unet.py:154-198 model_fn (its own H2D copies, voxelization, CE loss)
+            loss = ref_model_fn(b, net, 0)["loss"]
+        else:
+            loss, _ = model_step(net, b, criterion=criterion, device=dev)
         loss.backward()
         if world > 1 and not args.ddp:
             parallel.allreduce_grads(params, world)  # the path's only collective: gradient mean over ranks (NCCL)
@@ -265,10 +461,10 @@ def main():
                 sampler.sample()  # between two steps, GPU busy with the steps queued so far (see ClockSampler)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
-            if read_loss and i == 0:
+            if read_loss and i == 0 and ref_model_fn is None:
                 nxt = ops.stage_batch(b, dev, tensor_keys)  # step 0 copies its own inputs inside its interval
             cur = nxt
-            if read_loss and i + 1 < nsteps:
+            if read_loss and i + 1 < nsteps and ref_model_fn is None:
                 nxt = ops.stage_batch(b, dev, tensor_keys)  # step i+1's H2D copies overlap step i (all K in the region)
             loss = step(cur)
             if read_loss:
@@ -318,52 +514,29 @@ def main():
     value = scenes_per_step * args.steps / (ms_total / 1e3)
     e2e_val = scenes_per_step * args.steps / (ms_e2e / 1e3)
 
+    peak, how = peaks()
     roof = None
     detail = None
     if not args.no_roofline:
-        # every rank runs this extra step (DDP's gradient all-reduce is a collective); only rank 0 keeps the records
+        # every rank runs this extra step (the gradient all-reduce is a collective); only rank 0 keeps the records
         ops.profile_begin()
         step(resident)
         torch.cuda.synchronize()
         recs = ops.profile_end()
         if rank != 0:
             recs = []
-        gg = [r for r in recs if r["kernel"] == "k_gather_gemm"]
-        if gg:
-            # dominant kernel = the conv gather-GEMM (fwd + dgrad; k_conv_direct on the 16/32-channel layers,
-            # k_conv_tc elsewhere); dominant LAUNCH SHAPE = the group of identical launches with the largest total
-            # time.  achieved = algorithmic bytes of one such launch (SURVEY.md 8(d) / DESIGN.md 3) / its average
-            # CUDA-event duration (events on the launch stream).
-            groups = {}
-            for r in gg:
-                groups.setdefault((r["n_out"], r["Cin"], r["Cout"], r["K"], r.get("pairs_mode", 0)), []).append(r)
-            key, grp = max(groups.items(), key=lambda kv: sum(r["ms"] for r in kv[1]))
-            g_ms = sum(r["ms"] for r in grp) / len(grp)
-            g_bytes = conv_layer_bytes(grp[0])
-            tot_ms = sum(r["ms"] for r in gg)
-            tot_bytes = sum(conv_layer_bytes(r) for r in gg)
-            tot_flops = sum(2.0 * r["pairs"] * r["Cin"] * r["Cout"] for r in gg)
-            all_ms = sum(r["ms"] for r in recs)
-            peak, how = peaks()
-            ach = g_bytes / (g_ms * 1e-3) / 1e9
-            traffic = None
-            kname = "k_conv_direct" if (not key[4] and ops._direct_covers(key[3], key[1], key[2])) else "k_conv_tc"
-            tpath = os.path.join(ROOT, "profiles", "traffic.json")  # dram bytes per launch from `ncu --set full`
-            if os.path.exists(tpath):
-                for t in json.load(open(tpath)).get(kname, []):
-                    if (t["Cin"], t["Cout"], t["K"]) == key[1:4] and abs(t["n_out"] - key[0]) <= 0.1 * key[0]:
-                        traffic = t["dram_bytes"]
-            roof = {"bound": "hbm", "kernel": kname, "achieved": ach, "peak": peak, "unit": "GB/s",
-                    "frac": ach / peak, "traffic": traffic, "peak_source": how,
-                    "launch_shape": {"rows": key[0], "Cin": key[1], "Cout": key[2], "K": key[3], "pairs_mode": key[4],
-                                     "launches_per_step": len(grp), "avg_launch_ms": g_ms,
-                                     "algorithmic_bytes": g_bytes},
-                    "all_conv_launches": {"launches_per_step": len(gg), "total_ms": tot_ms,
-                                          "algorithmic_GBs": tot_bytes / (tot_ms * 1e-3) / 1e9,
-                                          "useful_dense_tflops": tot_flops / (tot_ms * 1e-3) / 1e12,
-                                          "share_of_engine_kernel_time": tot_ms / max(all_ms, 1e-9)}}
-            detail = recs
-    cpu_base = None
+        roof = roofline_from_records(recs, peak, how)
+        detail = recs
+    pm_levels = None
+    if rank == 0:
+        pm_levels = pairs_per_level(model, resident, dev, ref_model_fn is not None)
+    gpu_native = None
+    if rank == 0 and world == 1 and not args.no_gpu_native:
+        gpu_native = run_gpu_native(model, batch, dev, value_ms=ms_total / args.steps, bs=args.bs)
+    m32 = None
+    if rank == 0 and world == 1 and not args.no_m32 and args.mid != 32 and ref_model_fn is None:
+        m32 = run_other_width(32, batch, dev, model_step, SparseConvNet, ops, flush)
+    cpu_base = parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N=1 only (rank 0, the box's host cores)
         from oracle.unet_ref import model_step_ref
         cores = os.cpu_count() or 1
@@ -371,26 +544,42 @@ def main():
         sd = {k: v.detach().cpu().clone().requires_grad_(v.dtype.is_floating_point)
               for k, v in model.state_dict().items()}
         t0 = time.perf_counter()
-        loss_c, _ = model_step_ref(sd, batch, training=True)
+        loss_c, scores_c = model_step_ref(sd, batch, training=True)
         loss_c.backward()
         dt = time.perf_counter() - t0
         cpu_base = {"value": args.bs / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                     "sample": "1 full step (bs=%d x %dk voxels, m=%d) of the CPU oracle, %.1f s"
                               % (args.bs, args.voxels // 1000, args.mid, dt)}
+        # parity AT the full size: the engine's forward on the same weights / batch against the fp32 CPU oracle
+        with torch.no_grad():
+            if ref_model_fn is not None:
+                r = ref_model_fn(resident, net, 0)
+                loss_g, scores_g = r["loss"], r["output"]
+            else:
+                loss_g, scores_g = model_step(net, resident, criterion=criterion, device=dev)
+        sc = scores_c.detach().double()
+        parity = {"scores_rel": float((scores_g.double().cpu() - sc).abs().max() / sc.abs().max()),
+                  "loss_abs": abs(float(loss_g) - float(loss_c.detach())), "oracle": "fp32 CPU port (oracle/unet_ref.py)",
+                  "points": int(sc.shape[0]), "bar": "scores_rel <= 1e-4 (north_star); tests/test_fullsize_gpu.py holds "
+                                                     "the same comparison against the fp64 oracle"}
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": "2x150k-voxel ScanNet-shape scenes, full SparseConvNet fwd+bwd, bs=%d, m=%d"
-                          % (args.bs, args.mid), "voxels_per_scene": args.voxels, "scenes_per_gpu": args.bs,
-                          "mid_channel": args.mid, "parallelism": "dp%d (whole scenes per rank, %s)"
+               "config": {"workload": WORKLOAD % (args.bs, args.mid), "voxels_per_scene": args.voxels,
+                          "scenes_per_gpu": args.bs,
+                          "mid_channel": args.mid, "model": "doda_b200/unet.py (mirror of the reference model)" if
+                          ref_model_fn is None else "reference model/unet.py + unet_block.py + model_fn, unchanged, via compat/",
+                          "parallelism": "dp%d (whole scenes per rank, %s)"
                           % (world, "DDP grad all-reduce" if args.ddp else "one in-place NCCL gradient mean after backward"), "l2": "256 MB flush between timed steps",
                           "settle": "%d further untimed steps through the timing harness before each timed loop"
-                          % SETTLE},
+                          % SETTLE, "levels": pm_levels},
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                        "ms_per_step": ms_e2e / args.steps,
                        "h2d": "pinned host -> device on the engine's index stream (ops.stage_batch): step i+1's inputs are "
-                              "copied while step i computes, step 0 copies its own; all K copies inside the timed region",
+                              "copied while step i computes, step 0 copies its own; all K copies inside the timed region"
+                       if ref_model_fn is None else "the reference's test_model_feat copies the pinned host batch itself "
+                                                    "(.cuda(non_blocking=True), model/unet.py:79-84) every step",
                        "loss_read": "async 4-byte copy to pinned memory every step; the host reads step i-1's value "
                                     "during step i and the last one before the closing sync (all K inside the timed "
                                     "region)"},
@@ -398,8 +587,15 @@ def main():
                "step_ms_rank0": steps_ms, "cuda_mallocs_in_timed_steps": mallocs}
         if roof:
             out["roofline"] = roof
+        if gpu_native:
+            out["baseline_gpu_native"] = gpu_native
+            out["vs_gpu_native"] = gpu_native["vs_gpu_native"]
+        if m32:
+            out["m32"] = m32
         if cpu_base:
             out["cpu_baseline"] = cpu_base
+        if parity:
+            out["parity_full_size"] = parity
         print(json.dumps(out))
         if args.detail and detail is not None:
             with open(args.detail, "w") as f:

@@ -10,6 +10,7 @@
 namespace b200sp {
 
 void set_error(const char* fmt, ...);
+void note_kernel(const char* name);  // b200sp_last_kernel(): which kernel family a dispatching entry point chose
 
 #define B200SP_CHECK_ARG(cond, ...)                  \
     do {                                             \

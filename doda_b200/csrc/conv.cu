@@ -507,6 +507,7 @@ extern "C" int b200sp_gather_gemm(const float* in, int64_t n_in, int Cin, const 
     p.in = in; p.W = Wuse; p.tab = tab; p.orow = orow; p.out = out;
     p.n_rows = n_out; p.Cin = Cin; p.Cout = Cout; p.K = K;
     p.accumulate = accumulate; p.pairs_mode = 0;
+    note_kernel("k_gather_gemm");
     return dispatch_gg(p, n_out, 1, st);
 }
 
@@ -531,6 +532,7 @@ extern "C" int b200sp_gather_gemm_pairs(const float* in, int Cin, const float* W
     p.in = in; p.W = Wuse; p.pin = pin; p.pout = pout; p.pairnum = pairnum_dev; p.out = out;
     p.pstride = pstride; p.Cin = Cin; p.Cout = Cout; p.K = K;
     p.accumulate = accumulate; p.pairs_mode = 1;
+    note_kernel("k_gather_gemm");
     return dispatch_gg(p, n_upper, K, st);
 }
 
@@ -555,6 +557,7 @@ extern "C" int b200sp_wgrad(const float* a, int Ca, const float* b, int Cb, cons
     int64_t ppb = 4096;
     while (ppb > 256 && cdiv(nmax, ppb) * K * tiles < 2 * 148) ppb >>= 1;
     p.ppb = (int)ppb;
+    note_kernel("k_wgrad");
     dim3 grid((unsigned)cdiv(nmax, ppb), K, tiles);
     k_wgrad<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     B200SP_LAUNCH_CHECK();

@@ -240,6 +240,7 @@ int conv_direct_run(const float* in, int Cin, const float* W, int wflags, const 
     if (!tab && K != 1) return B200SP_EUNSUP;
     B200SP_CHECK_ARG((((uintptr_t)in | (uintptr_t)out | (uintptr_t)W) & 15) == 0, "conv_direct: pointers must be 16-byte aligned");
     DirectParams p{};
+    note_kernel("k_conv_direct");
     p.in = in; p.W = W; p.tab = tab; p.orow = orow; p.rowmask = rowmask; p.out = out;
     p.n_rows = n_rows; p.K = K; p.Cin = Cin; p.Cout = Cout;
     p.transposed = wflags & 1; p.mirror = (wflags >> 1) & 1; p.accumulate = accumulate;

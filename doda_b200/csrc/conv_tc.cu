@@ -24,6 +24,9 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <algorithm>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 #include <stdlib.h>
 #include <string.h>
@@ -70,7 +73,10 @@ struct TCParams {
     int ni;                 // MMA issuer warps in use (accumulators per set)
     int row_tiles;          // ceil(n_rows / 128)
     int total_tiles;        // row_tiles * (pairs_mode ? K : 1)
-    int nsplit;             // table mode: the active offsets of a row tile are dealt to nsplit CTAs (atomic epilogue)
+    int nsplit;             // table mode: the active offsets of a row tile are dealt to nsplit CTAs; their partial sums
+                            // go to `partial` and the LAST CTA of the row tile adds them in split order (deterministic)
+    float* partial;         // [nsplit][row_tiles * 128][Cout_pad] (split mode only)
+    int* tickets;           // [row_tiles] arrival counters, zero on entry and reset to zero by the reducing CTA
     int dbg;                // dev only: 1 no MMAs, 2 no gathers, 4 no transform, 8 no epilogue data, 16 no table copy/mask, 32 no weight copies
 };
 
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
     uint64_t* acce = accf + TC_NBUF;      // [NBUF] accumulator set drained -> issuers
     uint64_t* tload = acce + TC_NBUF;     // [NBUF] bulk copy of the tile's table rows landed (prefetcher only)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tload + TC_NBUF);
+    int* s_flag = reinterpret_cast<int*>(s_tmem + 1);  // epilogue warps, split mode: "this CTA reduces the row tile"
 
     const int ntiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -174,6 +181,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
 #define TC_KLIST(b) (TC_META(b) + TC_BM * KT + TC_BM)
 #define TC_NK(b) (TC_META(b)[TC_BM * KT + TC_BM + TC_MAXK])
 #define TC_KFIX(b) (TC_META(b)[TC_BM * KT + TC_BM + TC_MAXK + 1])
+#define TC_NPOS(b) (TC_META(b)[TC_BM * KT + TC_BM + TC_MAXK + 2])  // active offsets of the row tile (all splits)
 
     if (warp == TC_W_TILE) {
         // ========== tile prefetcher ==========
@@ -262,6 +270,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                         }
                     TC_NK(b) = nk;
                     TC_KFIX(b) = 0;
+                    TC_NPOS(b) = pos;
                 }
             }
             __syncwarp();
@@ -384,6 +393,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             const int nused = min(ni, nit);
             const uint32_t set_col = tmem + (uint32_t)(b * ni * p.Cout_pad);
             const bool split_mode = p.nsplit > 1;
+            const int tile = (int)blockIdx.x + i * (int)gridDim.x;
+            const int rt = split_mode ? tile / p.nsplit : 0, split = split_mode ? tile - rt * p.nsplit : 0;
+            const int npos = TC_NPOS(b);
+            // split mode: this CTA's partial sums of the tile, row r of the tile at partial[split][rt * 128 + r][:]
+            float* part = split_mode ? p.partial + ((size_t)split * p.row_tiles * TC_BM + (size_t)rt * TC_BM + q4 * 32 + lane) * p.Cout_pad
+                                     : nullptr;
             for (int ch = 0; ch * 16 < (((split_mode && nit == 0) || (p.dbg & 8)) ? 0 : p.Cout_pad); ++ch) {
                 float v[16];
 #pragma unroll
@@ -395,22 +410,20 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) v[e] += t[e];
                 }
+                if (split_mode) {
+#pragma unroll
+                    for (int g4 = 0; g4 < 4; ++g4)
+                        __stcg(reinterpret_cast<float4*>(part + ch * 16 + g4 * 4),
+                               make_float4(v[g4 * 4 + 0], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]));
+                    continue;
+                }
                 if (orow < 0) continue;
                 float* o = p.out + (int64_t)orow * Cout + ch * 16;
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
                     const int col = ch * 16 + g4 * 4;
                     if (col >= Cout) break;
-                    if (split_mode) {
-                        if (vecO) {
-                            atomicAdd(reinterpret_cast<float4*>(o + g4 * 4),
-                                      make_float4(v[g4 * 4 + 0], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]));
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                if (col + e < Cout) atomicAdd(o + g4 * 4 + e, v[g4 * 4 + e]);
-                        }
-                    } else if (vecO) {
+                    if (vecO) {
                         float4 wv = make_float4(v[g4 * 4 + 0], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
                         if (p.accumulate) {
                             const float4 old = *reinterpret_cast<const float4*>(o + g4 * 4);
@@ -435,6 +448,50 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                 if (lane == 0) mbar_arrive(&acce[b]);
             }
             g0 += nit;
+            if (split_mode) {
+                // the last of the row tile's nsplit CTAs to arrive adds the partial sums in split order 0, 1, ...:
+                // the same summation order whatever the arrival order (no float atomics on the output)
+                __threadfence();
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                if (q4 == 0 && lane == 0) {
+                    const int t = atomicAdd(p.tickets + rt, 1);
+                    const int last = (t == p.nsplit - 1);
+                    if (last) p.tickets[rt] = 0;  // ready for the next launch on this stream
+                    *s_flag = last;
+                }
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");
+                const int last = *reinterpret_cast<volatile int*>(s_flag);
+                if (last && !(p.dbg & 8)) {
+                    __threadfence();
+                    const int nact = min(p.nsplit, npos);  // splits that were dealt at least one offset
+                    const float* p0 = p.partial + ((size_t)rt * TC_BM + q4 * 32 + lane) * p.Cout_pad;
+                    const size_t sstride = (size_t)p.row_tiles * TC_BM * p.Cout_pad;
+                    if (orow >= 0) {
+                        for (int c4 = 0; c4 * 4 < Cout; ++c4) {
+                            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                            for (int sp = 0; sp < nact; ++sp) {
+                                const float4 t = __ldcg(reinterpret_cast<const float4*>(p0 + sp * sstride + c4 * 4));
+                                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                            }
+                            float* o = p.out + (int64_t)orow * Cout + c4 * 4;
+                            const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+                            if (vecO) {
+                                float4 wv = acc;
+                                if (p.accumulate) {
+                                    const float4 old = *reinterpret_cast<const float4*>(o);
+                                    wv.x += old.x; wv.y += old.y; wv.z += old.z; wv.w += old.w;
+                                }
+                                *reinterpret_cast<float4*>(o) = wv;
+                            } else {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    if (c4 * 4 + e < Cout) o[e] = p.accumulate ? o[e] + av[e] : av[e];
+                            }
+                        }
+                    }
+                }
+                asm volatile("bar.sync 1, 128;\n" ::: "memory");  // s_flag is reused by the next tile
+            }
         }
     } else if (warp >= TC_W_MMA && warp < TC_W_MMA + TC_MAX_ISSUERS) {
         // ========== MMA issuers: warp w owns the global stages g = w (mod ni) and accumulator w of each set.  The whole
@@ -532,6 +589,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
 #undef TC_KLIST
 #undef TC_NK
 #undef TC_KFIX
+#undef TC_NPOS
     tc_fence_before();
     __syncthreads();
     if (warp == TC_W_MMA) tmem_dealloc(tmem, p.tmem_cols);
@@ -673,6 +731,43 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
     return true;
 }
 
+// Scratch of the deterministic split-K reduction, owned by the library: one grow-only buffer per stream (launches on
+// one stream are ordered, so they can share it) plus a zero-initialised ticket array that every launch leaves zeroed.
+struct SplitScratch {
+    float* partial = nullptr;
+    int* tickets = nullptr;
+    size_t bytes = 0;
+};
+static constexpr int TC_MAX_TICKETS = 1024;
+static int split_scratch(cudaStream_t st, size_t bytes, int row_tiles, float** partial, int** tickets) {
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, SplitScratch> tab;
+    if (row_tiles > TC_MAX_TICKETS) return B200SP_EUNSUP;
+    int dev = 0;
+    B200SP_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    SplitScratch& sc = tab[std::make_pair(dev, st)];
+    if (!sc.tickets) {
+        B200SP_CUDA(cudaMalloc(&sc.tickets, TC_MAX_TICKETS * sizeof(int)));
+        B200SP_CUDA(cudaMemsetAsync(sc.tickets, 0, TC_MAX_TICKETS * sizeof(int), st));
+    }
+    if (sc.bytes < bytes) {
+        // earlier launches on this stream may still read the old buffer: free it only once the stream has drained
+        if (sc.partial) {
+            B200SP_CUDA(cudaStreamSynchronize(st));
+            B200SP_CUDA(cudaFree(sc.partial));
+            sc.partial = nullptr;
+            sc.bytes = 0;
+        }
+        const size_t want = std::max(bytes + bytes / 2, (size_t)(8u << 20));
+        B200SP_CUDA(cudaMalloc(&sc.partial, want));
+        sc.bytes = want;
+    }
+    *partial = sc.partial;
+    *tickets = sc.tickets;
+    return B200SP_OK;
+}
+
 template <int KC>
 static int launch_tc(const TCParams& p, int KT, cudaStream_t st) {
     using L = TCLayout<KC>;
@@ -713,6 +808,7 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
                                                pl.Cout_pad, Wp);
         B200SP_LAUNCH_CHECK();
     }
+    note_kernel("k_conv_tc");
     TCParams p{};
     p.in = in; p.Wp = Wp; p.tab = tab; p.orow = orow; p.rowmask = rowmask; p.pin = pin; p.pout = pout; p.pairnum = pairnum; p.out = out;
     p.n_rows = n_rows; p.pstride = pstride; p.Cin = Cin; p.Cout = Cout; p.K = K;
@@ -724,13 +820,17 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
     }
     p.row_tiles = (int)cdiv(n_rows, TC_BM);
     // few row tiles (deep U-Net levels): deal each tile's active offsets to nsplit CTAs so the machine is not idle
-    // behind two or three serial tiles; the partial sums meet in the output through float4 atomics
+    // behind two or three serial tiles; the partial sums are added in split order by the row tile's last CTA
     p.nsplit = 1;
     if (!pairs_mode && tab && K > 1 && p.row_tiles * 2 <= num_sms()) {
         B200SP_ENV_INT(env_nosplit, "B200SP_TC_NOSPLIT", 0);
         if (!env_nosplit) p.nsplit = std::max(1, std::min(K, 2 * num_sms() / p.row_tiles));
     }
-    if (p.nsplit > 1 && !accumulate) B200SP_CUDA(cudaMemsetAsync(out, 0, (size_t)n_rows * Cout * sizeof(float), st));
+    if (p.nsplit > 1) {
+        int rc = split_scratch(st, (size_t)p.nsplit * p.row_tiles * TC_BM * pl.Cout_pad * sizeof(float), p.row_tiles,
+                               &p.partial, &p.tickets);
+        if (rc) return rc;
+    }
     p.total_tiles = p.row_tiles * (pairs_mode ? K : p.nsplit);
     if (pl.KC == 32) return launch_tc<32>(p, KT, st);
     if (pl.KC == 16) return launch_tc<16>(p, KT, st);

@@ -19,6 +19,9 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static thread_local const char* g_kernel = "";
+void note_kernel(const char* name) { g_kernel = name; }
+
 static std::atomic<long long> g_launches{0};
 void add_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long get_launches() { return g_launches.load(std::memory_order_relaxed); }
@@ -53,7 +56,8 @@ struct Key4Hash {
 using namespace b200sp;
 
 extern "C" const char* b200sp_last_error(void) { return g_err; }
-extern "C" int b200sp_version(void) { return 100; }
+extern "C" const char* b200sp_last_kernel(void) { return g_kernel; }
+extern "C" int b200sp_version(void) { return 200; }
 extern "C" int64_t b200sp_launch_count(void) { return (int64_t)b200sp::get_launches(); }
 
 // Fork / join of a side stream around independent kernels of one layer (the weight gradient next to dgrad + BN

@@ -57,6 +57,12 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restric
 #pragma unroll
     for (int v = 0; v < VEC; ++v) a0[v] = a1[v] = 0.f;
     float sc[VEC], sh[VEC], mu[VEC], is[VEC];
+    if (MODE == 0 && active) {
+        // statistics are accumulated around row 0's values: var = E[(x-k)^2] - (E[x-k])^2 does not cancel
+        // catastrophically when |mean| >> std (the single-pass E[x^2] - mean^2 loses ~(mean/std)^2 ulps)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) mu[v] = __ldg(x + cg * VEC + v);
+    }
     if (MODE == 1 && active) {
         (void)scale;
         (void)shift;
@@ -99,8 +105,9 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restric
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) {
                     if (MODE == 0) {
-                        a0[v] += xv[u][v];
-                        a1[v] = fmaf(xv[u][v], xv[u][v], a1[v]);
+                        const float d = xv[u][v] - mu[v];
+                        a0[v] += d;
+                        a1[v] = fmaf(d, d, a1[v]);
                     } else {
                         float g = gv[u][v];
                         if (relu && fmaf(xv[u][v], sc[v], sh[v]) <= 0.f) g = 0.f;
@@ -135,33 +142,48 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restric
     __shared__ double s_fold[512];
     const int G = gridDim.x;
     const int E = 2 * C;
-    const int SL = E >= BN_THREADS ? 1 : BN_THREADS / E;
-    for (int i = tid; i < E * SL; i += BN_THREADS) {
-        const int sl = i / E, e = i - sl * E;
-        // eight loads in flight per thread: with two, a 96-entry layer walked 74 dependent L2 round trips here and the
-        // fold, not the reduction, set the kernel's duration (25 us for 27 k rows x 48 channels)
+    // eight loads in flight per thread: with two, a 96-entry layer walked 74 dependent L2 round trips here and the
+    // fold, not the reduction, set the kernel's duration (25 us for 27 k rows x 48 channels)
+    auto fold = [&](int e, int first, int step) {
         double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-        int g = sl;
-        for (; g + 7 * SL < G; g += 8 * SL) {
+        int g = first;
+        for (; g + 7 * step < G; g += 8 * step) {
             float v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = __ldcg(&partial[(int64_t)(g + u * SL) * E + e]);
+            for (int u = 0; u < 8; ++u) v[u] = __ldcg(&partial[(int64_t)(g + u * step) * E + e]);
 #pragma unroll
             for (int u = 0; u < 8; ++u) a[u] += (double)v[u];
         }
-        for (; g < G; g += SL) a[0] += (double)__ldcg(&partial[(int64_t)g * E + e]);
-        s_fold[i] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+        for (; g < G; g += step) a[0] += (double)__ldcg(&partial[(int64_t)g * E + e]);
+        return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+    };
+    // narrow layers (E <= 256 entries): SL slices of the partial rows per entry so that all threads work, slices meet
+    // in shared memory (E * SL <= 256 doubles).  Wide layers (C > 128, up to 1024): one thread per entry folds all
+    // rows itself and nothing is staged -- s_fold is never indexed past E * SL <= 512.
+    const bool sliced = E <= BN_THREADS;
+    const int SL = sliced ? BN_THREADS / E : 1;
+    if (sliced) {
+        for (int i = tid; i < E * SL; i += BN_THREADS) {
+            const int sl = i / E, e = i - sl * E;
+            s_fold[i] = fold(e, sl, SL);
+        }
     }
     __syncthreads();
     for (int c = tid; c < C; c += BN_THREADS) {
         double s0 = 0.0, s1 = 0.0;
-        for (int sl = 0; sl < SL; ++sl) {
-            s0 += s_fold[sl * E + c];
-            s1 += s_fold[sl * E + C + c];
+        if (sliced) {
+            for (int sl = 0; sl < SL; ++sl) {
+                s0 += s_fold[sl * E + c];
+                s1 += s_fold[sl * E + C + c];
+            }
+        } else {
+            s0 = fold(c, 0, 1);
+            s1 = fold(C + c, 0, 1);
         }
         if (MODE == 0) {
-            const double mu = s0 / (double)fin.M;
-            double var = s1 / (double)fin.M - mu * mu;
+            const double dm = s0 / (double)fin.M;  // mean of (x - k), k = row 0's value of this channel
+            const double mu = (double)__ldg(x + c) + dm;
+            double var = s1 / (double)fin.M - dm * dm;
             if (var < 0.0) var = 0.0;
             const float is = (float)(1.0 / sqrt(var + (double)fin.eps));
             fin.mean[c] = (float)mu;

@@ -214,6 +214,7 @@ int wgrad_direct_run(const float* a, int Ca, const float* g, int Cb, const int* 
     B200SP_CHECK_ARG((((uintptr_t)a | (uintptr_t)g | (uintptr_t)dW) & 15) == 0, "wgrad_direct: pointers must be 16-byte aligned");
     if (n_rows <= 0) return B200SP_OK;
     WDParams p{};
+    note_kernel("k_wgrad_direct");
     p.a = a; p.g = g; p.tab = tab; p.orow = orow; p.rowmask = rowmask; p.dW = dW;
     p.n_rows = n_rows; p.K = K; p.Ca = Ca; p.Cb = Cb;
     if (Ca == 16) return Cb == 16 ? launch<1, 1>(p, st) : launch<1, 2>(p, st);

@@ -371,6 +371,7 @@ int wgrad_tc_run(const float* a, int Ca, const float* b, int Cb, const int* pa, 
         B200SP_CUDA(cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
+    note_kernel("k_wgrad_tc");
     dim3 grid((unsigned)cdiv(n_upper, ppb), (unsigned)K);
     k_wgrad_tc<<<grid, WG_THREADS, smem, st>>>(p);
     B200SP_LAUNCH_CHECK();

@@ -40,3 +40,49 @@ def intersection_and_union_ref(output, target, K, ignore_index=255):
     ao = torch.histc(output.float(), bins=K, min=0, max=K - 1)
     at = torch.histc(target.float(), bins=K, min=0, max=K - 1)
     return ai, ao + at - ai, at
+
+
+def packed_epilogue(loss, preds, labels, n_classes, ignore_label=255, dist_train=False):
+    """The per-iteration metric epilogue of the reference's training loop (tool/train.py:107-118 +
+    util/common_utils.py:250-256) in ONE device pass, ONE collective and ONE device->host read.
+
+    The reference all-reduces the loss, the point count and the three per-class histograms separately (5 tiny
+    collectives) and reads them back with `.item()` / three `.cpu()` calls (6+ host syncs per iteration).  Here the
+    histograms come from `b200sp_intersection_union`, everything is packed into one float64 vector
+    [loss * n, n, intersection[K], union[K], target[K]], summed over ranks by one all-reduce, and copied to the host
+    once.  float64 keeps the counts exact (the reference's float32 `histc` counts are exact below 2^24 as well).
+    -> (mean loss over all ranks' points, n_total, intersection, union, target) with numpy float32 histograms like the
+    reference's `update_meter` returns."""
+    K = int(n_classes)
+    inter, union, target = intersectionAndUnionGPU(preds, labels, K, ignore_label)
+    n = preds.shape[0]
+    pack = torch.empty(2 + 3 * K, dtype=torch.float64, device=preds.device)
+    pack[0] = loss.detach().double() * n
+    pack[1] = n
+    pack[2:2 + K] = inter
+    pack[2 + K:2 + 2 * K] = union
+    pack[2 + 2 * K:] = target
+    if dist_train:
+        import torch.distributed as dist
+        dist.all_reduce(pack)
+    host = pack.cpu().numpy()  # the one host sync of the iteration
+    n_tot = int(round(host[1]))
+    f32 = host[2:].astype("float32")
+    return float(host[0] / max(n_tot, 1)), n_tot, f32[:K], f32[K:2 * K], f32[2 * K:]
+
+
+def update_meter(intersection_meter, union_meter, target_meter, preds, labels, n_classes, ignore_label, dist_train):
+    """Drop-in for the reference's `update_meter` (util/common_utils.py:250-256): same arguments, same return tuple
+    (meters, running accuracy, this iteration's intersection / union / target as numpy arrays); the three histograms
+    cross the ranks in one packed all-reduce and reach the host in one copy."""
+    K = int(n_classes)
+    inter, union, target = intersectionAndUnionGPU(preds, labels, K, ignore_label)
+    pack = torch.cat((inter, union, target))
+    if dist_train:
+        import torch.distributed as dist
+        dist.all_reduce(pack)
+    host = pack.cpu().numpy()
+    intersection, union, target = host[:K].copy(), host[K:2 * K].copy(), host[2 * K:].copy()
+    intersection_meter.update(intersection), union_meter.update(union), target_meter.update(target)
+    accuracy = sum(intersection_meter.val) / (sum(target_meter.val) + 1e-10)
+    return intersection_meter, union_meter, target_meter, accuracy, intersection, union, target

@@ -105,6 +105,8 @@ class _Timed(object):
         if _prof is not None:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
+            if self.info.get("kernel") in ("k_gather_gemm", "k_wgrad"):
+                self.info["name"] = lib.b200sp_last_kernel().decode()  # the kernel family the C side dispatched to
             _prof.append((self.info, self.s, e))
         return False
 
@@ -521,10 +523,16 @@ def _bwd_flags(m):
 def prepared_weights(module):
     """-> (image for the forward, image for dgrad) of module.weight, or None when the tensor path does not cover the
     shape / is switched off.  Images are keyed on (data_ptr, _version): the first conv that finds its image stale
-    re-prepares EVERY registered conv layer whose weight changed (one optimizer step -> one launch)."""
+    re-prepares EVERY registered conv layer whose weight changed (one optimizer step -> one launch).
+    NB torch does not bump `_version` for writes through `.data` (`w.data.mul_(a)`, `w.data.copy_(..)`, EMA teachers):
+    call `invalidate_prepared_weights()` after such an update."""
     w = module.weight
     if not (prepare_ahead and w.is_cuda and _conv_impl_name == "tc"):
         return None
+    if module not in _conv_modules:  # copy.deepcopy / pickled modules never ran __init__'s registration
+        _conv_modules.add(module)
+        module.__dict__.pop("_b200sp_prep", None)
+        module.__dict__.pop("_b200sp_img", None)  # a deep copy must not share (and overwrite) the original's images
     key = (w.data_ptr(), w._version)
     st = module.__dict__.get("_b200sp_prep")
     if st is None or st[0] != key:
@@ -619,7 +627,8 @@ def wgrad(a, b, pa, pb, pairnum, n_upper, K, out=None):
         if rc:
             check(rc, "wgrad")
         return dW
-    with _Timed(kernel="k_wgrad", n_rows=a.shape[0], Ca=Ca, Cb=Cb, K=K, n_upper=n_upper):
+    pairs = int(pairnum.sum()) if pairnum is not None else int(n_upper)  # profile pass only (host sync)
+    with _Timed(kernel="k_wgrad", n_rows=a.shape[0], n_b=b.shape[0], Ca=Ca, Cb=Cb, K=K, n_upper=n_upper, pairs=pairs):
         check(lib.b200sp_wgrad(a.data_ptr(), Ca, b.data_ptr(), Cb, pa.data_ptr() if pa is not None else None,
                                pb.data_ptr() if pb is not None else None,
                                pairnum.data_ptr() if pairnum is not None else None, n_upper, K,
@@ -650,7 +659,8 @@ def wgrad_table(a, g, tab, n_rows, K, orow=None, rowmask=None, out=None):
         if rc:
             check(rc, "wgrad_table")
         return dW
-    with _Timed(kernel="k_wgrad", n_rows=a.shape[0], Ca=Ca, Cb=Cb, K=K, n_upper=n_rows):
+    pairs = int((tab >= 0).sum()) if tab is not None else int(n_rows)  # profile pass only (host sync)
+    with _Timed(kernel="k_wgrad", n_rows=a.shape[0], n_b=g.shape[0], Ca=Ca, Cb=Cb, K=K, n_upper=n_rows, pairs=pairs):
         check(lib.b200sp_wgrad_table(a.data_ptr(), Ca, g.data_ptr(), Cb, tab.data_ptr() if tab is not None else None,
                                      orow.data_ptr() if orow is not None else None,
                                      rowmask.data_ptr() if rowmask is not None else None, n_rows, K, dW.data_ptr(),
@@ -884,6 +894,17 @@ def conv_backward_raw(kind, features, filters, grad_out, rb, prep, need_din=True
     return din, dW
 
 
+def _drop_pending_join():
+    """an exception between fork and join must not leave a stale join for the next backward node"""
+    global _pending_join, _wg_stream
+    if _pending_join is not None:
+        try:
+            _join_side(_pending_join)
+        finally:
+            _pending_join = None
+    _wg_stream = None
+
+
 def _bn_forward_raw(x, weight, bias, running_mean, running_var, nbt, momentum, eps, relu):
     M, C = x.shape
     dev = x.device
@@ -955,6 +976,14 @@ class BNReLUConvFunction(Function):
     @staticmethod
     def backward(ctx, grad_out, grad_y):
         x, bn_w, bn_b, stats, y, filters = ctx.saved_tensors
+        try:
+            return BNReLUConvFunction._backward(ctx, grad_out, grad_y, x, bn_w, bn_b, stats, y, filters)
+        except BaseException:
+            _drop_pending_join()
+            raise
+
+    @staticmethod
+    def _backward(ctx, grad_out, grad_y, x, bn_w, bn_b, stats, y, filters):
         dy = dW = None
         if grad_out is not None:
             grad_out = _f32c(grad_out)
@@ -1191,3 +1220,42 @@ class GatherRowsFunction(Function):
 
 def gather_rows(src, idx):
     return GatherRowsFunction.apply(src, idx)
+
+
+class DevoxelizeFunction(Function):
+    """voxel -> point broadcast `features[p2v]` (model/unet.py:62) whose backward is the atomics-free segmented sum
+    over each voxel's point list: d_features[v] = sum_j g[v2p[v][1 + j]] -- the voxelizer's own output_map already
+    holds the segments, so no sort, no atomics, and the same summation order every run."""
+
+    @staticmethod
+    def forward(ctx, src, p2v, v2p):
+        _req_cuda(src, p2v, v2p)
+        src = _f32c(src)
+        p2v = p2v.contiguous()
+        if p2v.dtype not in (torch.int32, torch.int64) or v2p.dtype != torch.int32:
+            raise TypeError("devoxelize: p2v must be int32/int64, v2p int32")
+        n, C = p2v.shape[0], src.shape[1]
+        out = torch.empty((n, C), dtype=_F32, device=src.device)
+        check(lib.b200sp_gather_rows(src.data_ptr(), p2v.data_ptr(), 1 if p2v.dtype == torch.int64 else 0, n, C,
+                                     out.data_ptr(), _stream()), "gather_rows")
+        ctx.save_for_backward(v2p.contiguous())
+        ctx.n_src = src.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (v2p,) = ctx.saved_tensors
+        g = _f32c(g)
+        M, C = ctx.n_src, g.shape[1]
+        d = torch.zeros((M, C), dtype=_F32, device=g.device)
+        check(lib.b200sp_voxelize_fp(g.data_ptr(), d.data_ptr(), v2p.data_ptr(), 0, M, v2p.shape[1] - 1, C, _stream()),
+              "devoxelize_bwd")
+        return d, None, None
+
+
+def devoxelize(src, p2v, v2p=None):
+    """features[p2v]; with the voxel -> points map `v2p` ([M, 1 + maxActive], the voxelizer's output_map) the backward
+    is a deterministic segmented sum, without it a vector-atomic scatter-add"""
+    if v2p is None:
+        return GatherRowsFunction.apply(src, p2v)
+    return DevoxelizeFunction.apply(src, p2v, v2p)

@@ -36,17 +36,48 @@ def allreduce_grads(params, world):
         st = g.untyped_storage()
         if g.is_contiguous() and st.nbytes() >= (1 << 20) and g.numel() * g.element_size() < st.nbytes():
             lo = g.storage_offset()
-            e = spans.setdefault((st.data_ptr(), g.dtype), [g, lo, lo + g.numel()])
+            e = spans.setdefault((st.data_ptr(), g.dtype), [g, lo, lo + g.numel(), 0, []])
             e[1], e[2] = min(e[1], lo), max(e[2], lo + g.numel())
+            e[3] += (g.numel() + 63) // 64 * 64  # the arena hands out 64-float aligned slices
+            e[4].append(g)
         else:
             rest.append(g)
-    for (_, dtype), (g, lo, hi) in spans.items():  # insertion order = backward order: identical on every rank
+    # a span is reduced in place only if these gradients (almost) fill it: anything else living between them in the
+    # arena block (another model's gradients, a stale slice) must not be averaged along
+    for key in [k for k, e in spans.items() if e[3] < 0.98 * (e[2] - e[1])]:
+        rest.extend(spans.pop(key)[4])
+    # every rank must bring the same span lengths (same sequence of arena slices since the block was taken): checked
+    # with one tiny all-gather whenever the signature changes, instead of hanging or corrupting inside NCCL
+    sig = tuple(e[2] - e[1] for e in spans.values()) + (len(rest), sum(g.numel() for g in rest))
+    if sig not in _checked_signatures:
+        mine = torch.tensor(list(sig) + [0] * (32 - len(sig)) if len(sig) <= 32 else [hash(sig) % (1 << 40)] * 32,
+                            dtype=torch.int64, device=grads[0].device)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        if any(not torch.equal(t, mine) for t in every):
+            raise RuntimeError("allreduce_grads: ranks disagree on the gradient layout %s -- a rank-asymmetric backward "
+                               "(skipped step, different need_dw); use torch DDP or reduce per parameter" % (sig,))
+        _checked_signatures.add(sig)
+    for (_, dtype), (g, lo, hi, _, _) in spans.items():  # insertion order = backward order: identical on every rank
         flat = torch.empty(0, dtype=dtype, device=g.device).set_(g.untyped_storage(), lo, (hi - lo,))
         _avg_all_reduce(flat, world)
     if rest:
         flat = torch.cat([g.reshape(-1) for g in rest])
         _avg_all_reduce(flat, world)
         torch._foreach_copy_(rest, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in rest]), rest)])
+
+
+_checked_signatures = set()
+
+
+def broadcast_parameters(module, src=0):
+    """what DistributedDataParallel does at construction (tool/train.py:361): every rank starts from rank `src`'s
+    parameters and buffers.  Call once before training when `allreduce_grads` replaces DDP."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() <= 1:
+        return
+    with torch.no_grad():
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t, src)
 
 
 def max_over_ranks(value, device):

@@ -3,8 +3,6 @@ schema of the reference (dataset/dataset.py:121-187): no dataset or network need
 import numpy as np
 import torch
 
-from . import pointgroup_ops
-
 
 def surface_scene(seed, W=300, D=225, H=135, nbox=14, dropout=0.2):
     """Integer voxel coords [M,3] of a room: floor, 4 partial-height walls, `nbox` boxes (top + 4 sides)."""
@@ -53,9 +51,11 @@ def uniform_scene(seed, n_voxels, occupancy):
     return np.stack(np.unravel_index(flat, (side, side, side)), axis=1).astype(np.int64)
 
 
-def collate(scenes, seed=0, n_classes=11, dup_max=1, ignore_frac=0.05, full_scale_min=128, mode=4):
+def collate(scenes, seed=0, n_classes=11, dup_max=1, ignore_frac=0.05, full_scale_min=128, mode=4, voxelize=None):
     """scenes: list of int64 [M_i,3] voxel coords -> the reference's batch dict (CPU tensors).
-    Points = voxels repeated 1..dup_max times (exercises maxActive > 1), shuffled like the augmentor does."""
+    Points = voxels repeated 1..dup_max times (exercises maxActive > 1), shuffled like the augmentor does.
+    `voxelize(locs, batch_size, mode)`: the CPU voxelizer to collate with; default = the engine's
+    `pointgroup_ops.voxelization_idx` (imported on first use, so that generating scenes loads no native library)."""
     rng = np.random.RandomState(seed + 12345)
     locs, feats, labels, offsets = [], [], [], [0]
     for b, vox in enumerate(scenes):
@@ -75,7 +75,10 @@ def collate(scenes, seed=0, n_classes=11, dup_max=1, ignore_frac=0.05, full_scal
     feats = torch.from_numpy(np.concatenate(feats, 0))
     labels = torch.from_numpy(np.concatenate(labels, 0))
     spatial_shape = np.clip((locs.max(0)[0][1:] + 1).numpy(), full_scale_min, None)  # dataset/dataset.py:176
-    voxel_locs, p2v_map, v2p_map = pointgroup_ops.voxelization_idx(locs, len(scenes), mode)
+    if voxelize is None:
+        from . import pointgroup_ops
+        voxelize = pointgroup_ops.voxelization_idx
+    voxel_locs, p2v_map, v2p_map = voxelize(locs, len(scenes), mode)
     return {"locs": locs, "voxel_locs": voxel_locs, "p2v_map": p2v_map, "v2p_map": v2p_map,
             "locs_float": locs[:, 1:].float(), "feats": feats, "labels": labels,
             "offsets": torch.tensor(offsets, dtype=torch.int32), "spatial_shape": spatial_shape,

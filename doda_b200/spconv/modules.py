@@ -20,6 +20,7 @@ class SparseModule(nn.Module):
 
 
 fuse_conv = True  # run [BatchNorm, ReLU, sparse conv] triplets as one autograd node
+fuse_bn = True    # run BatchNorm-like modules through the engine's kernels (False: call the module itself; A/B tests)
 
 
 def is_sparse_conv(module):
@@ -99,7 +100,7 @@ class SparseSequential(SparseModule):
             if isinstance(input, SparseConvTensor):
                 if input.indices.shape[0] != 0:
                     feats = input.features
-                    if _is_bn_like(module) and feats.is_cuda and feats.dim() == 2:
+                    if fuse_bn and _is_bn_like(module) and feats.is_cuda and feats.dim() == 2:
                         fuse_relu = i + 1 < n and isinstance(mods[i + 1], nn.ReLU)
                         if fuse_conv and fuse_relu and i + 2 < n and is_sparse_conv(mods[i + 2]) \
                                 and feats.dtype == torch.float32:

@@ -95,9 +95,10 @@ class SparseConvNet(nn.Module):
                 mod.weight.data.fill_(1.0)
                 mod.bias.data.fill_(0.0)
 
-    def forward(self, input, input_map, return_mid_feat=False):
+    def forward(self, input, input_map, return_mid_feat=False, v2p_map=None):
         out = self.output_layer(self.unet(self.input_conv(input)))
-        point_feats = _ops.gather_rows(out.features, input_map)  # voxel -> points (model/unet.py:62)
+        # voxel -> points (model/unet.py:62); with the voxelizer's v2p map the backward is an atomics-free segmented sum
+        point_feats = _ops.devoxelize(out.features, input_map, v2p_map)
         scores = self.linear(point_feats)
         return (point_feats, scores) if return_mid_feat else scores
 
@@ -120,7 +121,7 @@ def model_step(model, batch, voxel_mode=4, criterion=None, device="cuda", coords
     batch_size = batch["offsets"].size(0) - 1
     voxel_feats = pointgroup_ops.voxelization(feats, v2p_map, voxel_mode)
     x = spconv.SparseConvTensor(voxel_feats, voxel_coords, batch["spatial_shape"], batch_size)
-    scores = model(x, p2v_map)
+    scores = model(x, p2v_map, v2p_map=v2p_map) if isinstance(model, SparseConvNet) else model(x, p2v_map)
     if criterion is None:  # the engine's one-pass cross-entropy (same result as nn.CrossEntropyLoss(ignore_index=255))
         loss = _ops.cross_entropy(scores, labels, ignore_index=255)
     else:

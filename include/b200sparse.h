@@ -33,6 +33,10 @@ const char* b200sp_last_error(void);
 int b200sp_version(void);
 /* number of CUDA kernels this library has launched in this process (bench.py: gpu_launches) */
 int64_t b200sp_launch_count(void);
+/* name of the conv / weight-gradient kernel family the last b200sp_gather_gemm* / b200sp_wgrad* call of this thread
+ * dispatched to ("k_conv_direct", "k_conv_tc", "k_gather_gemm", "k_wgrad_direct", "k_wgrad_os", "k_wgrad_tc",
+ * "k_wgrad"); bench.py labels its per-kernel roofline rows with it. */
+const char* b200sp_last_kernel(void);
 /* fork / join of a side stream (cudaEventRecord + cudaStreamWaitEvent in one call): the host runs a layer's weight
  * gradient on a side stream next to its dgrad + BN backward.  Events are created once and reused. */
 int b200sp_event_create(void** event_out);

@@ -42,11 +42,25 @@ def _residual(sd, pre, t, key, training):
     return _Sp(h + skip, t.idx, t.shape, t.bs, t.rbs)
 
 
+def _vgg(sd, pre, t, key, training):
+    # model/unet_block.py:41-52 (block_residual: False): BN-ReLU-SubM3, no skip
+    h = _bn_relu(sd, pre + ".conv_layers.0", t.f, training)
+    h = _subm3(sd, pre + ".conv_layers.2.weight", _Sp(h, t.idx, t.shape, t.bs, t.rbs), key)
+    return _Sp(h, t.idx, t.shape, t.bs, t.rbs)
+
+
+def _block(sd, pre, t, key, training):
+    # the block type is read off the state_dict keys (ResidualBlock has a conv_branch, VGGBlock has conv_layers)
+    if (pre + ".conv_layers.2.weight") in sd:
+        return _vgg(sd, pre, t, key, training)
+    return _residual(sd, pre, t, key, training)
+
+
 def _ublock(sd, pre, t, level, nlevels, reps, training):
     # model/unet_block.py:87-100
     key = "subm%d" % level
     for i in range(reps):
-        t = _residual(sd, "%s.blocks.block%d" % (pre, i), t, key, training)
+        t = _block(sd, "%s.blocks.block%d" % (pre, i), t, key, training)
     if level < nlevels:
         skip = t.f
         h = _bn_relu(sd, pre + ".conv.0", t.f, training)
@@ -57,7 +71,7 @@ def _ublock(sd, pre, t, level, nlevels, reps, training):
         up = indice_conv_ref(h, sd[pre + ".deconv.2.weight"], pairs, pairnum, t.f.shape[0], inverse=True)
         t = _Sp(torch.cat((skip, up), dim=1), t.idx, t.shape, t.bs, t.rbs)
         for i in range(reps):
-            t = _residual(sd, "%s.blocks_tail.block%d" % (pre, i), t, key, training)
+            t = _block(sd, "%s.blocks_tail.block%d" % (pre, i), t, key, training)
     return t
 
 
@@ -91,3 +105,26 @@ def model_step_ref(sd, batch, training=True):
                               batch["offsets"].shape[0] - 1, batch["p2v_map"].numpy(), training)
     loss = F.cross_entropy(scores, batch["labels"], ignore_index=255)
     return loss, scores
+
+
+def encoder_decoder_ref(weights_down, weights_up, bn_down, bn_up, x, coords, spatial_shape, batch_size, training=True):
+    """BASELINE configs[3]: the stride-2 SparseConv3d / SparseInverseConv3d encoder-decoder of UBlock
+    (model/unet_block.py:67-79) without the SubM blocks.  weights_down[l] / weights_up[l]: [2,2,2,Cin,Cout] filters of
+    level l's down conv / inverse conv; bn_down[l] / bn_up[l]: (weight, bias) of the BatchNorm in front of each (None =
+    no BN/ReLU).  -> features on the input's own active set [M, C0]."""
+    idx = np.asarray(coords, dtype=np.int64)
+    shape = [int(s) for s in spatial_shape]
+    stack, f = [], x
+    for l, W in enumerate(weights_down):
+        if bn_down is not None:
+            f = F.relu(F.batch_norm(f, None, None, bn_down[l][0], bn_down[l][1], True, 0.1, 1e-4))
+        outids, pairs, pairnum, oshape = get_indice_pairs_ref(idx, batch_size, shape, 2, 2, 0, 1, subm=False)
+        stack.append((pairs, pairnum, f.shape[0]))
+        f = indice_conv_ref(f, W, pairs, pairnum, outids.shape[0])
+        idx, shape = outids, oshape
+    for l in reversed(range(len(weights_up))):
+        pairs, pairnum, n_fine = stack[l]
+        if bn_up is not None:
+            f = F.relu(F.batch_norm(f, None, None, bn_up[l][0], bn_up[l][1], True, 0.1, 1e-4))
+        f = indice_conv_ref(f, weights_up[l], pairs, pairnum, n_fine, inverse=True)
+    return f

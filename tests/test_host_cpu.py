@@ -196,3 +196,28 @@ def test_staging_and_metrics_refuse_cpu_devices():
     ri, ru, rt = metrics.intersection_and_union_ref(torch.tensor([0, 1, 2, 3, 4, 6, 1, 1]),
                                                     torch.tensor([0, 1, 1, 255, 4, 2, 255, 0]), 5)
     assert ri.tolist() == [1, 1, 0, 0, 1] and ru.tolist() == [2, 3, 2, 0, 1] and rt.tolist() == [2, 2, 1, 0, 1]
+
+
+def test_reference_arm_imports_load_no_product_library():
+    """bench.py --impl reference must time the CPU oracle with none of the product's native code in the process
+    (VERDICT r1 weak #9): scenes are numpy, the collate uses the oracle's voxelizer"""
+    import subprocess
+    code = ("import sys; sys.path.insert(0, %r); import bench; b = bench._oracle_batch(1, 1500); "
+            "maps = open('/proc/self/maps').read(); "
+            "assert 'libb200sparse' not in maps and '_b200fast' not in maps, 'product .so loaded'; "
+            "assert b['voxel_locs'].shape[0] == 1500; print('ok')") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_staged_reference_files_match_their_manifest():
+    from oracle import stage_ref
+    if stage_ref.staged_root() is None:
+        pytest.skip("nothing staged (needs /root/reference once: python -m oracle.stage_ref)")
+    assert stage_ref.verify()
+    if os.path.isdir("/root/reference"):
+        import filecmp
+        for rel in stage_ref.FILES:
+            src = os.path.join("/root/reference", rel)
+            if os.path.exists(src):
+                assert filecmp.cmp(src, os.path.join(stage_ref.DST, rel), shallow=False), rel

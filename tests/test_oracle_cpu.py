@@ -173,3 +173,63 @@ def test_metric_restatement_matches_reference_golden():
         ai, au, at = metrics.intersection_and_union_ref(torch.from_numpy(z["c%d/pred" % i]), torch.from_numpy(z["c%d/label" % i]), K, 255)
         assert np.array_equal(ai.numpy(), z["c%d/intersection" % i])
         assert np.array_equal(au.numpy(), z["c%d/union" % i]) and np.array_equal(at.numpy(), z["c%d/target" % i])
+
+
+@pytest.mark.parametrize("name", ["six", "rand4_m3", "rand4_m4", "big_m4"])
+def test_numpy_voxelizer_matches_reference_golden(name):
+    """oracle/voxelize.py (collate step of bench.py's reference arm) against fixtures produced by the reference's own
+    compiled voxelize_idx (tests/golden/make_golden.py)"""
+    import os
+    from oracle.voxelize import voxelize_idx_ref
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxelize_idx.npz"))
+    bs, mode = g[name + "/args"]
+    oc, im, om = voxelize_idx_ref(g[name + "/coords"], int(bs), int(mode))
+    assert np.array_equal(oc.numpy(), g[name + "/out_coords"])
+    assert np.array_equal(im.numpy(), g[name + "/input_map"])
+    assert np.array_equal(om.numpy(), g[name + "/output_map"])
+
+
+def test_gpu_native_baseline_is_the_oracles_algorithm():
+    """baseline/gpu_native.py (stock torch ops, its own sort + searchsorted rulebooks) and oracle/unet_ref.py (numpy
+    rulebooks) are two independent statements of spconv v1.2's native algorithm: identical in fp64 on CPU tensors,
+    forward and backward, residual net"""
+    import json
+    import os
+    from baseline.gpu_native import NativeUNet, voxelize_mean
+    from oracle.voxelize import voxelize_idx_ref, init_state_dict
+    from oracle.unet_ref import model_step_ref
+    from doda_b200 import scenes
+    shapes = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "unet_state_dict.json")))["m16"]
+    sd = init_state_dict(shapes, seed=1)
+    batch = scenes.collate([scenes.scene_with_voxels(0, 2500), scenes.scene_with_voxels(1, 2000)], dup_max=2,
+                           voxelize=voxelize_idx_ref)
+    sd64 = {k: (v.double().clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    b64 = dict(batch)
+    b64["feats"] = batch["feats"].double()
+    l64, s64 = model_step_ref(sd64, b64, True)
+    l64.backward()
+    net = NativeUNet({k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}, torch.device("cpu"))
+    net.build_rulebooks(batch["voxel_locs"], batch["spatial_shape"])
+    loss, scores = net.step(voxelize_mean(batch["feats"].double(), batch["v2p_map"]), batch["p2v_map"].long(),
+                            batch["labels"])
+    assert abs(float(loss.detach()) - float(l64.detach())) <= 1e-12
+    assert float((scores.detach() - s64.detach()).abs().max()) <= 1e-10
+    for k in ("input_conv.0.weight", "unet.u.u.conv.2.weight", "unet.u.deconv.2.weight", "linear.weight"):
+        r = sd64[k].grad
+        assert float((net.sd[k].grad - r).abs().max() / r.abs().max()) <= 1e-9, k
+
+
+def test_encoder_decoder_oracle_restores_the_active_set_and_is_linear_without_bn():
+    from helpers import surface_coords
+    from oracle.unet_ref import encoder_decoder_ref
+    coords, shape = surface_coords(7, 3000, 1)
+    planes = [4, 8, 12]
+    torch.manual_seed(0)
+    wd = [torch.randn(2, 2, 2, planes[i], planes[i + 1], dtype=torch.float64) for i in range(2)]
+    wu = [torch.randn(2, 2, 2, planes[i + 1], planes[i], dtype=torch.float64) for i in range(2)]
+    x1 = torch.randn(coords.shape[0], 4, dtype=torch.float64)
+    x2 = torch.randn(coords.shape[0], 4, dtype=torch.float64)
+    f = lambda x: encoder_decoder_ref(wd, wu, None, None, x, coords, shape, 1)
+    y = f(2 * x1 - 3 * x2)
+    assert y.shape == x1.shape
+    assert float((y - (2 * f(x1) - 3 * f(x2))).abs().max()) <= 1e-9 * float(y.abs().max())
