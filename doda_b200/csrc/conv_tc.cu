@@ -97,7 +97,7 @@ struct TCLayout {
         return (o + 15u) & ~15u;
     }
     __host__ __device__ static uint32_t total(int nslots, int nslots_b, uint32_t stageB, int KT) {
-        return offBars(nslots, nslots_b, stageB, KT) + (uint32_t)(3 * nslots + 2 * nslots_b + 5 * TC_NBUF) * 8u + 16u;
+        return offBars(nslots, nslots_b, stageB, KT) + (uint32_t)(3 * nslots + 2 * nslots_b + 5 * TC_NBUF) * 8u + 16u + TC_BM * 4u;
     }
 };
 
@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
     uint64_t* tload = acce + TC_NBUF;     // [NBUF] bulk copy of the tile's table rows landed (prefetcher only)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tload + TC_NBUF);
     int* s_flag = reinterpret_cast<int*>(s_tmem + 1);  // epilogue warps, split mode: "this CTA reduces the row tile"
+    int* s_orow = reinterpret_cast<int*>(s_tmem + 4);  // [128] output rows of the tile being reduced (split mode)
 
     const int ntiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -383,6 +384,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             mbar_wait(&tready[b], ph);
             const int nit = TC_NK(b) * nchunks;
             const int orow = TC_OROW(b)[q4 * 32 + lane];
+            const int npos = TC_NPOS(b);  // read before the metadata buffer is handed back to the prefetcher
             __syncwarp();
             if (lane == 0) mbar_arrive(&tfree[b]);
             if (nit > 0) {
@@ -395,7 +397,6 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             const bool split_mode = p.nsplit > 1;
             const int tile = (int)blockIdx.x + i * (int)gridDim.x;
             const int rt = split_mode ? tile / p.nsplit : 0, split = split_mode ? tile - rt * p.nsplit : 0;
-            const int npos = TC_NPOS(b);
             // split mode: this CTA's partial sums of the tile, row r of the tile at partial[split][rt * 128 + r][:]
             float* part = split_mode ? p.partial + ((size_t)split * p.row_tiles * TC_BM + (size_t)rt * TC_BM + q4 * 32 + lane) * p.Cout_pad
                                      : nullptr;
@@ -451,6 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             if (split_mode) {
                 // the last of the row tile's nsplit CTAs to arrive adds the partial sums in split order 0, 1, ...:
                 // the same summation order whatever the arrival order (no float atomics on the output)
+                s_orow[q4 * 32 + lane] = orow;
                 __threadfence();
                 asm volatile("bar.sync 1, 128;\n" ::: "memory");
                 if (q4 == 0 && lane == 0) {
@@ -463,30 +465,46 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                 const int last = *reinterpret_cast<volatile int*>(s_flag);
                 if (last && !(p.dbg & 8)) {
                     __threadfence();
+                    // flat, coalesced walk over the tile's [rows_valid][Cout_pad] block: consecutive threads take
+                    // consecutive float4; per element the nact partials are loaded eight at a time (independent
+                    // loads in flight) and added in split order
                     const int nact = min(p.nsplit, npos);  // splits that were dealt at least one offset
-                    const float* p0 = p.partial + ((size_t)rt * TC_BM + q4 * 32 + lane) * p.Cout_pad;
-                    const size_t sstride = (size_t)p.row_tiles * TC_BM * p.Cout_pad;
-                    if (orow >= 0) {
-                        for (int c4 = 0; c4 * 4 < Cout; ++c4) {
-                            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                            for (int sp = 0; sp < nact; ++sp) {
-                                const float4 t = __ldcg(reinterpret_cast<const float4*>(p0 + sp * sstride + c4 * 4));
-                                acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-                            }
-                            float* o = p.out + (int64_t)orow * Cout + c4 * 4;
-                            const float av[4] = {acc.x, acc.y, acc.z, acc.w};
-                            if (vecO) {
-                                float4 wv = acc;
-                                if (p.accumulate) {
-                                    const float4 old = *reinterpret_cast<const float4*>(o);
-                                    wv.x += old.x; wv.y += old.y; wv.z += old.z; wv.w += old.w;
-                                }
-                                *reinterpret_cast<float4*>(o) = wv;
-                            } else {
+                    const int cp4 = p.Cout_pad >> 2;
+                    const int rows_valid = (int)min((int64_t)TC_BM, p.n_rows - (int64_t)rt * TC_BM);
+                    const float4* p0 = reinterpret_cast<const float4*>(p.partial + (size_t)rt * TC_BM * p.Cout_pad);
+                    const size_t sstride4 = ((size_t)p.row_tiles * TC_BM * p.Cout_pad) >> 2;
+                    const int et = q4 * 32 + lane;
+                    for (int e = et; e < rows_valid * cp4; e += 128) {
+                        const int row = e / cp4, c4 = e - row * cp4;
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                        int sp = 0;
+                        for (; sp + 8 <= nact; sp += 8) {
+                            float4 t[8];
 #pragma unroll
-                                for (int e = 0; e < 4; ++e)
-                                    if (c4 * 4 + e < Cout) o[e] = p.accumulate ? o[e] + av[e] : av[e];
+                            for (int u = 0; u < 8; ++u) t[u] = __ldcg(p0 + (size_t)(sp + u) * sstride4 + e);
+#pragma unroll
+                            for (int u = 0; u < 8; ++u) { acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w; }
+                        }
+                        for (; sp < nact; ++sp) {
+                            const float4 t = __ldcg(p0 + (size_t)sp * sstride4 + e);
+                            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                        }
+                        if (c4 * 4 >= Cout) continue;
+                        const int orw = s_orow[row];
+                        if (orw < 0) continue;
+                        float* o = p.out + (int64_t)orw * Cout + c4 * 4;
+                        const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+                        if (vecO) {
+                            float4 wv = acc;
+                            if (p.accumulate) {
+                                const float4 old = *reinterpret_cast<const float4*>(o);
+                                wv.x += old.x; wv.y += old.y; wv.z += old.z; wv.w += old.w;
                             }
+                            *reinterpret_cast<float4*>(o) = wv;
+                        } else {
+#pragma unroll
+                            for (int e2 = 0; e2 < 4; ++e2)
+                                if (c4 * 4 + e2 < Cout) o[e2] = p.accumulate ? o[e2] + av[e2] : av[e2];
                         }
                     }
                 }
@@ -679,7 +697,7 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
     pl.wp_bytes = (int64_t)K * pl.nchunks * pl.stageB;
     const uint32_t cpr = (uint32_t)pl.KC / 4u;
     const uint32_t a_bytes = 2u * ((cpr * (TC_BM * 16u + 128u / cpr) + 127u) & ~127u);
-    const uint32_t fixed = TC_NBUF * (uint32_t)(TC_BM * KT + TC_BM + TC_MAXK + 4) * 4u + 1536u;
+    const uint32_t fixed = TC_NBUF * (uint32_t)(TC_BM * KT + TC_BM + TC_MAXK + 4) * 4u + 1536u + TC_BM * 4u;
     // slots: 4 under ~110 KB lets two CTAs share an SM; big stages fall back to fewer slots / one CTA per SM
     int best = 0;
     int smax = 4;
@@ -824,7 +842,10 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
     p.nsplit = 1;
     if (!pairs_mode && tab && K > 1 && p.row_tiles * 2 <= num_sms()) {
         B200SP_ENV_INT(env_nosplit, "B200SP_TC_NOSPLIT", 0);
-        if (!env_nosplit) p.nsplit = std::max(1, std::min(K, 2 * num_sms() / p.row_tiles));
+        // at most TC_MAX_SPLIT ways: the reducing CTA reads nsplit partial tiles back from L2, which beyond ~8 costs
+        // more than the stages it saves (measured: 26 ways on 11 row tiles took 130 us, 22 us with float atomics)
+        B200SP_ENV_INT(env_maxsplit, "B200SP_TC_MAXSPLIT", 8);
+        if (!env_nosplit) p.nsplit = std::max(1, std::min(std::min(K, env_maxsplit), 2 * num_sms() / p.row_tiles));
     }
     if (p.nsplit > 1) {
         int rc = split_scratch(st, (size_t)p.nsplit * p.row_tiles * TC_BM * pl.Cout_pad * sizeof(float), p.row_tiles,

@@ -31,3 +31,49 @@ def surface_coords(seed, target, batch):
     c = np.concatenate(out, 0).astype(np.int32)
     shape = (c[:, 1:].max(0) + 1).tolist()
     return c, shape
+
+
+def oracle_step(sd_f32, batch, dtype):
+    """one forward + backward of the CPU oracle (oracle/unet_ref.py) in `dtype` -> (loss, scores, state_dict with .grad)"""
+    from oracle.unet_ref import model_step_ref
+    sd = {k: (v.detach().to(dtype).clone().requires_grad_(True) if v.is_floating_point() else v.clone())
+          for k, v in sd_f32.items()}
+    b = dict(batch)
+    b["feats"] = batch["feats"].to(dtype)
+    loss, scores = model_step_ref(sd, b, training=True)
+    loss.backward()
+    return loss.detach(), scores.detach(), sd
+
+
+def grad_report(named_grads, sd64, sd32):
+    """per-parameter max-norm errors and the global L2 error of `named_grads` against the fp64 oracle, next to the
+    same numbers for the fp32 oracle (the reference algorithm in plain fp32 torch ops)"""
+    e_gpu, e_f32, num, den, num32 = [], [], 0.0, 0.0, 0.0
+    for name, g in named_grads:
+        r = sd64[name].grad
+        e_gpu.append(rel_err(g, r))
+        e_f32.append(rel_err(sd32[name].grad, r))
+        num += float((g.double().cpu() - r).pow(2).sum())
+        num32 += float((sd32[name].grad.double() - r).pow(2).sum())
+        den += float(r.pow(2).sum())
+    return {"gpu_median": float(np.median(e_gpu)), "gpu_p90": float(np.percentile(e_gpu, 90)),
+            "gpu_max": float(np.max(e_gpu)), "gpu_l2": float((num / den) ** 0.5),
+            "f32_median": float(np.median(e_f32)), "f32_p90": float(np.percentile(e_f32, 90)),
+            "f32_max": float(np.max(e_f32)), "f32_l2": float((num32 / den) ** 0.5)}
+
+
+GRAD_FACTOR = 4.0   # engine-vs-fp64 gradient error allowed as a multiple of the fp32 oracle's own error (measured ~2.2)
+GRAD_CAP = 5e-2     # and never more than this, whatever the fp32 oracle does
+
+
+def assert_grad_parity(rep, what=""):
+    """Whole-net GRADIENTS of a 71-conv / 65-BN ReLU net cannot be held to a per-op bar: two fp32 evaluations whose
+    forward activations agree to ~1e-6 disagree on the sign of a ~1e-6 fraction of the ReLU pre-activations, and every
+    flipped gate changes its gradient contribution by 100 % -- an L2 gradient difference of ~sqrt(1e-6) = 1e-3 per layer,
+    ~1e-2 over the net.  The fp32 CPU oracle (the reference algorithm in plain torch fp32) shows exactly that against
+    its own fp64 evaluation: L2 5.7e-3 at 2 x 150 k voxels, 1.4e-3 at 2 x 8 k.  The engine is
+    therefore held to a small multiple of the fp32 reference's own distance from fp64 (measured 2.2x; the 3xTF32
+    products round at 2^-21 instead of 2^-24), with an absolute cap."""
+    for k in ("median", "p90", "l2"):
+        g, f = rep["gpu_" + k], rep["f32_" + k]
+        assert g <= max(GRAD_FACTOR * f, 1e-4) and g <= GRAD_CAP, (what, k, rep)
