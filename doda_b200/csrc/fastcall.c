@@ -92,7 +92,35 @@ static PyObject* f_join(PyObject* self, PyObject* const* a, Py_ssize_t nargs) {
     CHECKED(b200sp_stream_join(m, s, e))
 }
 
+/* b200sp_conv_layer_fwd / _bwd: every argument becomes one int64 (None -> 0, float -> its double bit pattern) */
+#include <string.h>
+#define LAYER_MAXARGS 48
+static PyObject* layer_call(PyObject* const* a, Py_ssize_t nargs, int (*fn)(const int64_t*, int)) {
+    int64_t v[LAYER_MAXARGS];
+    if (nargs > LAYER_MAXARGS) {
+        PyErr_SetString(PyExc_TypeError, "too many arguments for a layer call");
+        return NULL;
+    }
+    for (Py_ssize_t i = 0; i < nargs; ++i) {
+        PyObject* o = a[i];
+        if (o == Py_None) {
+            v[i] = 0;
+        } else if (PyFloat_CheckExact(o)) {
+            double d = PyFloat_AS_DOUBLE(o);
+            memcpy(&v[i], &d, sizeof(d));
+        } else {
+            v[i] = (int64_t)PyLong_AsUnsignedLongLongMask(o);
+        }
+    }
+    if (PyErr_Occurred()) return NULL;
+    return PyLong_FromLong((long)fn(v, (int)nargs));
+}
+static PyObject* f_layer_fwd(PyObject* self, PyObject* const* a, Py_ssize_t nargs) { return layer_call(a, nargs, b200sp_conv_layer_fwd); }
+static PyObject* f_layer_bwd(PyObject* self, PyObject* const* a, Py_ssize_t nargs) { return layer_call(a, nargs, b200sp_conv_layer_bwd); }
+
 static PyMethodDef methods[] = {
+    {"layer_fwd", (PyCFunction)(void (*)(void))f_layer_fwd, METH_FASTCALL, "b200sp_conv_layer_fwd"},
+    {"layer_bwd", (PyCFunction)(void (*)(void))f_layer_bwd, METH_FASTCALL, "b200sp_conv_layer_bwd"},
     {"fork", (PyCFunction)(void (*)(void))f_fork, METH_FASTCALL, "b200sp_stream_fork"},
     {"join", (PyCFunction)(void (*)(void))f_join, METH_FASTCALL, "b200sp_stream_join"},
     {"gather_gemm", (PyCFunction)(void (*)(void))f_gather_gemm, METH_FASTCALL, "b200sp_gather_gemm"},

@@ -166,7 +166,25 @@ class Rulebook(object):
 
     __slots__ = ("kind", "outids", "indices", "pairs", "pairnum", "spatial_shape", "out_spatial_shape", "K",
                  "ksize", "stride", "padding", "dilation", "nbr", "fwd", "bwd", "nonoverlap", "batch_size", "order",
-                 "nbr_perm", "rowmask")
+                 "nbr_perm", "rowmask", "desc", "desc_ptr")
+
+    def descriptor(self):
+        """host descriptor for the C layer executor (B200SP_RB_* words of include/b200sparse.h), built once"""
+        p = getattr(self, "desc_ptr", None)
+        if p is None:
+            import numpy as np
+            d = np.zeros(16, dtype=np.int64)
+            ptr = lambda t: t.data_ptr() if t is not None else 0  # noqa: E731
+            d[0], d[1], d[2], d[3] = ptr(self.nbr), ptr(self.nbr_perm), ptr(self.order), ptr(self.rowmask)
+            d[4], d[5] = ptr(self.fwd), ptr(self.bwd)
+            if self.pairs is not None:
+                d[6], d[7], d[8] = self.pairs[0].data_ptr(), self.pairs[1].data_ptr(), self.pairnum.data_ptr()
+                d[11] = self.pairs.shape[2]
+            d[9], d[10] = self.indices.shape[0], self.outids.shape[0]
+            d[12], d[13] = self.K, 1 if self.nonoverlap else 0
+            self.desc = d  # keeps the memory alive
+            p = self.desc_ptr = int(d.ctypes.data)
+        return p
 
     def __iter__(self):
         return iter((self.outids, self.indices, self.pairs, self.pairnum, self.spatial_shape))
@@ -306,6 +324,7 @@ def _build_rulebook(indices, batch_size, spatial_shape, ksize, stride=1, padding
     rb.K, rb.ksize, rb.stride, rb.padding, rb.dilation = K, ks, st, pd, dl
     rb.indices, rb.spatial_shape, rb.batch_size = indices, shape, int(batch_size)
     rb.nbr = rb.fwd = rb.bwd = rb.order = rb.nbr_perm = rb.rowmask = None
+    rb.desc = rb.desc_ptr = None
     rb.pairs = torch.empty((2, K, M), dtype=_I32, device=dev) if need_pairs else None
     rb.pairnum = torch.empty((K,), dtype=_I32, device=dev) if need_pairs else None
     pp = rb.pairs.data_ptr() if need_pairs else None
@@ -682,6 +701,111 @@ def _w3(filters):
     return filters if filters.is_contiguous() else filters.contiguous()
 
 
+
+# ------------------------------------------------------------------------------------------------
+# layer executor: one C call per [BN -> ReLU ->] conv layer and direction (csrc/layer.cu)
+# ------------------------------------------------------------------------------------------------
+layer_exec = os.environ.get("B200SP_LAYER_EXEC", "1") != "0"
+_KIND_ID = {"subm": 0, "dense": 1, "conv": 2, "inverse": 3}
+
+
+def _conv_out_rows(kind, rb, M):
+    if kind == "conv":
+        return rb.outids.shape[0]
+    if kind == "inverse":
+        return rb.indices.shape[0]
+    return M
+
+
+def _side_state(dev):
+    """(raw side stream, fork event, join event) of `dev` for the weight gradient"""
+    st = _wg_side.get(dev.index)
+    if st is None:
+        import ctypes
+        side = torch.cuda.Stream(dev)
+        evs = []
+        for _ in range(2):
+            h = ctypes.c_void_p()
+            check(lib.b200sp_event_create(ctypes.byref(h)), "event_create")
+            evs.append(h.value)
+        st = _wg_side[dev.index] = (side, side.cuda_stream, evs[0], evs[1])
+    return st
+
+
+def _layer_fwd(kind, x, filters, rb, prep, bn=None):
+    """-> (out, y, stats): one C call for [BN + ReLU +] conv.  bn = (weight, bias, running_mean, running_var,
+    num_batches_tracked, momentum, eps) or None"""
+    M, Cin = x.shape
+    dev = x.device
+    K, Ci_w, Cout = _kcc(filters)
+    n_out = _conv_out_rows(kind, rb, M)
+    out = torch.empty((n_out, Cout), dtype=_F32, device=dev)
+    if prep:
+        wimg, cws, cwn = prep[0].data_ptr(), None, 0
+    else:
+        ws = _workspace(_conv_ws_bytes(K, Cin, Cout), dev, "conv")
+        wimg, cws, cwn = None, ws.data_ptr(), ws.numel()
+    rbp = rb.descriptor() if rb is not None else None
+    if bn is None:
+        rc = _fast.layer_fwd(_KIND_ID[kind], rbp, x.data_ptr(), M, Cin, filters.data_ptr(), wimg, K, Cout, out.data_ptr(),
+                             n_out, 0, None, None, 0.0, 0.0, None, None, None, None, None, None, 0, cws, cwn, _stream())
+        if rc:
+            check(rc, "conv_layer_fwd")
+        return out, None, None
+    bw, bb, rm, rv, nbt, momentum, eps = bn
+    y = torch.empty_like(x)
+    stats = torch.empty((2, Cin), dtype=_F32, device=dev)
+    bws = _workspace(_bn_ws_bytes(Cin), dev, "bn")
+    rc = _fast.layer_fwd(_KIND_ID[kind], rbp, x.data_ptr(), M, Cin, filters.data_ptr(), wimg, K, Cout, out.data_ptr(), n_out,
+                         1, bw.data_ptr() if bw is not None else None, bb.data_ptr() if bb is not None else None,
+                         float(eps), float(momentum), rm.data_ptr() if rm is not None else None,
+                         rv.data_ptr() if rv is not None else None, nbt.data_ptr() if nbt is not None else None,
+                         y.data_ptr(), stats.data_ptr(), bws.data_ptr(), bws.numel(), cws, cwn, _stream())
+    if rc:
+        check(rc, "conv_layer_fwd")
+    return out, y, stats
+
+
+def _layer_bwd(kind, x, act, filters, grad_out, rb, prep, need_din, need_dw, bn=None, stats=None, grad_y=None):
+    """-> (din or dx, dW, dwb): one C call for wgrad (side stream) + dgrad [+ grad_y] [+ BN backward]"""
+    M, Cin = act.shape
+    dev = act.device
+    K, Ci_w, Cout = _kcc(filters)
+    wb = prep[1] if prep else None
+    if wb is not None:
+        wimg, cws, cwn = wb.data_ptr(), None, 0
+    else:
+        ws = _workspace(_conv_ws_bytes(K, Cout, Cin), dev, "conv")
+        wimg, cws, cwn = None, ws.data_ptr(), ws.numel()
+    has_bn = bn is not None
+    dW = _dw_arena.take(filters.shape, dev) if need_dw else None
+    dy = torch.empty_like(act) if (need_din or has_bn) else None
+    side = None
+    if need_dw and dy is not None and async_wgrad and M <= async_wgrad_max_rows:
+        side = _side_state(dev)
+    rbp = rb.descriptor() if rb is not None else None
+    dx = dwb = None
+    if has_bn:
+        bw, bb = bn
+        dx = torch.empty_like(x)
+        dwb = torch.empty((2, Cin), dtype=_F32, device=dev)
+        bws = _workspace(_bn_ws_bytes(Cin), dev, "bn")
+        bargs = (1, bw.data_ptr() if bw is not None else None, bb.data_ptr() if bb is not None else None, stats.data_ptr(),
+                 act.data_ptr(), bws.data_ptr(), bws.numel())
+    else:
+        bargs = (0, None, None, None, act.data_ptr(), None, 0)
+    rc = _fast.layer_bwd(_KIND_ID[kind], rbp, x.data_ptr() if x is not None else None, M, Cin, filters.data_ptr(), wimg, K,
+                         Cout, grad_out.data_ptr(), grad_out.shape[0], *bargs, cws, cwn, 1 if need_din else 0,
+                         1 if need_dw else 0, dW.data_ptr() if dW is not None else None,
+                         dy.data_ptr() if dy is not None else None, dx.data_ptr() if dx is not None else None,
+                         dwb.data_ptr() if dwb is not None else None, _stream(), side[1] if side else None,
+                         side[2] if side else None, side[3] if side else None,
+                         grad_y.data_ptr() if grad_y is not None else None, 0)
+    if rc:
+        check(rc, "conv_layer_bwd")
+    return (dx if has_bn else dy), dW, dwb
+
+
 class _ConvFunctionBase(Function):
     """forward / backward of one sparse conv through conv_forward_raw / conv_backward_raw (one dispatch for every
     kernel choice: register-gather vs tcgen05, table vs pair lists, side-stream wgrad)"""
@@ -693,12 +817,18 @@ class _ConvFunctionBase(Function):
         features = _f32c(features)
         ctx.rb, ctx.prep = rb, prep
         ctx.save_for_backward(features, filters)
+        if layer_exec and _prof is None and filters.is_contiguous():
+            return _layer_fwd(cls.KIND, features, filters, rb, prep)[0]
         return conv_forward_raw(cls.KIND, features, filters, rb, prep)
 
     @classmethod
     def _bwd(cls, ctx, grad_out):
         features, filters = ctx.saved_tensors
         grad_out = _f32c(grad_out)  # the llijiang fork's `.contiguous()` (docs/INSTALL.md:25)
+        if layer_exec and _prof is None and filters.is_contiguous():
+            din, dW, _ = _layer_bwd(cls.KIND, None, features, filters, grad_out, ctx.rb, ctx.prep, ctx.needs_input_grad[0],
+                                    ctx.needs_input_grad[1])
+            return din, dW
         return conv_backward_raw(cls.KIND, features, filters, grad_out, ctx.rb, ctx.prep, ctx.needs_input_grad[0],
                                  ctx.needs_input_grad[1])
 
@@ -966,8 +1096,11 @@ class BNReLUConvFunction(Function):
     def forward(ctx, x, bn_w, bn_b, filters, running_mean, running_var, nbt, momentum, eps, rb, prep, kind):
         _req_cuda(x, filters)
         x = _f32c(x)
-        y, stats = _bn_forward_raw(x, bn_w, bn_b, running_mean, running_var, nbt, momentum, eps, True)
-        out = conv_forward_raw(kind, y, filters, rb, prep)
+        if layer_exec and _prof is None and filters.is_contiguous():
+            out, y, stats = _layer_fwd(kind, x, filters, rb, prep, (bn_w, bn_b, running_mean, running_var, nbt, momentum, eps))
+        else:
+            y, stats = _bn_forward_raw(x, bn_w, bn_b, running_mean, running_var, nbt, momentum, eps, True)
+            out = conv_forward_raw(kind, y, filters, rb, prep)
         ctx.save_for_backward(x, bn_w, bn_b, stats, y, filters)
         ctx.rb, ctx.prep, ctx.kind = rb, prep, kind
         ctx.set_materialize_grads(False)
@@ -985,6 +1118,12 @@ class BNReLUConvFunction(Function):
     @staticmethod
     def _backward(ctx, grad_out, grad_y, x, bn_w, bn_b, stats, y, filters):
         dy = dW = None
+        if layer_exec and _prof is None and grad_out is not None and filters.is_contiguous():
+            dx, dW, dwb = _layer_bwd(ctx.kind, x, y, filters, _f32c(grad_out), ctx.rb, ctx.prep, True, ctx.needs_input_grad[3],
+                                     bn=(bn_w, bn_b), stats=stats, grad_y=_f32c(grad_y) if grad_y is not None else None)
+            dw = dwb[0] if bn_w is not None and ctx.needs_input_grad[1] else None
+            db = dwb[1] if bn_b is not None and ctx.needs_input_grad[2] else None
+            return dx, dw, db, dW, None, None, None, None, None, None, None, None
         if grad_out is not None:
             grad_out = _f32c(grad_out)
             dy, dW = conv_backward_raw(ctx.kind, y, filters, grad_out, ctx.rb, ctx.prep, True, ctx.needs_input_grad[3],

@@ -164,6 +164,37 @@ int b200sp_wgrad_table(const float* a_dev, int Ca, const float* g_dev, int Cb, c
                        const int32_t* orow_dev, const int32_t* rowmask_dev, int64_t n_rows, int K, float* dW_dev,
                        void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Layer executor: ONE call per [BatchNorm -> ReLU ->] sparse conv layer and direction (csrc/layer.cu).  Replaces,
+ * per layer, what spconv v1.2's SparseConvolution.forward + SubMConvFunction / SparseConvFunction /
+ * SparseInverseConvFunction .forward/.backward and nn.BatchNorm1d + nn.ReLU run from Python
+ * (model/unet_block.py:24-29,68-70,76-78): kernel choice (register-gather / tcgen05 table or pair mode / fp32),
+ * side-stream weight gradient, BN statistics / apply / backward -- no allocation inside, every buffer from the caller.
+ *
+ * A rulebook is described by B200SP_RB_WORDS int64 words on the HOST (device pointers of its tables, 0 = absent):
+ * ------------------------------------------------------------------------------------------ */
+enum {
+    B200SP_RB_NBR = 0,     /* SubM out->in table [M][K] */
+    B200SP_RB_NBR_PERM,    /* the same in mask-sorted processing order */
+    B200SP_RB_ORDER,       /* [M] output row of processing row r */
+    B200SP_RB_ROWMASK,     /* [M] K-bit neighbour mask of processing row r */
+    B200SP_RB_FWD,         /* strided conv: [n_fine][K] fine row -> coarse row per offset */
+    B200SP_RB_BWD,         /* strided conv: [n_coarse][K] coarse row -> fine row per offset */
+    B200SP_RB_PAIRS_IN,    /* indice_pairs[0] = [K][pstride] input rows (spconv layout, canonical order) */
+    B200SP_RB_PAIRS_OUT,   /* indice_pairs[1] */
+    B200SP_RB_PAIRNUM,     /* [K] */
+    B200SP_RB_N_FINE,      /* rows of the rulebook's input sites */
+    B200SP_RB_N_COARSE,    /* rows of its output sites (= N_FINE for SubM) */
+    B200SP_RB_PSTRIDE,
+    B200SP_RB_K,
+    B200SP_RB_NONOVERLAP,  /* strided conv with one candidate per input (k == s): pair mode is atomics-free */
+    B200SP_RB_WORDS = 16
+};
+/* args_host: int64 vector (pointers and sizes; eps / momentum as IEEE-754 double bit patterns), layout documented at
+ * the definitions in csrc/layer.cu and built by doda_b200/ops.py (_layer_fwd / _layer_bwd). */
+int b200sp_conv_layer_fwd(const int64_t* args_host, int n);
+int b200sp_conv_layer_bwd(const int64_t* args_host, int n);
+
 /* out[k'][co][ci] = W[k][ci][co], k' = mirror ? K-1-k : k   (weights for dgrad) */
 int b200sp_weight_transpose(const float* W_dev, int K, int Cin, int Cout, int mirror, float* out_dev, void* stream);
 
