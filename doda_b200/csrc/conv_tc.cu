@@ -24,9 +24,6 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 #include <algorithm>
-#include <map>
-#include <mutex>
-#include <utility>
 #include <vector>
 #include <stdlib.h>
 #include <string.h>
@@ -73,10 +70,9 @@ struct TCParams {
     int ni;                 // MMA issuer warps in use (accumulators per set)
     int row_tiles;          // ceil(n_rows / 128)
     int total_tiles;        // row_tiles * (pairs_mode ? K : 1)
-    int nsplit;             // table mode: the active offsets of a row tile are dealt to nsplit CTAs; their partial sums
-                            // go to `partial` and the LAST CTA of the row tile adds them in split order (deterministic)
-    float* partial;         // [nsplit][row_tiles * 128][Cout_pad] (split mode only)
-    int* tickets;           // [row_tiles] arrival counters, zero on entry and reset to zero by the reducing CTA
+    int nsplit;             // table mode, few row tiles: the active offsets of a row tile are dealt to the nsplit CTAs of
+                            // one thread-block CLUSTER; their partial tiles meet through distributed shared memory and
+                            // are added in split order 0, 1, ... (deterministic: no float atomics on the output)
     int dbg;                // dev only: 1 no MMAs, 2 no gathers, 4 no transform, 8 no epilogue data, 16 no table copy/mask, 32 no weight copies
 };
 
@@ -97,7 +93,7 @@ struct TCLayout {
         return (o + 15u) & ~15u;
     }
     __host__ __device__ static uint32_t total(int nslots, int nslots_b, uint32_t stageB, int KT) {
-        return offBars(nslots, nslots_b, stageB, KT) + (uint32_t)(3 * nslots + 2 * nslots_b + 5 * TC_NBUF) * 8u + 16u + TC_BM * 4u;
+        return offBars(nslots, nslots_b, stageB, KT) + (uint32_t)(3 * nslots + 2 * nslots_b + 5 * TC_NBUF) * 8u + 16u;
     }
 };
 
@@ -116,7 +112,7 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 // (tile sequence number i, global stage number g); the smem stage ring and the two TMEM accumulator sets run
 // seamlessly across tiles, so gathers of tile t+1 are in flight while tile t is multiplied and tile t-1 is stored.
 template <int KC>
-__global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TCParams p) {  // 2 CTAs per SM: <= 56 registers
     using L = TCLayout<KC>;
     constexpr int NV = KC / 4;  // 16-byte chunks per row per stage
     extern __shared__ __align__(128) unsigned char smem[];
@@ -143,8 +139,6 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
     uint64_t* acce = accf + TC_NBUF;      // [NBUF] accumulator set drained -> issuers
     uint64_t* tload = acce + TC_NBUF;     // [NBUF] bulk copy of the tile's table rows landed (prefetcher only)
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tload + TC_NBUF);
-    int* s_flag = reinterpret_cast<int*>(s_tmem + 1);  // epilogue warps, split mode: "this CTA reduces the row tile"
-    int* s_orow = reinterpret_cast<int*>(s_tmem + 4);  // [128] output rows of the tile being reduced (split mode)
 
     const int ntiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
@@ -384,7 +378,6 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             mbar_wait(&tready[b], ph);
             const int nit = TC_NK(b) * nchunks;
             const int orow = TC_OROW(b)[q4 * 32 + lane];
-            const int npos = TC_NPOS(b);  // read before the metadata buffer is handed back to the prefetcher
             __syncwarp();
             if (lane == 0) mbar_arrive(&tfree[b]);
             if (nit > 0) {
@@ -397,9 +390,10 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
             const bool split_mode = p.nsplit > 1;
             const int tile = (int)blockIdx.x + i * (int)gridDim.x;
             const int rt = split_mode ? tile / p.nsplit : 0, split = split_mode ? tile - rt * p.nsplit : 0;
-            // split mode: this CTA's partial sums of the tile, row r of the tile at partial[split][rt * 128 + r][:]
-            float* part = split_mode ? p.partial + ((size_t)split * p.row_tiles * TC_BM + (size_t)rt * TC_BM + q4 * 32 + lane) * p.Cout_pad
-                                     : nullptr;
+            // split mode: this CTA's partial sums of the tile go to its OWN shared memory (the stage rings are idle once
+            // the accumulators are complete), row r at s_part[r][:] with a 4-float pad against bank conflicts
+            float* part = split_mode ? reinterpret_cast<float*>(smem) + (size_t)(q4 * 32 + lane) * (p.Cout_pad + 4) : nullptr;
+            (void)rt; (void)split;
             for (int ch = 0; ch * 16 < (((split_mode && nit == 0) || (p.dbg & 8)) ? 0 : p.Cout_pad); ++ch) {
                 float v[16];
 #pragma unroll
@@ -414,8 +408,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                 if (split_mode) {
 #pragma unroll
                     for (int g4 = 0; g4 < 4; ++g4)
-                        __stcg(reinterpret_cast<float4*>(part + ch * 16 + g4 * 4),
-                               make_float4(v[g4 * 4 + 0], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]));
+                        *reinterpret_cast<float4*>(part + ch * 16 + g4 * 4) =
+                            make_float4(v[g4 * 4 + 0], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
                     continue;
                 }
                 if (orow < 0) continue;
@@ -449,67 +443,6 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                 if (lane == 0) mbar_arrive(&acce[b]);
             }
             g0 += nit;
-            if (split_mode) {
-                // the last of the row tile's nsplit CTAs to arrive adds the partial sums in split order 0, 1, ...:
-                // the same summation order whatever the arrival order (no float atomics on the output)
-                s_orow[q4 * 32 + lane] = orow;
-                __threadfence();
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                if (q4 == 0 && lane == 0) {
-                    const int t = atomicAdd(p.tickets + rt, 1);
-                    const int last = (t == p.nsplit - 1);
-                    if (last) p.tickets[rt] = 0;  // ready for the next launch on this stream
-                    *s_flag = last;
-                }
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                const int last = *reinterpret_cast<volatile int*>(s_flag);
-                if (last && !(p.dbg & 8)) {
-                    __threadfence();
-                    // flat, coalesced walk over the tile's [rows_valid][Cout_pad] block: consecutive threads take
-                    // consecutive float4; per element the nact partials are loaded eight at a time (independent
-                    // loads in flight) and added in split order
-                    const int nact = min(p.nsplit, npos);  // splits that were dealt at least one offset
-                    const int cp4 = p.Cout_pad >> 2;
-                    const int rows_valid = (int)min((int64_t)TC_BM, p.n_rows - (int64_t)rt * TC_BM);
-                    const float4* p0 = reinterpret_cast<const float4*>(p.partial + (size_t)rt * TC_BM * p.Cout_pad);
-                    const size_t sstride4 = ((size_t)p.row_tiles * TC_BM * p.Cout_pad) >> 2;
-                    const int et = q4 * 32 + lane;
-                    for (int e = et; e < rows_valid * cp4; e += 128) {
-                        const int row = e / cp4, c4 = e - row * cp4;
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                        int sp = 0;
-                        for (; sp + 8 <= nact; sp += 8) {
-                            float4 t[8];
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) t[u] = __ldcg(p0 + (size_t)(sp + u) * sstride4 + e);
-#pragma unroll
-                            for (int u = 0; u < 8; ++u) { acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w; }
-                        }
-                        for (; sp < nact; ++sp) {
-                            const float4 t = __ldcg(p0 + (size_t)sp * sstride4 + e);
-                            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-                        }
-                        if (c4 * 4 >= Cout) continue;
-                        const int orw = s_orow[row];
-                        if (orw < 0) continue;
-                        float* o = p.out + (int64_t)orw * Cout + c4 * 4;
-                        const float av[4] = {acc.x, acc.y, acc.z, acc.w};
-                        if (vecO) {
-                            float4 wv = acc;
-                            if (p.accumulate) {
-                                const float4 old = *reinterpret_cast<const float4*>(o);
-                                wv.x += old.x; wv.y += old.y; wv.z += old.z; wv.w += old.w;
-                            }
-                            *reinterpret_cast<float4*>(o) = wv;
-                        } else {
-#pragma unroll
-                            for (int e2 = 0; e2 < 4; ++e2)
-                                if (c4 * 4 + e2 < Cout) o[e2] = p.accumulate ? o[e2] + av[e2] : av[e2];
-                        }
-                    }
-                }
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");  // s_flag is reused by the next tile
-            }
         }
     } else if (warp >= TC_W_MMA && warp < TC_W_MMA + TC_MAX_ISSUERS) {
         // ========== MMA issuers: warp w owns the global stages g = w (mod ni) and accumulator w of each set.  The whole
@@ -600,6 +533,61 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TCParams p) {
                 mbar_arrive(&tfree[b]);
             }
         }
+    }
+    if (p.nsplit > 1) {
+        // ---- split mode: one tile per CTA, the nsplit CTAs of the row tile form one cluster ----
+        // every thread of the cluster: partial tiles are complete and visible cluster-wide
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+        if (warp >= TC_W_EPI && warp < TC_W_EPI + 4 && !(p.dbg & 8)) {
+            const int et = (warp - TC_W_EPI) * 32 + lane;
+            const int rt = (int)blockIdx.x / p.nsplit, split = (int)blockIdx.x - rt * p.nsplit;
+            const int nact = min(p.nsplit, TC_NPOS(0));  // splits that were dealt at least one offset (same in every CTA)
+            const int cp4 = p.Cout_pad >> 2, pstr4 = cp4 + 1;
+            const int rows_valid = (int)min((int64_t)TC_BM, p.n_rows - (int64_t)rt * TC_BM);
+            const int total = rows_valid * cp4;
+            const int per = (total + p.nsplit - 1) / p.nsplit;
+            const int e_end = min(total, (split + 1) * per);
+            const bool vecO = (Cout % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0);
+            const int* orow_s = TC_OROW(0);
+            const uint32_t base = smem_u32(smem);
+            // this CTA adds ITS slice of the tile's [rows][Cout_pad] block over the peers' partial tiles, in split order
+            for (int e = split * per + et; e < e_end; e += 128) {
+                const int row = e / cp4, c4 = e - row * cp4;
+                const uint32_t laddr = base + (uint32_t)(row * pstr4 + c4) * 16u;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int sp = 0; sp < nact; ++sp) {
+                    uint32_t raddr;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(laddr), "r"(sp));
+                    float4 t;
+                    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+                                 : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                                 : "r"(raddr)
+                                 : "memory");
+                    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                }
+                if (c4 * 4 >= Cout) continue;
+                const int orw = orow_s[row];
+                if (orw < 0) continue;
+                float* o = p.out + (int64_t)orw * Cout + c4 * 4;
+                const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+                if (vecO) {
+                    float4 wv = acc;
+                    if (p.accumulate) {
+                        const float4 old = *reinterpret_cast<const float4*>(o);
+                        wv.x += old.x; wv.y += old.y; wv.z += old.z; wv.w += old.w;
+                    }
+                    *reinterpret_cast<float4*>(o) = wv;
+                } else {
+#pragma unroll
+                    for (int e2 = 0; e2 < 4; ++e2)
+                        if (c4 * 4 + e2 < Cout) o[e2] = p.accumulate ? o[e2] + av[e2] : av[e2];
+                }
+            }
+        }
+        // nobody leaves (and frees its shared memory) while a peer may still read it
+        asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
     }
 #undef TC_META
 #undef TC_IDX
@@ -697,7 +685,7 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
     pl.wp_bytes = (int64_t)K * pl.nchunks * pl.stageB;
     const uint32_t cpr = (uint32_t)pl.KC / 4u;
     const uint32_t a_bytes = 2u * ((cpr * (TC_BM * 16u + 128u / cpr) + 127u) & ~127u);
-    const uint32_t fixed = TC_NBUF * (uint32_t)(TC_BM * KT + TC_BM + TC_MAXK + 4) * 4u + 1536u + TC_BM * 4u;
+    const uint32_t fixed = TC_NBUF * (uint32_t)(TC_BM * KT + TC_BM + TC_MAXK + 4) * 4u + 1536u;
     // slots: 4 under ~110 KB lets two CTAs share an SM; big stages fall back to fewer slots / one CTA per SM
     int best = 0;
     int smax = 4;
@@ -749,46 +737,10 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
     return true;
 }
 
-// Scratch of the deterministic split-K reduction, owned by the library: one grow-only buffer per stream (launches on
-// one stream are ordered, so they can share it) plus a zero-initialised ticket array that every launch leaves zeroed.
-struct SplitScratch {
-    float* partial = nullptr;
-    int* tickets = nullptr;
-    size_t bytes = 0;
-};
-static constexpr int TC_MAX_TICKETS = 1024;
-static int split_scratch(cudaStream_t st, size_t bytes, int row_tiles, float** partial, int** tickets) {
-    static std::mutex mu;
-    static std::map<std::pair<int, cudaStream_t>, SplitScratch> tab;
-    if (row_tiles > TC_MAX_TICKETS) return B200SP_EUNSUP;
-    int dev = 0;
-    B200SP_CUDA(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lk(mu);
-    SplitScratch& sc = tab[std::make_pair(dev, st)];
-    if (!sc.tickets) {
-        B200SP_CUDA(cudaMalloc(&sc.tickets, TC_MAX_TICKETS * sizeof(int)));
-        B200SP_CUDA(cudaMemsetAsync(sc.tickets, 0, TC_MAX_TICKETS * sizeof(int), st));
-    }
-    if (sc.bytes < bytes) {
-        // earlier launches on this stream may still read the old buffer: free it only once the stream has drained
-        if (sc.partial) {
-            B200SP_CUDA(cudaStreamSynchronize(st));
-            B200SP_CUDA(cudaFree(sc.partial));
-            sc.partial = nullptr;
-            sc.bytes = 0;
-        }
-        const size_t want = std::max(bytes + bytes / 2, (size_t)(8u << 20));
-        B200SP_CUDA(cudaMalloc(&sc.partial, want));
-        sc.bytes = want;
-    }
-    *partial = sc.partial;
-    *tickets = sc.tickets;
-    return B200SP_OK;
-}
-
 template <int KC>
-static int launch_tc(const TCParams& p, int KT, cudaStream_t st) {
+static int launch_tc(const TCParams& p0, int KT, cudaStream_t st) {
     using L = TCLayout<KC>;
+    TCParams p = p0;
     const uint32_t smem = L::total(p.nslots, p.nslots_b, p.stageB_bytes, KT);
     static uint32_t attr_smem = 0;
     if (smem > attr_smem) {
@@ -798,6 +750,32 @@ static int launch_tc(const TCParams& p, int KT, cudaStream_t st) {
     // persistent grid: as many CTAs as fit on the machine (TMEM: 512 columns per SM), never more than tiles
     int occ = smem <= 110u * 1024u ? 2 : 1;
     while (occ > 1 && (uint32_t)occ * p.tmem_cols > 512u) --occ;
+    if (p.nsplit > 1) {
+        // split mode: p.nsplit is the WISH.  One tile per CTA, the nsplit CTAs of a row tile are one cluster (co-scheduled
+        // by the hardware, so they may wait for each other); their partial tiles must fit into the idle stage rings
+        p.nsplit = std::min(std::min(p.nsplit, 8), num_sms() * occ / p.row_tiles);
+        const uint32_t part_bytes = (uint32_t)TC_BM * (uint32_t)(p.Cout_pad + 4) * 4u;
+        if (part_bytes > L::offMeta(p.nslots, p.nslots_b, p.stageB_bytes)) p.nsplit = 1;
+        if (p.nsplit < 2) p.nsplit = 1;
+        p.total_tiles = p.row_tiles * p.nsplit;
+        if (p.nsplit > 1) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3((unsigned)p.total_tiles);
+            cfg.blockDim = dim3(TC_THREADS);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)p.nsplit;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            B200SP_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<KC>, p));
+            B200SP_LAUNCH_CHECK();
+            return B200SP_OK;
+        }
+    }
     const int grid = std::min(p.total_tiles, num_sms() * occ);
     k_conv_tc<KC><<<grid, TC_THREADS, smem, st>>>(p);
     B200SP_LAUNCH_CHECK();
@@ -838,21 +816,15 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
     }
     p.row_tiles = (int)cdiv(n_rows, TC_BM);
     // few row tiles (deep U-Net levels): deal each tile's active offsets to nsplit CTAs so the machine is not idle
-    // behind two or three serial tiles; the partial sums are added in split order by the row tile's last CTA
+    // behind two or three serial tiles; the partial tiles are added in split order through the cluster's shared memory
     p.nsplit = 1;
     if (!pairs_mode && tab && K > 1 && p.row_tiles * 2 <= num_sms()) {
         B200SP_ENV_INT(env_nosplit, "B200SP_TC_NOSPLIT", 0);
-        // at most TC_MAX_SPLIT ways: the reducing CTA reads nsplit partial tiles back from L2, which beyond ~8 costs
-        // more than the stages it saves (measured: 26 ways on 11 row tiles took 130 us, 22 us with float atomics)
+        // up to 8 ways = the portable cluster size (B200SP_TC_MAXSPLIT: dev knob)
         B200SP_ENV_INT(env_maxsplit, "B200SP_TC_MAXSPLIT", 8);
         if (!env_nosplit) p.nsplit = std::max(1, std::min(std::min(K, env_maxsplit), 2 * num_sms() / p.row_tiles));
     }
-    if (p.nsplit > 1) {
-        int rc = split_scratch(st, (size_t)p.nsplit * p.row_tiles * TC_BM * pl.Cout_pad * sizeof(float), p.row_tiles,
-                               &p.partial, &p.tickets);
-        if (rc) return rc;
-    }
-    p.total_tiles = p.row_tiles * (pairs_mode ? K : p.nsplit);
+    p.total_tiles = p.row_tiles * (pairs_mode ? K : p.nsplit);  // split mode: finalised by launch_tc (residency)
     if (pl.KC == 32) return launch_tc<32>(p, KT, st);
     if (pl.KC == 16) return launch_tc<16>(p, KT, st);
     return launch_tc<8>(p, KT, st);

@@ -123,7 +123,11 @@ int conv_dgrad(int kind, const RB& rb, const float* g, int64_t n_g, int Cin, con
 // weight gradient dW [Kw][Cin][Cout] (zero-filled by the caller) from a = conv input [M, Cin], g = output gradient
 int conv_wgrad(int kind, const RB& rb, const float* a, int64_t M, int Cin, const float* g, int64_t n_g, int Cout, int Kw,
                float* dW, void* st) {
-    const bool table = b200sp_wgrad_table_covers(Kw, Cin, Cout) != 0;
+    // table rows of this layer's weight gradient: the output sites (SubM, 1x1: M; strided: coarse; inverse: fine)
+    const int64_t n_tab = kind == KIND_CONV ? n_g : (kind == KIND_INVERSE ? rb.n_fine : M);
+    const bool have_pairs = kind == KIND_DENSE || rb.pairs_in != nullptr;
+    const bool table = have_pairs ? b200sp_wgrad_table_prefers(Kw, Cin, Cout, n_tab) != 0
+                                  : b200sp_wgrad_table_covers(Kw, Cin, Cout) != 0;
     switch (kind) {
         case KIND_SUBM:
             if (rb.nbr_perm && table) return b200sp_wgrad_table(a, Cin, g, Cout, rb.nbr_perm, rb.order, rb.rowmask, M, Kw, dW, st);

@@ -658,7 +658,10 @@ def wgrad(a, b, pa, pb, pairnum, n_upper, K, out=None):
 _wgt_cache = {}
 
 
-def _wgrad_table_covers(K, Ca, Cb):
+def _wgrad_table_covers(K, Ca, Cb, n_rows=None):
+    """does the table-form weight gradient take this shape -- and, with n_rows, is it the faster choice?"""
+    if n_rows is not None:
+        return bool(lib.b200sp_wgrad_table_prefers(K, Ca, Cb, int(n_rows)))
     key = (K, Ca, Cb)
     v = _wgt_cache.get(key)
     if v is None:
@@ -964,19 +967,19 @@ def _conv_wgrad(kind, features, grad_out, rb, out):
     M = features.shape[0]
     Ca, Cb = features.shape[1], grad_out.shape[1]
     if kind == "subm":
-        if rb.nbr_perm is not None and _wgrad_table_covers(rb.K, Ca, Cb):
+        if rb.nbr_perm is not None and _wgrad_table_covers(rb.K, Ca, Cb, M):
             return wgrad_table(features, grad_out, rb.nbr_perm, M, rb.K, orow=rb.order, rowmask=rb.rowmask, out=out)
         return wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K, out=out)
     if kind == "dense":
-        if _wgrad_table_covers(1, Ca, Cb):
+        if _wgrad_table_covers(1, Ca, Cb, M):
             return wgrad_table(features, grad_out, None, M, 1, out=out)
         return wgrad(features, grad_out, None, None, None, M, 1, out=out)
     if kind == "conv":
-        if _wgrad_table_covers(rb.K, Ca, Cb):
+        if _wgrad_table_covers(rb.K, Ca, Cb, grad_out.shape[0]):
             return wgrad_table(features, grad_out, rb.bwd, grad_out.shape[0], rb.K, out=out)
         return wgrad(features, grad_out, rb.pairs[0], rb.pairs[1], rb.pairnum, M, rb.K, out=out)
     n_fine = rb.indices.shape[0]  # inverse
-    if _wgrad_table_covers(rb.K, Ca, Cb):
+    if _wgrad_table_covers(rb.K, Ca, Cb, n_fine):
         return wgrad_table(features, grad_out, rb.fwd, n_fine, rb.K, out=out)
     return wgrad(features, grad_out, rb.pairs[1], rb.pairs[0], rb.pairnum, n_fine, rb.K, out=out)
 

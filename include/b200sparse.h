@@ -160,6 +160,9 @@ int b200sp_wgrad(const float* a_dev, int Ca, const float* b_dev, int Cb, const i
  * (SubM: nbr_perm/order/rowmask of b200sp_rulebook_subm; strided conv: bwd table, a = input, g = output gradient;
  * inverse conv: fwd table).  g is read once per row instead of once per pair.  dW must be zeroed by the caller. */
 int b200sp_wgrad_table_covers(int K, int Ca, int Cb);
+/* 1 when the table form is also the faster choice for a layer of n_rows table rows (the dispatch rule of the layer
+ * executor; b200sp_wgrad_table itself accepts every covered shape) */
+int b200sp_wgrad_table_prefers(int K, int Ca, int Cb, int64_t n_rows);
 int b200sp_wgrad_table(const float* a_dev, int Ca, const float* g_dev, int Cb, const int32_t* tab_dev,
                        const int32_t* orow_dev, const int32_t* rowmask_dev, int64_t n_rows, int K, float* dW_dev,
                        void* stream);

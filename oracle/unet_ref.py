@@ -15,11 +15,20 @@ class _Sp(object):
         self.f, self.idx, self.shape, self.bs, self.rbs = feats, idx, shape, bs, rbs
 
 
+# Optional {BatchNorm key: bool mask [rows, C]} that PINS the ReLU gates (tests only): with the gates taken from the
+# implementation under test, the net is a smooth function of its inputs and whole-net gradients can be compared at a
+# fixed tight bar -- without it, two fp32-accurate evaluations disagree on the sign of a ~1e-6 fraction of the
+# pre-activations and every flipped gate moves the gradients by a whole row's contribution.
+_RELU_MASKS = None
+
+
 def _bn_relu(sd, pre, x, training, eps=1e-4, momentum=0.1):
     # nn.BatchNorm1d(eps=1e-4, momentum=0.1) + nn.ReLU (model/unet.py:28,43-44)
     rm, rv = sd.get(pre + ".running_mean"), sd.get(pre + ".running_var")
     y = F.batch_norm(x, None if training else rm, None if training else rv, sd[pre + ".weight"], sd[pre + ".bias"],
                      training, momentum, eps)
+    if _RELU_MASKS is not None and pre in _RELU_MASKS:
+        return y * _RELU_MASKS[pre].to(y.dtype)
     return F.relu(y)
 
 
@@ -98,11 +107,17 @@ def voxelize_mean_ref(feats, v2p):
     return out / cnt[:, None]
 
 
-def model_step_ref(sd, batch, training=True):
-    """model_fn forward (model/unet.py:72-99,154-198): voxelize features, net, CE(ignore 255). -> (loss, scores)"""
+def model_step_ref(sd, batch, training=True, relu_masks=None):
+    """model_fn forward (model/unet.py:72-99,154-198): voxelize features, net, CE(ignore 255). -> (loss, scores)
+    relu_masks: see _RELU_MASKS"""
+    global _RELU_MASKS
     vf = voxelize_mean_ref(batch["feats"], batch["v2p_map"])
-    scores = unet_forward_ref(sd, vf, batch["voxel_locs"].numpy(), batch["spatial_shape"],
-                              batch["offsets"].shape[0] - 1, batch["p2v_map"].numpy(), training)
+    _RELU_MASKS = relu_masks
+    try:
+        scores = unet_forward_ref(sd, vf, batch["voxel_locs"].numpy(), batch["spatial_shape"],
+                                  batch["offsets"].shape[0] - 1, batch["p2v_map"].numpy(), training)
+    finally:
+        _RELU_MASKS = None
     loss = F.cross_entropy(scores, batch["labels"], ignore_index=255)
     return loss, scores
 

@@ -33,14 +33,42 @@ def surface_coords(seed, target, batch):
     return c, shape
 
 
-def oracle_step(sd_f32, batch, dtype):
+def capture_relu_masks(model):
+    """Instrument a SparseConvNet (the mirror or the reference's own class) built on the engine's spconv surface so
+    that its next forward records, per BatchNorm key (state_dict prefix), which BN+ReLU outputs were > 0.
+    -> dict filled during the forward.  Test infrastructure: wraps the fused-triplet entry point per conv instance."""
+    from doda_b200 import spconv
+    from doda_b200.spconv.modules import is_sparse_conv, _is_bn_like
+    masks = {}
+    for name, seq in model.named_modules():
+        if not isinstance(seq, spconv.SparseSequential):
+            continue
+        mods = list(seq._modules.items())
+        for i, (k, m) in enumerate(mods):
+            if not _is_bn_like(m):
+                continue
+            key = "%s.%s" % (name, k)
+            if i + 2 < len(mods) and is_sparse_conv(mods[i + 2][1]):
+                conv = mods[i + 2][1]
+
+                def wrapped(input, bn, stats_args, _orig=conv.forward_after_bn_relu, _key=key):
+                    out = _orig(input, bn, stats_args)
+                    masks[_key] = (input.features.detach() > 0).cpu()
+                    return out
+                conv.forward_after_bn_relu = wrapped
+            else:  # BN + ReLU at the end of a sequential (output_layer): the sequential's output holds the activation
+                seq.register_forward_hook(lambda mod, inp, out, _key=key: masks.__setitem__(_key, (out.features.detach() > 0).cpu()))
+    return masks
+
+
+def oracle_step(sd_f32, batch, dtype, relu_masks=None):
     """one forward + backward of the CPU oracle (oracle/unet_ref.py) in `dtype` -> (loss, scores, state_dict with .grad)"""
     from oracle.unet_ref import model_step_ref
     sd = {k: (v.detach().to(dtype).clone().requires_grad_(True) if v.is_floating_point() else v.clone())
           for k, v in sd_f32.items()}
     b = dict(batch)
     b["feats"] = batch["feats"].to(dtype)
-    loss, scores = model_step_ref(sd, b, training=True)
+    loss, scores = model_step_ref(sd, b, training=True, relu_masks=relu_masks)
     loss.backward()
     return loss.detach(), scores.detach(), sd
 
@@ -62,8 +90,32 @@ def grad_report(named_grads, sd64, sd32):
             "f32_max": float(np.max(e_f32)), "f32_l2": float((num32 / den) ** 0.5)}
 
 
-GRAD_FACTOR = 4.0   # engine-vs-fp64 gradient error allowed as a multiple of the fp32 oracle's own error (measured ~2.2)
+GRAD_FACTOR = 40.0  # UNPINNED gates: engine-vs-fp64 gradient error as a multiple of the fp32 oracle's own (measured 3-22;
+                    # a sanity bound only -- the fixed bars are the PINNED ones below)
 GRAD_CAP = 5e-2     # and never more than this, whatever the fp32 oracle does
+
+
+def pinned_grad_report(named_grads, sd64p):
+    """errors against the fp64 oracle evaluated with the ReLU gates PINNED to the implementation's own (smooth net)"""
+    e, num, den = [], 0.0, 0.0
+    worst = ("", 0.0)
+    for name, g in named_grads:
+        r = sd64p[name].grad
+        v = rel_err(g, r)
+        e.append(v)
+        if v > worst[1]:
+            worst = (name, v)
+        num += float((g.double().cpu() - r).pow(2).sum())
+        den += float(r.pow(2).sum())
+    return {"median": float(np.median(e)), "p90": float(np.percentile(e, 90)), "max": float(np.max(e)),
+            "l2": float((num / den) ** 0.5), "worst": worst[0]}
+
+
+PINNED_MEDIAN, PINNED_P90, PINNED_L2 = 1e-4, 2e-4, 1e-4   # fixed bars with pinned gates (measured 2-3e-5 / 3-4e-5 / 2-3e-5)
+
+
+def assert_pinned_grad_parity(rep, what=""):
+    assert rep["median"] <= PINNED_MEDIAN and rep["p90"] <= PINNED_P90 and rep["l2"] <= PINNED_L2, (what, rep)
 
 
 def assert_grad_parity(rep, what=""):
@@ -72,8 +124,10 @@ def assert_grad_parity(rep, what=""):
     flipped gate changes its gradient contribution by 100 % -- an L2 gradient difference of ~sqrt(1e-6) = 1e-3 per layer,
     ~1e-2 over the net.  The fp32 CPU oracle (the reference algorithm in plain torch fp32) shows exactly that against
     its own fp64 evaluation: L2 5.7e-3 at 2 x 150 k voxels, 1.4e-3 at 2 x 8 k.  The engine is
-    therefore held to a small multiple of the fp32 reference's own distance from fp64 (measured 2.2x; the 3xTF32
-    products round at 2^-21 instead of 2^-24), with an absolute cap."""
+    therefore held (a) to FIXED tight bars against the fp64 oracle evaluated with the gates pinned to the engine's own
+    (assert_pinned_grad_parity: the smooth part of the computation), and (b) with free gates only to a multiple of the
+    fp32 reference's own distance from fp64 (the engine's 3xTF32 products round at 2^-21 instead of 2^-24, so it flips
+    several times more gates than plain fp32), with an absolute cap."""
     for k in ("median", "p90", "l2"):
         g, f = rep["gpu_" + k], rep["f32_" + k]
         assert g <= max(GRAD_FACTOR * f, 1e-4) and g <= GRAD_CAP, (what, k, rep)

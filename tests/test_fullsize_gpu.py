@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import rel_err, surface_coords, oracle_step, grad_report, assert_grad_parity
+from helpers import (rel_err, surface_coords, oracle_step, grad_report, assert_grad_parity, capture_relu_masks,
+                     pinned_grad_report, assert_pinned_grad_parity)
 
 pytestmark = pytest.mark.gpu
 
@@ -23,8 +24,10 @@ def test_full_size_unet_matches_oracle_2x150k(cuda_dev):
     loss64, scores64, sd64 = oracle_step(sd0, batch, torch.float64)
     loss32, scores32, sd32 = oracle_step(sd0, batch, torch.float32)
     model = model.to(cuda_dev).train()
+    masks = capture_relu_masks(model)
     loss, scores = model_step(model, batch, device=cuda_dev)
     loss.backward()
+    assert len(masks) == 65
     e, e32 = rel_err(scores, scores64), rel_err(scores32, scores64)
     print("full size 2x150k: scores rel err %.3e (fp32 oracle: %.3e), loss %.7f vs %.7f" % (e, e32, float(loss), float(loss64)))
     assert e <= 1e-4, e  # north_star: fp32 activations within 1e-4 rel
@@ -32,6 +35,11 @@ def test_full_size_unet_matches_oracle_2x150k(cuda_dev):
     rep = grad_report([(n, p.grad) for n, p in model.named_parameters()], sd64, sd32)
     print("full size grads vs fp64 oracle:", rep)
     assert_grad_parity(rep, "2x150k")
+    # the fixed bar: fp64 oracle with the ReLU gates pinned to the engine's own
+    _, scores64p, sd64p = oracle_step(sd0, batch, torch.float64, relu_masks=masks)
+    prep = pinned_grad_report([(n, p.grad) for n, p in model.named_parameters()], sd64p)
+    print("full size grads vs fp64 oracle with pinned gates:", prep, "scores", rel_err(scores, scores64p))
+    assert_pinned_grad_parity(prep, "2x150k")
     # the well-conditioned end of the backward chain is held to the per-op bar
     assert rel_err(model.linear.weight.grad, sd64["linear.weight"].grad) <= 1e-4
     assert rel_err(model.output_layer[0].weight.grad, sd64["output_layer.0.weight"].grad) <= 1e-4

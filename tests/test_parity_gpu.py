@@ -645,9 +645,16 @@ def _unet_parity(cuda_dev, target, mid, tol_scores, tol_grad):
     loss32, scores32 = model_step_ref(sd32, batch, training=True)
     loss32.backward()
     model = model.to(cuda_dev).train()
+    from helpers import capture_relu_masks, pinned_grad_report, assert_pinned_grad_parity, oracle_step
+    sd0 = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    masks = capture_relu_masks(model)
     loss, scores = model_step(model, batch, device=cuda_dev)
     loss.backward()
     assert rel_err(scores, scores_ref) <= tol_scores, ("scores", rel_err(scores, scores_ref))
+    _, _, sd64p = oracle_step(sd0, batch, torch.float64, relu_masks=masks)
+    prep = pinned_grad_report([(n, p.grad) for n, p in model.named_parameters()], sd64p)
+    print("unet grads vs fp64 oracle with pinned gates:", prep)
+    assert_pinned_grad_parity(prep, "target %d m %d" % (target, mid))
     assert abs(float(loss.detach()) - float(loss_ref.detach())) <= tol_scores * max(1.0, abs(float(loss_ref.detach())))
     from helpers import grad_report, assert_grad_parity
     report = grad_report([(n, p.grad) for n, p in model.named_parameters()], sd64, sd32)

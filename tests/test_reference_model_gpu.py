@@ -12,7 +12,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import rel_err, oracle_step, grad_report, assert_grad_parity
+from helpers import (rel_err, oracle_step, grad_report, assert_grad_parity, capture_relu_masks, pinned_grad_report,
+                     assert_pinned_grad_parity)
 
 pytestmark = pytest.mark.gpu
 
@@ -52,9 +53,11 @@ def test_reference_model_fn_runs_unchanged_and_matches_oracle_and_mirror(ref, cu
     _, _, sd32 = oracle_step(sd0, batch, torch.float32)
     net = net.to(cuda_dev).train()
     model_fn = model_fn_decorator(cfg, 2)
+    masks = capture_relu_masks(net)
     ret = model_fn(batch, net, 0)
     ret["loss"].backward()
     torch.cuda.synchronize()
+    assert len(masks) == 65
     assert set(ret) >= {"loss", "output", "preds", "labels"}
     # vs the fp64 oracle: the boundary's tolerance for activations (north_star: 1e-4 rel)
     e_scores = rel_err(ret["output"], scores64)
@@ -64,6 +67,10 @@ def test_reference_model_fn_runs_unchanged_and_matches_oracle_and_mirror(ref, cu
     rep = grad_report([(n, p.grad) for n, p in net.named_parameters()], sd64, sd32)
     print("reference model on the engine, grads vs fp64 oracle:", rep)
     assert_grad_parity(rep, "reference model")
+    _, _, sd64p = oracle_step(sd0, batch, torch.float64, relu_masks=masks)
+    prep = pinned_grad_report([(n, p.grad) for n, p in net.named_parameters()], sd64p)
+    print("reference model on the engine, grads vs fp64 oracle with pinned gates:", prep)
+    assert_pinned_grad_parity(prep, "reference model")
     assert rel_err(net.linear.weight.grad, sd64["linear.weight"].grad) <= 1e-4
     # vs the mirror (doda_b200/unet.py): same weights, same batch -> same activations (the mirror only swaps in the
     # engine's devoxelize gather and cross-entropy, which do not change the forward values)
@@ -97,12 +104,17 @@ def test_reference_vggblock_net_matches_oracle(ref, cuda_dev):
     loss64, scores64, sd64 = oracle_step(sd0, batch, torch.float64)
     _, _, sd32 = oracle_step(sd0, batch, torch.float32)
     net = net.to(cuda_dev).train()
+    masks = capture_relu_masks(net)
     ret = model_fn_decorator(cfg, 2)(batch, net, 0)
     ret["loss"].backward()
     assert rel_err(ret["output"], scores64) <= 1e-4
     rep = grad_report([(n, p.grad) for n, p in net.named_parameters()], sd64, sd32)
     print("VGG net grads:", rep)
     assert_grad_parity(rep, "vgg")
+    _, _, sd64p = oracle_step(sd0, batch, torch.float64, relu_masks=masks)
+    prep = pinned_grad_report([(n, p.grad) for n, p in net.named_parameters()], sd64p)
+    print("VGG net grads vs fp64 oracle with pinned gates:", prep)
+    assert_pinned_grad_parity(prep, "vgg")
     mirror = Mirror(mid_channel=16, block_residual=False)
     mirror.load_state_dict(sd0)
     mirror = mirror.to(cuda_dev).train()
