@@ -260,5 +260,6 @@ def measure(state_dict, batch, device, steps=5, warmup=2, graph=True):
             torch.cuda.synchronize()
             out["ms_graph"] = s.elapsed_time(e) / steps + ms_rb
         except Exception as ex:  # graph capture is a favour to the baseline, not a requirement
-            out["graph_error"] = repr(ex)[:200]
+            import traceback
+            out["graph_error"] = repr(ex)[:200] + " | " + traceback.format_exc()[-700:]
     return out

@@ -254,7 +254,8 @@ def run_gpu_native(model, batch, dev, value_ms, bs):
     try:
         r = gpu_native.measure(sd, batch, dev, steps=3, warmup=1, graph=True)
     except Exception as e:
-        return {"error": repr(e)[:300], "vs_gpu_native": None}
+        import traceback
+        return {"error": repr(e)[:300], "traceback": traceback.format_exc()[-800:], "vs_gpu_native": None}
     finally:
         torch.cuda.empty_cache()
     best = min(v for v in (r["ms_eager"], r["ms_graph"]) if v is not None)

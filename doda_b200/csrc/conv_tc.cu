@@ -674,7 +674,7 @@ struct TCPlan {
     int64_t wp_bytes;
 };
 
-static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
+static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl, int64_t n_tiles = 0) {
     if (K < 1 || K > TC_MAXK || Cin < 1 || Cout < 1) return false;
     const int Cin_pad = (Cin + 7) / 8 * 8;
     pl.KC = (Cin_pad % 32 == 0) ? 32 : (Cin_pad % 16 == 0) ? 16 : 8;
@@ -719,16 +719,24 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl) {
         pl.nslots_b = best * mult;
     }
     // issuer warps: each smem slot must belong to exactly ONE issuer (its mbarrier waits are parity waits, an issuer
-    // running a fill ahead of a slot it shares would alias phases), so ni divides nslots; two accumulator sets
+    // running a fill ahead of a slot it shares would alias phases), so ni divides nslots; two accumulator sets.
+    // TMEM decides the residency: with more tiles than SMs two CTAs per SM (<= 256 columns each) beat one CTA with
+    // twice the issuers -- the layer then runs in one round instead of two (ncu, level 3 of DODA's net: 207 tiles on
+    // 148 single CTAs took 72 us, the stage ring being latency-bound at ~0.55 us per stage per CTA).
     {
         B200SP_ENV_INT(env_issuers, "B200SP_TC_ISSUERS", TC_MAX_ISSUERS);
         const int want = std::max(1, std::min(env_issuers, TC_MAX_ISSUERS));
+        const bool two_cta_smem = budget == two_cta_budget && two_cta_budget > 0;
+        const uint32_t col_cap = (two_cta_smem && n_tiles > num_sms()) ? 256u : 512u;
         pl.ni = 0;
-        for (int ni = want; ni >= 1; --ni)
-            if (best % ni == 0 && TC_NBUF * ni * pl.Cout_pad <= 512) {
-                pl.ni = ni;
-                break;
-            }
+        for (int pass = 0; pass < 2 && pl.ni == 0; ++pass) {
+            const uint32_t cap = pass == 0 ? col_cap : 512u;
+            for (int ni = want; ni >= 1; --ni)
+                if (best % ni == 0 && (uint32_t)(TC_NBUF * ni * pl.Cout_pad) <= cap) {
+                    pl.ni = ni;
+                    break;
+                }
+        }
         if (pl.ni == 0) return false;
     }
     uint32_t cols = 32;
@@ -788,7 +796,7 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
                 int Cout, int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st) {
     TCPlan pl;
     const int KT = pairs_mode ? 1 : K;
-    if (!tc_plan(K, Cin, Cout, KT, pl)) return B200SP_EUNSUP;
+    if (!tc_plan(K, Cin, Cout, KT, pl, cdiv(n_rows, TC_BM) * (pairs_mode ? K : 1))) return B200SP_EUNSUP;
     if (!(wflags & 4) && (!ws || ws_bytes < pl.wp_bytes)) {
         set_error("conv_tc: workspace too small (%lld < %lld bytes)", (long long)ws_bytes, (long long)pl.wp_bytes);
         return B200SP_ENOMEM;
