@@ -46,6 +46,37 @@ void add_launches(int n);
         return e__ ? atoi(e__) : (dflt);                 \
     }()
 
+// ---- programmatic dependent launch (PDL) ----
+// One training step is ~800 dependent launches of 5-100 us kernels: the ~2-4 us between the end of one kernel and the
+// first useful instruction of the next (launch latency + prologue: barrier init, TMEM allocation) is a tenth of the
+// step.  Kernels of the hot path therefore (a) call pdl_trigger() first thing -- the next kernel of the stream may
+// become resident as soon as every CTA of this one has started -- and (b) call pdl_wait() before their FIRST global
+// memory access (read or write): it returns once the preceding kernel of the stream has completed and its writes are
+// visible.  Everything before pdl_wait() (shared-memory carve-up, mbarrier init, tcgen05.alloc) overlaps the
+// predecessor's tail.  Launched without the attribute (B200SP_PDL=0) both calls are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -60,6 +60,8 @@ __host__ __device__ constexpr int direct_mt(int CG, int NG) { return 1; }
 template <int CG, int NG, bool TRANSPOSED>
 __global__ void __launch_bounds__(256) k_conv_direct(const DirectParams p) {
     constexpr int MT = direct_mt(CG, NG);
+    pdl_trigger();
+    pdl_wait();
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int col0 = blockIdx.y * NG * 16;
@@ -193,9 +195,9 @@ int g_direct = -1;  // 1 = use the register-gather kernel where it applies (defa
 template <int CG, int NG>
 int launch(const DirectParams& p, dim3 grid, cudaStream_t st) {
     if (p.transposed)
-        k_conv_direct<CG, NG, true><<<grid, 256, 0, st>>>(p);
+        B200SP_CUDA(launch_pdl(k_conv_direct<CG, NG, true>, grid, dim3(256), 0, st, p));
     else
-        k_conv_direct<CG, NG, false><<<grid, 256, 0, st>>>(p);
+        B200SP_CUDA(launch_pdl(k_conv_direct<CG, NG, false>, grid, dim3(256), 0, st, p));
     B200SP_LAUNCH_CHECK();
     return B200SP_OK;
 }

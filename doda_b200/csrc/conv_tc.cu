@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TCParams p) {  // 2 C
     const uint32_t tmem = *s_tmem;
     const int nchunks = p.nchunks;
     const int Cin = p.Cin, Cout = p.Cout;
+    pdl_wait();  // barrier init and TMEM allocation above overlap the predecessor's tail; no global access before here
 
 #define TC_META(b) (s_meta + (b) * meta_ints)
 #define TC_IDX(b) (TC_META(b))
@@ -534,6 +535,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TCParams p) {  // 2 C
             }
         }
     }
+    pdl_trigger();  // this CTA's work is issued: the next kernel of the stream may start its prologue (TMEM-heavy kernels
+                    // trigger late -- an early-resident successor would sit on shared memory / TMEM for the whole run)
     if (p.nsplit > 1) {
         // ---- split mode: one tile per CTA, the nsplit CTAs of the row tile form one cluster ----
         // every thread of the cluster: partial tiles are complete and visible cluster-wide
@@ -772,20 +775,22 @@ static int launch_tc(const TCParams& p0, int KT, cudaStream_t st) {
             cfg.blockDim = dim3(TC_THREADS);
             cfg.dynamicSmemBytes = smem;
             cfg.stream = st;
-            cudaLaunchAttribute attr[1];
+            cudaLaunchAttribute attr[2];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = (unsigned)p.nsplit;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
-            cfg.numAttrs = 1;
+            cfg.numAttrs = pdl_enabled() ? 2 : 1;
             B200SP_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<KC>, p));
             B200SP_LAUNCH_CHECK();
             return B200SP_OK;
         }
     }
     const int grid = std::min(p.total_tiles, num_sms() * occ);
-    k_conv_tc<KC><<<grid, TC_THREADS, smem, st>>>(p);
+    B200SP_CUDA(launch_pdl(k_conv_tc<KC>, dim3((unsigned)grid), dim3(TC_THREADS), smem, st, p));
     B200SP_LAUNCH_CHECK();
     return B200SP_OK;
 }

@@ -26,6 +26,17 @@ static std::atomic<long long> g_launches{0};
 void add_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long get_launches() { return g_launches.load(std::memory_order_relaxed); }
 
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        // opt-in: measured on the full step (bench.py, 2 x 150 k voxels) PDL = 1 gave 12.95-13.45 ms against 12.80 ms
+        // without -- the GPU is ~94 % busy inside kernels, the gaps PDL can close are not where the time is
+        const char* e = getenv("B200SP_PDL");
+        on = (e && e[0] == '1') ? 1 : 0;
+    }
+    return on != 0;
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {

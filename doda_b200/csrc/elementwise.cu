@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restric
                                                           float* __restrict__ partial, BNFinal fin) {
     extern __shared__ float s_part[];  // [2][rpb][C]
     __shared__ int s_last;
+    pdl_trigger();
+    pdl_wait();
     const int CG = C / VEC;
     const int rpb = BN_THREADS / CG;
     const int tid = threadIdx.x;
@@ -223,6 +225,8 @@ __global__ void __launch_bounds__(256) k_affine_relu(const float* __restrict__ x
                                                      const float* __restrict__ scale,
                                                      const float* __restrict__ shift, int relu,
                                                      float* __restrict__ y) {
+    pdl_trigger();
+    pdl_wait();
     const int CG = C / VEC;
     const int64_t n = M * CG;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -255,6 +259,8 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
                                                       const float* __restrict__ c_mean_g,
                                                       const float* __restrict__ c_mean_gx, int relu,
                                                       float* __restrict__ dx) {
+    pdl_trigger();
+    pdl_wait();
     const int CG = C / VEC;
     const int64_t n = M * CG;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -404,13 +410,13 @@ extern "C" int b200sp_bn_fwd_train(const float* x, int64_t M, int C, const float
     fin.running_mean = running_mean; fin.running_var = running_var;
     fin.num_batches_tracked = (long long*)num_batches_tracked; fin.scale = scale; fin.shift = shift;
     if (v4)
-        k_bn_reduce<4, 0><<<G, BN_THREADS, smem, st>>>(x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, partial, fin);
+        B200SP_CUDA(launch_pdl(k_bn_reduce<4, 0>, dim3(G), dim3(BN_THREADS), smem, st, x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, partial, fin));
     else
-        k_bn_reduce<1, 0><<<G, BN_THREADS, smem, st>>>(x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, partial, fin);
+        B200SP_CUDA(launch_pdl(k_bn_reduce<1, 0>, dim3(G), dim3(BN_THREADS), smem, st, x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, partial, fin));
     if (v4)
-        k_affine_relu<4><<<stream_grid(M * (C / 4), 256), 256, 0, st>>>(x, M, C, scale, shift, relu, y);
+        B200SP_CUDA(launch_pdl(k_affine_relu<4>, dim3(stream_grid(M * (C / 4), 256)), dim3(256), 0, st, x, M, C, scale, shift, relu, y));
     else
-        k_affine_relu<1><<<stream_grid(M * C, 256), 256, 0, st>>>(x, M, C, scale, shift, relu, y);
+        B200SP_CUDA(launch_pdl(k_affine_relu<1>, dim3(stream_grid(M * C, 256)), dim3(256), 0, st, x, M, C, scale, shift, relu, y));
     B200SP_LAUNCH_CHECK_N(2);
     return B200SP_OK;
 }
@@ -421,9 +427,9 @@ extern "C" int b200sp_affine_relu(const float* x, int64_t M, int C, const float*
     B200SP_CHECK_ARG(M >= 0 && C >= 1, "affine_relu: bad sizes");
     if (M == 0) return B200SP_OK;
     if (vec4_ok(C, x, y, scale) && vec4_ok(C, shift))
-        k_affine_relu<4><<<stream_grid(M * (C / 4), 256), 256, 0, st>>>(x, M, C, scale, shift, relu, y);
+        B200SP_CUDA(launch_pdl(k_affine_relu<4>, dim3(stream_grid(M * (C / 4), 256)), dim3(256), 0, st, x, M, C, scale, shift, relu, y));
     else
-        k_affine_relu<1><<<stream_grid(M * C, 256), 256, 0, st>>>(x, M, C, scale, shift, relu, y);
+        B200SP_CUDA(launch_pdl(k_affine_relu<1>, dim3(stream_grid(M * C, 256)), dim3(256), 0, st, x, M, C, scale, shift, relu, y));
     B200SP_LAUNCH_CHECK();
     return B200SP_OK;
 }
@@ -451,15 +457,15 @@ extern "C" int b200sp_bn_bwd(const float* x, const float* dy, int64_t M, int C, 
     fin.M = M; fin.w = w; fin.b = b; fin.scale = scale; fin.shift = shift; fin.dw = dw; fin.db = db;
     fin.c_g = c_g; fin.c_mean_g = c_mg; fin.c_mean_gx = c_mgx;
     if (v4)
-        k_bn_reduce<4, 1><<<G, BN_THREADS, smem, st>>>(x, dy, M, C, nullptr, nullptr, mean, invstd, relu, partial, fin);
+        B200SP_CUDA(launch_pdl(k_bn_reduce<4, 1>, dim3(G), dim3(BN_THREADS), smem, st, x, dy, M, C, nullptr, nullptr, mean, invstd, relu, partial, fin));
     else
-        k_bn_reduce<1, 1><<<G, BN_THREADS, smem, st>>>(x, dy, M, C, nullptr, nullptr, mean, invstd, relu, partial, fin);
+        B200SP_CUDA(launch_pdl(k_bn_reduce<1, 1>, dim3(G), dim3(BN_THREADS), smem, st, x, dy, M, C, nullptr, nullptr, mean, invstd, relu, partial, fin));
     if (v4)
-        k_bn_bwd_apply<4><<<stream_grid(M * (C / 4), 256), 256, 0, st>>>(x, dy, M, C, scale, shift, mean, invstd, c_g,
-                                                                        c_mg, c_mgx, relu, dx);
+        B200SP_CUDA(launch_pdl(k_bn_bwd_apply<4>, dim3(stream_grid(M * (C / 4), 256)), dim3(256), 0, st, x, dy, M, C, scale, shift,
+                               mean, invstd, c_g, c_mg, c_mgx, relu, dx));
     else
-        k_bn_bwd_apply<1><<<stream_grid(M * C, 256), 256, 0, st>>>(x, dy, M, C, scale, shift, mean, invstd, c_g, c_mg,
-                                                                  c_mgx, relu, dx);
+        B200SP_CUDA(launch_pdl(k_bn_bwd_apply<1>, dim3(stream_grid(M * C, 256)), dim3(256), 0, st, x, dy, M, C, scale, shift, mean,
+                               invstd, c_g, c_mg, c_mgx, relu, dx));
     B200SP_LAUNCH_CHECK_N(2);
     return B200SP_OK;
 }

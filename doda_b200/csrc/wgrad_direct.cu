@@ -64,6 +64,7 @@ __global__ void __launch_bounds__(256) k_wgrad_direct(const WDParams p) {
     const int K = p.K, Ca = p.Ca, Cb = p.Cb;
     for (int i = threadIdx.x; i < K * REGS * 32; i += blockDim.x) acc_s[i] = 0.f;
     __syncthreads();
+    pdl_wait();  // the accumulator clear above overlaps the predecessor's tail
     const long long n_tiles = (p.n_rows + 15) >> 4;
 
     for (long long tile = warp; tile < n_tiles; tile += p.total_warps) {
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(256) k_wgrad_direct(const WDParams p) {
         }
     }
     __syncthreads();
+    pdl_trigger();  // late trigger (the block holds up to 55 KB of shared memory)
     // c-fragment: i = 2h + e  <->  m = g + 8h, n = 2t + e.  The lane owns, for each of its 2*CA channels of a, the
     // 4*CB consecutive channels of g starting at 4*CB*t.
     for (int idx = threadIdx.x; idx < K * 32; idx += blockDim.x) {
@@ -189,7 +191,7 @@ int launch(const WDParams& p0, cudaStream_t st) {
     const long long cap = (long long)num_sms() * per_sm;
     if (blocks > cap) blocks = cap;
     p.total_warps = (int)blocks * 8;
-    k_wgrad_direct<CA, CB><<<(unsigned)blocks, 256, smem, st>>>(p);
+    B200SP_CUDA(launch_pdl(k_wgrad_direct<CA, CB>, dim3((unsigned)blocks), dim3(256), smem, st, p));
     B200SP_LAUNCH_CHECK();
     return B200SP_OK;
 }

@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(OS_THREADS, 1) k_wgrad_os(const OSParams p) { 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *s_tmem;
+    pdl_wait();  // barrier init and TMEM allocation above overlap the predecessor's tail; no global access before here
 
     if (warp == OS_W_META) {
         // ========== tile metadata, one tile ahead ==========
@@ -478,6 +479,7 @@ __global__ void __launch_bounds__(OS_THREADS, 1) k_wgrad_os(const OSParams p) { 
         }
         }  // team < nteams
     }
+    pdl_trigger();  // late trigger: see conv_tc.cu
 #undef OS_IDX
 #undef OS_OROW
 #undef OS_GLIST
@@ -572,7 +574,7 @@ int wgrad_os_run(const float* a, int Ca, const float* g, int Cb, const int* tab,
     gx = std::min(gx, p.ntiles);
     note_kernel("k_wgrad_os");
     dim3 grid((unsigned)gx, (unsigned)npass);
-    k_wgrad_os<<<grid, OS_THREADS, smem, st>>>(p);
+    B200SP_CUDA(launch_pdl(k_wgrad_os, grid, dim3(OS_THREADS), smem, st, p));
     B200SP_LAUNCH_CHECK();
     return B200SP_OK;
 }

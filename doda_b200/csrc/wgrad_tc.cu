@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(WGTParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = p.nslots;
     const int k = blockIdx.y;
+    pdl_wait();
     const int64_t n = p.pairnum ? (int64_t)p.pairnum[k] : p.n_rows;
     const int64_t p0 = (int64_t)blockIdx.x * p.ppb;
     if (p0 >= n) return;
@@ -293,6 +294,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_wgrad_tc(WGTParams p) {
             __syncwarp();
         }
     }
+    pdl_trigger();  // late trigger: see conv_tc.cu (CTAs that returned early count as triggered)
     tc_fence_before();
     __syncthreads();
     if (warp == WG_WARP_MMA) tmem_dealloc(tmem, p.tmem_cols);
@@ -373,7 +375,7 @@ int wgrad_tc_run(const float* a, int Ca, const float* b, int Cb, const int* pa, 
     }
     note_kernel("k_wgrad_tc");
     dim3 grid((unsigned)cdiv(n_upper, ppb), (unsigned)K);
-    k_wgrad_tc<<<grid, WG_THREADS, smem, st>>>(p);
+    B200SP_CUDA(launch_pdl(k_wgrad_tc, grid, dim3(WG_THREADS), smem, st, p));
     B200SP_LAUNCH_CHECK();
     return B200SP_OK;
 }
