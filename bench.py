@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--ddp", action="store_true", help="N>1: torch DistributedDataParallel instead of parallel.allreduce_grads")
     ap.add_argument("--model", default="mirror", choices=["mirror", "reference"],
                     help="mirror: doda_b200/unet.py; reference: the reference's own model/unet.py, unchanged, via compat/")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: one gradient mean AFTER backward instead of the overlapped reducer")
+    ap.add_argument("--no-allreduce", action="store_true", help="N>1 diagnosis: skip the collective (load imbalance only)")
     ap.add_argument("--no-gpu-native", action="store_true")
     ap.add_argument("--no-m32", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -420,6 +422,13 @@ def main():
     params = [p for p in model.parameters()]
     from doda_b200 import ops as _engine_ops
     from doda_b200 import parallel
+    reducer = None
+    if world > 1 and not args.ddp:
+        parallel.broadcast_parameters(model)
+        if not args.no_overlap:
+            # the gradient mean starts as soon as backward leaves the sub-network below level 1 (97 % of the parameters)
+            reducer = parallel.OverlappedGradReducer(params, world)
+            reducer.attach(model.unet.u)
 
     def step(b):
         for p in params:  # what optimizer.zero_grad(set_to_none=True) does
@@ -432,8 +441,10 @@ def main():
         else:
             loss, _ = model_step(net, b, criterion=criterion, device=dev)
         loss.backward()
-        if world > 1 and not args.ddp:
-            parallel.allreduce_grads(params, world)  # the path's only collective: gradient mean over ranks (NCCL)
+        if reducer is not None:
+            reducer.finish()  # the path's only collective: gradient mean over ranks (NCCL), started inside backward
+        elif world > 1 and not args.ddp and not args.no_allreduce:
+            parallel.allreduce_grads(params, world)
         return loss
 
     def barrier():
@@ -572,7 +583,7 @@ def main():
                           "mid_channel": args.mid, "model": "doda_b200/unet.py (mirror of the reference model)" if
                           ref_model_fn is None else "reference model/unet.py + unet_block.py + model_fn, unchanged, via compat/",
                           "parallelism": "dp%d (whole scenes per rank, %s)"
-                          % (world, "DDP grad all-reduce" if args.ddp else "one in-place NCCL gradient mean after backward"), "l2": "256 MB flush between timed steps",
+                          % (world, "DDP grad all-reduce" if args.ddp else ("in-place NCCL gradient mean started inside backward (OverlappedGradReducer)" if reducer is not None else "one in-place NCCL gradient mean after backward")), "l2": "256 MB flush between timed steps",
                           "settle": "%d further untimed steps through the timing harness before each timed loop"
                           % SETTLE, "levels": pm_levels},
                "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,

@@ -10,15 +10,23 @@ def scene_ids(rank, world, scenes_per_rank):
     return [1000 * rank + i for i in range(scenes_per_rank)]
 
 
-def _avg_all_reduce(t, world):
+def _avg_all_reduce(t, world, async_op=False):
+    """in-place mean over ranks; async_op -> returns a callable that makes the current stream wait for it"""
     if dist.get_backend() == "nccl":
-        dist.all_reduce(t, op=dist.ReduceOp.AVG)
-    else:  # gloo has no AVG
-        dist.all_reduce(t)
+        work = dist.all_reduce(t, op=dist.ReduceOp.AVG, async_op=async_op)
+        return work.wait if async_op else None
+    work = dist.all_reduce(t, async_op=async_op)  # gloo has no AVG
+    if not async_op:
         t.div_(world)
+        return None
+
+    def done(work=work, t=t):
+        work.wait()
+        t.div_(world)
+    return done
 
 
-def allreduce_grads(params, world):
+def allreduce_grads(params, world, async_op=False):
     """Mean of the gradients over ranks, after backward, in as few collectives as there are gradient STORAGES.
 
     The engine hands out every conv weight gradient of a step as a slice of one zero-filled arena block
@@ -58,16 +66,74 @@ def allreduce_grads(params, world):
             raise RuntimeError("allreduce_grads: ranks disagree on the gradient layout %s -- a rank-asymmetric backward "
                                "(skipped step, different need_dw); use torch DDP or reduce per parameter" % (sig,))
         _checked_signatures.add(sig)
+    waits = []
     for (_, dtype), (g, lo, hi, _, _) in spans.items():  # insertion order = backward order: identical on every rank
         flat = torch.empty(0, dtype=dtype, device=g.device).set_(g.untyped_storage(), lo, (hi - lo,))
-        _avg_all_reduce(flat, world)
+        w = _avg_all_reduce(flat, world, async_op)
+        if w is not None:
+            waits.append(w)
     if rest:
         flat = torch.cat([g.reshape(-1) for g in rest])
-        _avg_all_reduce(flat, world)
-        torch._foreach_copy_(rest, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in rest]), rest)])
+        w = _avg_all_reduce(flat, world, async_op)
+
+        def copy_back(w=w, flat=flat, rest=rest):
+            if w is not None:
+                w()
+            torch._foreach_copy_(rest, [v.view_as(g) for v, g in zip(flat.split([g.numel() for g in rest]), rest)])
+        if async_op:
+            waits.append(copy_back)
+        else:
+            copy_back()
+    return waits if async_op else None
 
 
 _checked_signatures = set()
+
+
+class OverlappedGradReducer(object):
+    """Gradient mean over ranks that STARTS during backward (the role of DistributedDataParallel's bucket hooks,
+    tool/train.py:361, without its per-parameter host cost).
+
+    DODA's U-Net holds 97 % of its parameters below level 1 (`unet.u`), and backward leaves that sub-network with the
+    level-1 down conv, two residual blocks and the input conv (~2 ms of GPU work) still to run.  `attach(module)`
+    arranges that, the moment the gradient of `module`'s input features is produced -- i.e. its whole backward is
+    done -- every gradient accumulated so far is reduced with an ASYNC NCCL call (one in-place call over the dW arena
+    span they fill, one flat call for the small BN / linear ones) on the process group's own stream, overlapping the
+    rest of backward.  `finish()` after `loss.backward()` reduces what came later and makes the current stream wait.
+
+        reducer = OverlappedGradReducer(params, world); reducer.attach(model.unet.u)
+        loss.backward(); reducer.finish()
+    """
+
+    def __init__(self, params, world):
+        self.params, self.world = list(params), world
+        self._done = set()
+        self._work = []
+
+    def attach(self, module):
+        def pre(mod, inputs):
+            x = inputs[0]
+            feats = getattr(x, "features", x)
+            if torch.is_tensor(feats) and feats.requires_grad and self.world > 1:
+                feats.register_hook(self._on_grad)
+        return module.register_forward_pre_hook(pre)
+
+    def _on_grad(self, grad):
+        self._reduce([p for p in self.params if p.grad is not None and id(p) not in self._done], async_op=True)
+        return None
+
+    def _reduce(self, ps, async_op):
+        if not ps or self.world <= 1:
+            return
+        for p in ps:
+            self._done.add(id(p))
+        self._work.extend(allreduce_grads(ps, self.world, async_op=async_op) or [])
+
+    def finish(self):
+        self._reduce([p for p in self.params if p.grad is not None and id(p) not in self._done], async_op=True)
+        for w in self._work:
+            w()  # current stream waits for the collective (and the small gradients are copied back)
+        self._work, self._done = [], set()
 
 
 def broadcast_parameters(module, src=0):

@@ -133,6 +133,35 @@ parallel.allreduce_grads(big, world)
 assert all(torch.allclose(p.grad, r, atol=1e-6) for p, r in zip(big, ref))
 assert big[0].grad.untyped_storage().data_ptr() == block.untyped_storage().data_ptr()  # still the arena slice
 assert bool((sentinel == 7.0).all()) and float(block[:1024].abs().sum()) == 0.0
+# the overlapped reducer: gradients of the sub-network below the attached module are reduced from INSIDE backward
+# (tensor hook on that module's input), the rest by finish(); result == plain mean over ranks
+class Inner(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a, self.b = torch.nn.Linear(6, 6), torch.nn.Linear(6, 6)
+    def forward(self, x):
+        return self.b(torch.relu(self.a(x)))
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Linear(4, 6), Inner(), torch.nn.Linear(6, 2))
+parallel.broadcast_parameters(net)
+ps = list(net.parameters())
+red = parallel.OverlappedGradReducer(ps, world)
+red.attach(net[1])
+early = []
+orig = red._reduce
+def spy(plist, async_op):
+    early.append(len(plist))
+    return orig(plist, async_op)
+red._reduce = spy
+torch.manual_seed(100 + rank)
+x = torch.randn(9, 4)
+net(x).square().sum().backward()
+local = [p.grad.clone() for p in ps]
+red.finish()
+assert len(early) == 2 and early[0] >= 4 and early[0] + early[1] == len(ps), early  # inner + last layer first, first layer later
+for p, g in zip(ps, local):
+    r = g.clone(); dist.all_reduce(r)
+    assert torch.allclose(p.grad, r / world, atol=1e-6)
 # max-over-ranks timing reduction
 t = parallel.max_over_ranks(float(rank + 1), torch.device("cpu"))
 assert t == float(world)
