@@ -567,40 +567,42 @@ extern "C" int b200sp_wgrad(const float* a, int Ca, const float* b, int Cb, cons
     return B200SP_OK;
 }
 
-// which table-form kernel takes a shape: 1 = register-gather (wgrad_direct.cu: Ca, Cb in {16, 32}, not both 32),
-// 2 = out-stationary tcgen05 (wgrad_os.cu: everything else with channels % 8 == 0 up to 256), 0 = neither
-static int wgrad_table_kernel(int K, int Ca, int Cb) {
+// which table-form kernel takes a layer: 1 = register-gather (wgrad_direct.cu: Ca, Cb in {16, 32}, not both 32),
+// 2 = out-stationary tcgen05 (wgrad_os.cu: channels % 8 == 0 up to 256), 0 = neither (the pair-list kernels).
+// n_rows < 0: shape only.  Measured (tools/dev_wgrad_os.py, us): 300 k rows 16x16 direct 76 / os 118; 32x16 176 / 160;
+// 16x32 167 / 133; 118 k rows 32x32 os 72 / pair-list 170; 64x32 os ~150 / pair-list 259; 26.5 k rows 48x48 os 68 /
+// pair-list 46; 223 rows 96x96 os 13 / pair-list 20.
+static int wgrad_table_kernel(int K, int Ca, int Cb, int64_t n_rows) {
     if (conv_impl() != 0) return 0;
-    B200SP_ENV_INT(env_os, "B200SP_WGRAD_OS", 1);
-    if (env_os == 2 && b200sp::wgrad_os_covers(K, Ca, Cb)) return 2;
-    if (b200sp::wgrad_direct_covers(K, Ca, Cb)) return 1;
-    return b200sp::wgrad_os_covers(K, Ca, Cb) ? 2 : 0;
-}
-
-extern "C" int b200sp_wgrad_table_covers(int K, int Ca, int Cb) { return wgrad_table_kernel(K, Ca, Cb) ? 1 : 0; }
-
-// Is the table form also the FASTER one for n_rows rows?  The out-stationary tcgen05 kernel reads g once per row and
-// keeps dW in TMEM, which pays on the big levels (118 k rows, 32 x 32: 2x the pair-list kernel) and on the launch-bound
-// tiny ones; in between (level 3-5 of DODA's net) the pair-list kernel's (offset, pair range) CTAs fill the machine
-// better (tools/dev_wgrad_os.py).  Shapes the pair-list tensor kernel cannot take (Ca > 128 with wide Cb) always go
-// to the table form.
-extern "C" int b200sp_wgrad_table_prefers(int K, int Ca, int Cb, int64_t n_rows) {
-    const int which = wgrad_table_kernel(K, Ca, Cb);
-    if (which != 2) return which;
     B200SP_ENV_INT(env_os, "B200SP_WGRAD_OS", 1);
     B200SP_ENV_INT(env_lo, "B200SP_WGOS_MIN_ROWS", 50000);
     B200SP_ENV_INT(env_tiny, "B200SP_WGOS_TINY_ROWS", 512);
-    if (env_os == 2) return 1;
-    const int MB = Ca <= 64 ? 1 : (Ca + 127) / 128, Npad = (Cb + 15) / 16 * 16;
-    const bool pairlist_tc = MB * Npad <= 512 && MB <= 4;  // wgrad_tc_run's coverage
-    return (n_rows >= env_lo || n_rows <= env_tiny || !pairlist_tc) ? 1 : 0;
+    const bool direct = b200sp::wgrad_direct_covers(K, Ca, Cb);
+    const bool os = env_os && b200sp::wgrad_os_covers(K, Ca, Cb);
+    if (env_os == 2 && os) return 2;
+    if (direct && (Ca == 16 && Cb == 16)) return 1;
+    if (os) {
+        const int MB = Ca <= 64 ? 1 : (Ca + 127) / 128, Npad = (Cb + 15) / 16 * 16;
+        const bool pairlist_tc = MB * Npad <= 512 && MB <= 4;  // wgrad_tc_run's coverage
+        if (n_rows < 0) return direct ? 1 : 2;
+        if (n_rows >= env_lo || (n_rows <= env_tiny && !direct) || !pairlist_tc) return 2;
+    }
+    return direct ? 1 : 0;
+}
+
+extern "C" int b200sp_wgrad_table_covers(int K, int Ca, int Cb) { return wgrad_table_kernel(K, Ca, Cb, -1) ? 1 : 0; }
+
+// Is the table form also the FASTER one for n_rows rows?  (the dispatch rule of the layer executor)
+extern "C" int b200sp_wgrad_table_prefers(int K, int Ca, int Cb, int64_t n_rows) {
+    return wgrad_table_kernel(K, Ca, Cb, n_rows < 0 ? 0 : n_rows) ? 1 : 0;
 }
 
 extern "C" int b200sp_wgrad_table(const float* a, int Ca, const float* g, int Cb, const int32_t* tab, const int32_t* orow,
                                   const int32_t* rowmask, int64_t n_rows, int K, float* dW, void* stream) {
     B200SP_CHECK_ARG(Ca >= 1 && Cb >= 1 && K >= 1 && n_rows >= 0, "wgrad_table: bad sizes");
     B200SP_CHECK_ARG(tab || K == 1, "wgrad_table: tab == NULL requires K == 1");
-    const int which = wgrad_table_kernel(K, Ca, Cb);
+    int which = wgrad_table_kernel(K, Ca, Cb, n_rows);
+    if (!which) which = wgrad_table_kernel(K, Ca, Cb, -1);  // covered, just not preferred at this size: still runs
     B200SP_CHECK_ARG(which, "wgrad_table: shape K=%d %dx%d is not covered (ask b200sp_wgrad_table_covers; use b200sp_wgrad)", K, Ca, Cb);
     if (which == 2) return wgrad_os_run(a, Ca, g, Cb, tab, orow, rowmask, n_rows, K, dW, (cudaStream_t)stream);
     return wgrad_direct_run(a, Ca, g, Cb, tab, orow, rowmask, n_rows, K, dW, (cudaStream_t)stream);

@@ -522,19 +522,26 @@ bool os_plan(int K, int Ca, int Cb, long long n_rows, OSParams& p) {
         p.nteams = p.S == 4 ? 4 : 2;
         if (env_teams == 1 || env_teams == 2 || (env_teams == 4 && p.S == 4)) p.nteams = env_teams;
     }
-    // issuers x groups per pass: 4 issuers when the offsets then still fit into <= 8 passes (each pass re-reads the
-    // g tile) or the layer is small anyway (deep levels: latency, not traffic)
+    // issuers x groups per pass.  Every pass re-reads the g tiles and walks all tiles again, so on the big levels the
+    // FEWEST passes win and issuers come second (118 k rows, 32 x 32: one pass x 2 issuers 72 us, two passes x 4 issuers
+    // 99 us); the deep levels (a handful of tiles) want CTAs, i.e. many passes with 4 issuers each.
     B200SP_ENV_INT(env_ni, "B200SP_WGOS_ISSUERS", 0);
-    int ni = 0;
+    int ni = 0, best_pass = 1 << 30;
     for (int cand = (p.S == 4 ? 4 : 2); cand >= 1; cand >>= 1) {
-        if (env_ni && cand != env_ni && cand != 1) continue;
+        if (env_ni && cand != env_ni) continue;
         const int gpp = std::min(p.G, 512 / (cand * cols));
         if (gpp < 1) continue;
         const int npass = (p.G + gpp - 1) / gpp;
-        if (cand > 1 && npass > 8 && n_rows > 8192 && !env_ni) continue;
-        ni = cand;
-        p.gpp = gpp;
-        break;
+        if (n_rows <= 8192 && !env_ni) {  // small layer: the first (largest) issuer count that fits
+            ni = cand;
+            p.gpp = gpp;
+            break;
+        }
+        if (npass < best_pass) {
+            best_pass = npass;
+            ni = cand;
+            p.gpp = gpp;
+        }
     }
     if (ni == 0) return false;
     p.ni = ni;

@@ -31,7 +31,9 @@ def ref_wgrad(a, g, tab, K):
 
 cases = [(20000, 32, 32), (20000, 64, 32), (20000, 48, 48), (9000, 96, 48), (6149, 64, 64), (6149, 128, 64), (1381, 80, 80),
          (1381, 160, 80), (223, 96, 96), (223, 192, 96), (45, 112, 112), (20000, 16, 32)]
-if len(sys.argv) > 1 and sys.argv[1] == "big":
+if len(sys.argv) > 1 and sys.argv[1] == "l1":
+    cases = [(300000, 16, 16), (300000, 32, 16), (300000, 16, 32), (117656, 32, 32)]
+elif len(sys.argv) > 1 and sys.argv[1] == "big":
     cases = [(117656, 32, 32), (117656, 64, 32), (26506, 48, 48), (26506, 96, 48), (300000, 32, 16)]
 for M, Ca, Cb in cases:
     torch.manual_seed(0)
