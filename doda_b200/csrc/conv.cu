@@ -405,7 +405,7 @@ namespace b200sp {
 int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, int wflags, const int* tab, const int* orow,
                 const int* rowmask, const int* pin,
                 const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out, int Cout,
-                int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st);
+                int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st, int64_t n_in);
 int64_t conv_tc_ws_bytes(int K, int Cin, int Cout);
 bool conv_direct_covers(int K, int Cin, int Cout);
 void conv_direct_set(int on);
@@ -466,6 +466,14 @@ extern "C" int64_t b200sp_conv_prepared_bytes(int K, int Cin, int Cout) {
     return b200sp::conv_tc_ws_bytes(K, Cin, Cout);
 }
 
+namespace b200sp {
+void conv_tc_set_tma(int on);
+}
+extern "C" int b200sp_set_conv_tma(int on) {
+    b200sp::conv_tc_set_tma(on);
+    return B200SP_OK;
+}
+
 extern "C" int b200sp_set_conv_direct(int on) {
     b200sp::conv_direct_set(on);
     return B200SP_OK;
@@ -488,7 +496,6 @@ extern "C" int64_t b200sp_conv_ws_bytes(int K, int Cin, int Cout) {
 extern "C" int b200sp_gather_gemm(const float* in, int64_t n_in, int Cin, const float* W, int wflags, const int32_t* tab,
                                   const int32_t* orow, const int32_t* rowmask, int K, float* out, int64_t n_out, int Cout,
                                   int accumulate, void* ws, int64_t ws_bytes, void* stream) {
-    (void)n_in;
     B200SP_CHECK_ARG(Cin >= 1 && Cout >= 1 && K >= 1, "gather_gemm: bad Cin/Cout/K");
     B200SP_CHECK_ARG(K <= GG_MAXK, "gather_gemm: K=%d > %d not supported by this build", K, GG_MAXK);
     B200SP_CHECK_ARG(tab || K == 1, "gather_gemm: tab==NULL requires K==1");
@@ -499,7 +506,7 @@ extern "C" int b200sp_gather_gemm(const float* in, int64_t n_in, int Cin, const 
         int rc = conv_direct_run(in, Cin, W, wflags, tab, orow, rowmask, n_out, K, out, Cout, accumulate, st);
         if (rc != B200SP_EUNSUP) return rc;
         rc = conv_tc_run(in, Cin, W, Ci_w, Co_w, wflags, tab, orow, rowmask, nullptr, nullptr, nullptr, n_out, 0, K, out, Cout,
-                             accumulate, 0, ws, ws_bytes, st);
+                             accumulate, 0, ws, ws_bytes, st, tab ? n_in : n_out);
         if (rc != B200SP_EUNSUP) return rc;
     }
     B200SP_CHECK_ARG(!(wflags & 4), "gather_gemm: a prepared weight image needs the tensor path");
@@ -525,7 +532,7 @@ extern "C" int b200sp_gather_gemm_pairs(const float* in, int Cin, const float* W
     if (conv_impl() == 0) {
         const int Ci_w = (wflags & 1) ? Cout : Cin, Co_w = (wflags & 1) ? Cin : Cout;
         int rc = conv_tc_run(in, Cin, W, Ci_w, Co_w, wflags, nullptr, nullptr, nullptr, pin, pout, pairnum_dev, n_upper, pstride, K,
-                             out, Cout, accumulate, 1, ws, ws_bytes, st);
+                             out, Cout, accumulate, 1, ws, ws_bytes, st, 0);
         if (rc != B200SP_EUNSUP) return rc;
     }
     const float* Wuse = nullptr;

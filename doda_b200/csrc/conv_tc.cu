@@ -23,6 +23,7 @@
 // strided dgrad use the pair-grouped mode (one offset per CTA, rows scattered through the pair list).
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <algorithm>
 #include <vector>
 #include <stdlib.h>
@@ -73,6 +74,7 @@ struct TCParams {
     int nsplit;             // table mode, few row tiles: the active offsets of a row tile are dealt to the nsplit CTAs of
                             // one thread-block CLUSTER; their partial tiles meet through distributed shared memory and
                             // are added in split order 0, 1, ... (deterministic: no float atomics on the output)
+    int use_tma;            // gathers by cp.async.bulk.tensor tile::gather4 (tensor map = kernel parameter) instead of LDGSTS
     int dbg;                // dev only: 1 no MMAs, 2 no gathers, 4 no transform, 8 no epilogue data, 16 no table copy/mask, 32 no weight copies
 };
 
@@ -82,7 +84,9 @@ struct TCLayout {
     // loaders' quarter-warps (8/CPR rows x CPR chunks of 16 B) write 128 distinct bytes' worth of banks.
     static constexpr uint32_t CPR = KC / 4;                       // 16-byte chunks per row per stage
     static constexpr uint32_t LBO = TC_BM * 16u + 128u / CPR;
-    static constexpr uint32_t A_BYTES = (CPR * LBO + 127u) & ~127u;  // one of {hi, lo}
+    static constexpr uint32_t A_BYTES = (CPR * LBO + 1023u) & ~1023u;  // one of {hi, lo}; 1024-aligned: the TMA path's
+                                                                         // 128-byte-swizzled tile needs it
+    static constexpr uint32_t ROWB = KC * 4u;                          // TMA path: bytes per row of the (swizzled) K-major tile
     __host__ __device__ static uint32_t meta_ints(int KT) { return (uint32_t)(TC_BM * KT + TC_BM + TC_MAXK + 4); }
     __host__ __device__ static uint32_t offB(int nslots) { return (uint32_t)nslots * 2u * A_BYTES; }
     __host__ __device__ static uint32_t offMeta(int nslots, int nslots_b, uint32_t stageB) {
@@ -112,10 +116,10 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
 // (tile sequence number i, global stage number g); the smem stage ring and the two TMEM accumulator sets run
 // seamlessly across tiles, so gathers of tile t+1 are in flight while tile t is multiplied and tile t-1 is stored.
 template <int KC>
-__global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TCParams p) {  // 2 CTAs per SM: <= 56 registers
+__global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const TCParams p, const __grid_constant__ CUtensorMap tmap) {  // 2 CTAs per SM: <= 56 registers
     using L = TCLayout<KC>;
     constexpr int NV = KC / 4;  // 16-byte chunks per row per stage
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int S = p.nslots;
@@ -146,7 +150,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TCParams p) {  // 2 C
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], TC_XFORM_THREADS / 32);
             mbar_init(&empty[s], 1);
-            mbar_init(&raw[s], TC_LOADERS);
+            mbar_init(&raw[s], p.use_tma ? 1 : TC_LOADERS);
         }
         for (int s = 0; s < SB; ++s) {
             mbar_init(&fullb[s], 1);
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TCParams p) {  // 2 C
         }
         for (int b = 0; b < TC_NBUF; ++b) {
             mbar_init(&tready[b], 1);
-            mbar_init(&tfree[b], TC_LOADERS + 4 /*xform warps*/ + 4 /*epilogue warps*/ + ni + 1 /*weights*/);
+            mbar_init(&tfree[b], (p.use_tma ? 1 : TC_LOADERS) + 4 /*xform warps*/ + 4 /*epilogue warps*/ + ni + 1 /*weights*/);
             mbar_init(&accf[b], ni);
             mbar_init(&acce[b], 4);
             mbar_init(&tload[b], 1);
@@ -281,6 +285,47 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TCParams p) {  // 2 C
         const bool vec = (Cin % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.in) & 15) == 0);
         int slot = 0;
         uint32_t sph = 0;
+        if (p.use_tma) {
+            // ========== TMA gather: ONE warp, one cp.async.bulk.tensor tile::gather4 per lane per stage: lane l hands the
+            // TMA engine the four table entries of rows 4l..4l+3 as row coordinates (a missing neighbour, -1, is out of
+            // bounds and arrives as zeros), the engine generates the addresses, writes the 4 rows in the 128/64/32-byte
+            // swizzled K-major layout the UMMA descriptor expects and completes the bytes on raw[slot] ==========
+            if (warp == TC_W_LOAD) {
+                for (int i = 0; i < ntiles; ++i) {
+                    const int b = i & 1;
+                    mbar_wait(&tready[b], (uint32_t)(i >> 1) & 1u);
+                    const int* idx = TC_IDX(b) + 4 * lane * KT;
+                    const int* klist = TC_KLIST(b);
+                    const int nk = TC_NK(b);
+                    for (int kk = 0; kk < nk; ++kk) {
+                        const int kcol = p.pairs_mode ? 0 : klist[kk];
+                        const int r0 = idx[kcol], r1 = idx[KT + kcol], r2 = idx[2 * KT + kcol], r3 = idx[3 * KT + kcol];
+                        for (int c = 0; c < nchunks; ++c) {
+                            mbar_wait(&empty[slot], sph ^ 1u);
+                            if (lane == 0) mbar_arrive_expect_tx(&raw[slot], (uint32_t)TC_BM * L::ROWB);
+                            __syncwarp();
+                            if (!(p.dbg & 2)) {
+                                const uint32_t dst = smem_u32(sA + (size_t)slot * 2 * L::A_BYTES) + (uint32_t)lane * 4u * L::ROWB;
+                                asm volatile(
+                                    "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes "
+                                    "[%0], [%1, {%2, %3, %4, %5, %6}], [%7];\n" ::"r"(dst),
+                                    "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(c * KC), "r"(r0), "r"(r1), "r"(r2), "r"(r3),
+                                    "r"(smem_u32(&raw[slot]))
+                                    : "memory");
+                            } else if (lane == 0) {
+                                asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&raw[slot])), "r"((uint32_t)TC_BM * L::ROWB) : "memory");
+                            }
+                            if (++slot == S) {
+                                slot = 0;
+                                sph ^= 1u;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tfree[b]);
+                }
+            }
+        } else
         for (int i = 0; i < ntiles; ++i) {
             const int b = i & 1;
             mbar_wait(&tready[b], (uint32_t)(i >> 1) & 1u);
@@ -301,9 +346,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TCParams p) {  // 2 C
                         const bool colok = c0 + 4 * j < Cin;
                         const uint32_t dstb = dst0 + (uint32_t)j * L::LBO + (uint32_t)(rowb >> 3) * 128u + (uint32_t)(rowb & 7) * 16u;
                         const int* ip = idx + rowb * KT + kcol;
+                        // all table entries first: the cp.async asm is a compiler barrier ("memory"), interleaved with
+                        // it every index load would sit in its own LDS -> compare -> address -> LDGSTS chain
+                        int srcs[CPR];
+#pragma unroll
+                        for (int q = 0; q < CPR; ++q) srcs[q] = ip[q * RPQ * KT];
 #pragma unroll
                         for (int q = 0; q < CPR; ++q) {
-                            const int src = ip[q * RPQ * KT];
+                            const int src = srcs[q];
                             const bool ok = (src >= 0) && colok;
                             const float* g = p.in + ((int64_t)(ok ? src : 0) * Cin + (ok ? c0 + 4 * j : 0));
                             cp_async16_zfill(dstb + (uint32_t)q * (RPQ / 8) * 128u, g, ok ? 16 : 0);
@@ -349,7 +399,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TCParams p) {  // 2 C
                 mbar_wait(&raw[slot], sph);
 #pragma unroll
                 for (int q = 0; q < ((p.dbg & 4) ? 0 : NV); ++q) {
-                    const uint32_t off = (uint32_t)q * L::LBO + soff;
+                    // legacy layout: this thread's row, chunk q; TMA layout: any bijection will do (lo sits at the same
+                    // swizzled position as hi), so consecutive threads take consecutive 16-byte pieces
+                    const uint32_t off = p.use_tma ? (uint32_t)(q * TC_XFORM_THREADS + tid) * 16u : (uint32_t)q * L::LBO + soff;
                     const float4 v = *reinterpret_cast<const float4*>(a_hi + off);
                     float4 h, l;
                     split_tf32(v.x, h.x, l.x);
@@ -453,9 +505,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TCParams p) {  // 2 C
             const uint32_t idesc = make_idesc_tf32(TC_BM, p.Cout_pad, 0, 0);
             const uint32_t lboB = (uint32_t)p.Cout_pad * 16u;  // K-adjacent core matrices of B
             // descriptors of slot 0 (hi tiles); lo tiles / other slots / K steps are constant offsets in 16-byte units
-            const uint64_t dA0 = make_desc(smem_u32(sA), L::LBO, 128u);
+            // A: legacy = un-swizzled canonical K-major (LBO between 16-byte K chunks, 128 B between 8-row groups);
+            // TMA = swizzled K-major rows of ROWB bytes (SBO = 8 rows, layout code 2 / 4 / 6 = SWIZZLE_128B / 64B / 32B)
+            const uint64_t dA0 = p.use_tma
+                                     ? (make_desc(smem_u32(sA), 16u, 8u * L::ROWB) |
+                                        ((uint64_t)(KC == 32 ? 2 : (KC == 16 ? 4 : 6)) << 61))
+                                     : make_desc(smem_u32(sA), L::LBO, 128u);
             const uint64_t dB0 = make_desc(smem_u32(sB), lboB, 128u);
-            const uint32_t slotA16 = (2u * L::A_BYTES) >> 4, loA16 = L::A_BYTES >> 4, kA16 = (2u * L::LBO) >> 4;
+            const uint32_t slotA16 = (2u * L::A_BYTES) >> 4, loA16 = L::A_BYTES >> 4, kA16 = p.use_tma ? 2u : (2u * L::LBO) >> 4;
             const uint32_t slotB16 = p.stageB_bytes >> 4, loB16 = p.stageB_bytes >> 5, kB16 = (2u * lboB) >> 4;
             int g0 = 0;
             uint32_t aph[TC_NBUF] = {0, 0};  // as in the epilogue: empty tiles do not touch the accumulator barriers
@@ -687,7 +744,7 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl, int64_t n_tile
     pl.stageB = 2u * (uint32_t)pl.Cout_pad * pl.KC * 4u;
     pl.wp_bytes = (int64_t)K * pl.nchunks * pl.stageB;
     const uint32_t cpr = (uint32_t)pl.KC / 4u;
-    const uint32_t a_bytes = 2u * ((cpr * (TC_BM * 16u + 128u / cpr) + 127u) & ~127u);
+    const uint32_t a_bytes = 2u * ((cpr * (TC_BM * 16u + 128u / cpr) + 1023u) & ~1023u);
     const uint32_t fixed = TC_NBUF * (uint32_t)(TC_BM * KT + TC_BM + TC_MAXK + 4) * 4u + 1536u;
     // slots: 4 under ~110 KB lets two CTAs share an SM; big stages fall back to fewer slots / one CTA per SM
     int best = 0;
@@ -748,10 +805,63 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl, int64_t n_tile
     return true;
 }
 
+static int g_tc_tma = -1;
+int conv_tc_tma_enabled() {
+    if (g_tc_tma < 0) {
+        const char* e = getenv("B200SP_TC_TMA");
+        g_tc_tma = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_tc_tma;
+}
+void conv_tc_set_tma(int on) { g_tc_tma = on ? 1 : 0; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links cudart only)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+
+// 2-D map of the feature matrix [rows][Cin] fp32 for tile::gather4: box = {KC columns, 1 row} (the instruction names 4
+// rows), swizzle = the row size (128 / 64 / 32 B), out-of-bounds rows / columns read as zeros
+static bool make_gather_map(const float* in, int64_t rows, int Cin, int KC, CUtensorMap* map) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)Cin * 4u};
+    cuuint32_t box[2] = {(cuuint32_t)KC, 1u};
+    cuuint32_t estr[2] = {1u, 1u};
+    const CUtensorMapSwizzle sw = KC == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : (KC == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int KC>
-static int launch_tc(const TCParams& p0, int KT, cudaStream_t st) {
+static int launch_tc(const TCParams& p0, int KT, int64_t n_in, cudaStream_t st) {
     using L = TCLayout<KC>;
     TCParams p = p0;
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    {
+        // TMA gather is possible whenever the rows are 16-byte aligned multiples of 16 bytes (everything but the 3-channel
+        // input conv).  It is OPT-IN (B200SP_TC_TMA=1 / b200sp_set_conv_tma): measured per launch, gather4 vs LDGSTS:
+        // 26.5 k rows x 48 ch 115 vs 65 us, 6 148 x 64 58 vs 47, 1 380 x 80 43 vs 29, 222 x 96 29 vs 25 -- with 64..128-byte
+        // rows one gather4 moves 256..512 bytes and the 32 instructions of a stage are bound by the TMA unit's issue
+        // rate, while 128 LDGSTS threads issue in parallel.
+        const int env_tma = conv_tc_tma_enabled();
+        p.use_tma = 0;
+        if (env_tma && p.Cin % 4 == 0 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && p.Cin >= KC / 2)
+            p.use_tma = make_gather_map(p.in, n_in > 0 ? n_in : ((int64_t)1 << 31) - 1, p.Cin, KC, &tmap) ? 1 : 0;
+    }
     const uint32_t smem = L::total(p.nslots, p.nslots_b, p.stageB_bytes, KT);
     static uint32_t attr_smem = 0;
     if (smem > attr_smem) {
@@ -784,13 +894,13 @@ static int launch_tc(const TCParams& p0, int KT, cudaStream_t st) {
             attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
             cfg.numAttrs = pdl_enabled() ? 2 : 1;
-            B200SP_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<KC>, p));
+            B200SP_CUDA(cudaLaunchKernelEx(&cfg, k_conv_tc<KC>, p, tmap));
             B200SP_LAUNCH_CHECK();
             return B200SP_OK;
         }
     }
     const int grid = std::min(p.total_tiles, num_sms() * occ);
-    B200SP_CUDA(launch_pdl(k_conv_tc<KC>, dim3((unsigned)grid), dim3(TC_THREADS), smem, st, p));
+    B200SP_CUDA(launch_pdl(k_conv_tc<KC>, dim3((unsigned)grid), dim3(TC_THREADS), smem, st, p, tmap));
     B200SP_LAUNCH_CHECK();
     return B200SP_OK;
 }
@@ -798,7 +908,7 @@ static int launch_tc(const TCParams& p0, int KT, cudaStream_t st) {
 // returns B200SP_EUNSUP when the shape is outside what the tensor path covers (caller falls back to the fp32 kernel)
 int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, int wflags, const int* tab, const int* orow,
                 const int* rowmask, const int* pin, const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out,
-                int Cout, int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                int Cout, int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st, int64_t n_in) {
     TCPlan pl;
     const int KT = pairs_mode ? 1 : K;
     if (!tc_plan(K, Cin, Cout, KT, pl, cdiv(n_rows, TC_BM) * (pairs_mode ? K : 1))) return B200SP_EUNSUP;
@@ -838,9 +948,9 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
         if (!env_nosplit) p.nsplit = std::max(1, std::min(std::min(K, env_maxsplit), 2 * num_sms() / p.row_tiles));
     }
     p.total_tiles = p.row_tiles * (pairs_mode ? K : p.nsplit);  // split mode: finalised by launch_tc (residency)
-    if (pl.KC == 32) return launch_tc<32>(p, KT, st);
-    if (pl.KC == 16) return launch_tc<16>(p, KT, st);
-    return launch_tc<8>(p, KT, st);
+    if (pl.KC == 32) return launch_tc<32>(p, KT, n_in, st);
+    if (pl.KC == 16) return launch_tc<16>(p, KT, n_in, st);
+    return launch_tc<8>(p, KT, n_in, st);
 }
 
 // rows of desc_host: {W ptr, Wp ptr, K, Ci_w, Co_w, wflags}; desc_dev: device scratch of n * sizeof(PrepItem) bytes

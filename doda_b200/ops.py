@@ -63,6 +63,11 @@ def set_conv_direct(on):
     invalidate_prepared_weights()
 
 
+def set_conv_tma(on):
+    """tcgen05 conv kernel: gather rows with TMA (tile::gather4) instead of cp.async (A/B testing; same results)"""
+    check(lib.b200sp_set_conv_tma(1 if on else 0), "set_conv_tma")
+
+
 def launch_count():
     """CUDA kernels launched by libb200sparse in this process (bench.py: gpu_launches)."""
     return int(lib.b200sp_launch_count())

@@ -147,6 +147,10 @@ int b200sp_set_conv_impl(int impl);
  * everything else runs the persistent tcgen05 kernel.  on = 0 switches the register-gather kernel off
  * (also B200SP_DIRECT=0); _covers tells which kernel a shape would get. */
 int b200sp_set_conv_direct(int on);
+/* on = 1: the tcgen05 conv kernel gathers its rows with TMA (cp.async.bulk.tensor tile::gather4, swizzled K-major tiles)
+ * instead of per-thread cp.async; also B200SP_TC_TMA=1.  Same results bit for bit; off by default (measured slower for
+ * the 64..128-byte rows of this path, csrc/conv_tc.cu). */
+int b200sp_set_conv_tma(int on);
 int b200sp_conv_direct_covers(int K, int Cin, int Cout);
 
 /* weight gradient: dW[k][ci][co] += sum_i a[pa[k][i]][ci] * b[pb[k][i]][co].   pa/pb NULL -> identity

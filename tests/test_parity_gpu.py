@@ -729,6 +729,44 @@ def test_conv_impls_agree(cuda_dev, impl):
     assert rel_err(a, ref) <= TOL and rel_err(b, ref) <= TOL
 
 
+@pytest.mark.parametrize("C", [(48, 48), (64, 32), (16, 80), (112, 112)])
+def test_tma_gather4_loader_matches_the_cp_async_loader(cuda_dev, C):
+    """k_conv_tc's two gather engines -- per-thread cp.async into the un-swizzled canonical layout, and TMA
+    cp.async.bulk.tensor tile::gather4 into 128/64/32-byte-swizzled K-major tiles (row coordinates straight from the
+    rulebook table, -1 = out of bounds = zeros) -- feed the same MMAs: identical results bit for bit, table and pair
+    mode, forward and dgrad, and both within the fp32 bar of the oracle"""
+    from doda_b200 import ops
+    torch.manual_seed(7)
+    Cin, Cout = C
+    coords, shape = surface_coords(5, 9000, 2)
+    c = torch.from_numpy(coords).to(cuda_dev)
+    rb = ops.build_rulebook(c, 2, shape, 3, 1, 1, 1, subm=True)
+    rbs = ops.build_rulebook(c, 2, shape, 2, 2, 0, 1, subm=False)
+    n = c.shape[0]
+    x = torch.randn(n, Cin, device=cuda_dev)
+    g = torch.randn(n, Cout, device=cuda_dev)
+    xc = torch.randn(rbs.outids.shape[0], Cin, device=cuda_dev)
+    W3 = torch.randn(27, Cin, Cout, device=cuda_dev) * 0.2
+    W8 = torch.randn(8, Cin, Cout, device=cuda_dev) * 0.2
+    outs = {}
+    try:
+        for tma in (0, 1):
+            ops.set_conv_tma(tma)
+            outs[tma] = (ops.gather_gemm(x, W3, rb.nbr_perm, n, orow=rb.order, rowmask=rb.rowmask),
+                         ops.gather_gemm(g, W3, rb.nbr_perm, n, wflags=ops.W_T_MIRROR, orow=rb.order, rowmask=rb.rowmask),
+                         ops.gather_gemm_pairs(xc, W8, rbs.pairs[1], rbs.pairs[0], rbs.pairnum, n, n))
+    finally:
+        ops.set_conv_tma(0)
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a, b)
+    ref = torch.zeros(n, Cout, dtype=torch.float64)
+    fd, Wd, t = x.double().cpu(), W3.double().cpu(), rb.nbr.cpu().long()
+    for k in range(27):
+        m = t[:, k] >= 0
+        ref[m] += fd[t[m, k]] @ Wd[k]
+    assert rel_err(outs[1][0], ref) <= TOL
+
+
 def test_spconv_surface_sequential_semantics(cuda_dev):
     """SparseSequential mutates .features of the SAME object for dense modules."""
     from doda_b200 import spconv
