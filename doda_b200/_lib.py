@@ -17,6 +17,7 @@ _CTYPE = {
     "int32_t": ctypes.c_int32,
     "int64_t": ctypes.c_int64,
     "float": ctypes.c_float,
+    "double": ctypes.c_double,
 }
 
 

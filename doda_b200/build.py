@@ -9,7 +9,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libb200sparse.so")
 FAST_SRC = os.path.join(CSRC, "fastcall.c")
 FAST_OUT = os.path.join(HERE, "_b200fast.so")  # CPython module doda_b200._b200fast (fast-call binding of the hot entry points)
-SOURCES = ["core.cu", "rulebook.cu", "conv.cu", "conv_tc.cu", "conv_direct.cu", "wgrad_tc.cu", "wgrad_direct.cu", "wgrad_os.cu", "layer.cu", "elementwise.cu", "loss.cu", "voxelize_gpu.cu", "pgops.cu", "pointops.cu"]
+SOURCES = ["core.cu", "rulebook.cu", "conv.cu", "conv_tc.cu", "conv_direct.cu", "wgrad_tc.cu", "wgrad_direct.cu", "wgrad_os.cu", "layer.cu", "elementwise.cu", "loss.cu", "voxelize_gpu.cu", "pgops.cu", "pointops.cu", "augment.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", 
          "-Xcompiler", "-fPIC", "-DB200SP_BUILD"]

@@ -39,6 +39,14 @@ struct BNFinal {
     float* c_mean_gx;
 };
 
+// the forward's fused shift, spelled once so that the forward's ReLU and every backward's gate test round identically
+__device__ __forceinline__ float bn_shift(float b, float mu, float sc) { return fmaf(-mu, sc, b); }
+
+// single-launch form for small layers (defined at the end of this file); *done = false when the layer does not qualify
+int bn_cluster_fwd(const float* x, int64_t M, int C, int relu, float* y, const BNFinal& fin, cudaStream_t st, bool* done);
+int bn_cluster_bwd(const float* x, const float* dy, int64_t M, int C, int relu, float* dx, const BNFinal& fin, const float* mean,
+                   const float* invstd, cudaStream_t st, bool* done);
+
 template <int VEC, int MODE>
 __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restrict__ x, const float* __restrict__ dy,
                                                           int64_t M, int C, const float* __restrict__ scale,
@@ -74,7 +82,7 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restric
             mu[v] = mean[c];
             is[v] = invstd[c];
             sc[v] = (fin.w ? fin.w[c] : 1.f) * is[v];  // the forward's fused scale / shift, recomputed per block
-            sh[v] = (fin.b ? fin.b[c] : 0.f) - mu[v] * sc[v];
+            sh[v] = bn_shift(fin.b ? fin.b[c] : 0.f, mu[v], sc[v]);
         }
     }
     if (active) {
@@ -199,7 +207,7 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restric
             const float wv = fin.w ? fin.w[c] : 1.f, bv = fin.b ? fin.b[c] : 0.f;
             const float scv = wv * is;
             fin.scale[c] = scv;
-            fin.shift[c] = bv - (float)mu * scv;
+            fin.shift[c] = bn_shift(bv, (float)mu, scv);
         } else {
             if (fin.dw) fin.dw[c] = (float)s1;
             if (fin.db) fin.db[c] = (float)s0;
@@ -210,7 +218,7 @@ __global__ void __launch_bounds__(BN_THREADS) k_bn_reduce(const float* __restric
             fin.c_mean_gx[c] = (float)(s1 / (double)fin.M);
             const float scv = wv * isv;
             fin.scale[c] = scv;
-            fin.shift[c] = (fin.b ? fin.b[c] : 0.f) - mean[c] * scv;
+            fin.shift[c] = bn_shift(fin.b ? fin.b[c] : 0.f, mean[c], scv);
         }
     }
     if (tid == 0) {
@@ -409,6 +417,11 @@ extern "C" int b200sp_bn_fwd_train(const float* x, int64_t M, int C, const float
     fin.M = M; fin.w = w; fin.b = b; fin.eps = eps; fin.momentum = momentum; fin.mean = mean; fin.invstd = invstd;
     fin.running_mean = running_mean; fin.running_var = running_var;
     fin.num_batches_tracked = (long long*)num_batches_tracked; fin.scale = scale; fin.shift = shift;
+    if (v4) {
+        bool done = false;
+        int rc = bn_cluster_fwd(x, M, C, relu, y, fin, st, &done);
+        if (rc != B200SP_OK || done) return rc;
+    }
     if (v4)
         B200SP_CUDA(launch_pdl(k_bn_reduce<4, 0>, dim3(G), dim3(BN_THREADS), smem, st, x, nullptr, M, C, nullptr, nullptr, nullptr, nullptr, 0, partial, fin));
     else
@@ -456,6 +469,11 @@ extern "C" int b200sp_bn_bwd(const float* x, const float* dy, int64_t M, int C, 
     fin.ticket = reinterpret_cast<unsigned*>(ws);
     fin.M = M; fin.w = w; fin.b = b; fin.scale = scale; fin.shift = shift; fin.dw = dw; fin.db = db;
     fin.c_g = c_g; fin.c_mean_g = c_mg; fin.c_mean_gx = c_mgx;
+    if (v4) {
+        bool done = false;
+        int rc = bn_cluster_bwd(x, dy, M, C, relu, dx, fin, mean, invstd, st, &done);
+        if (rc != B200SP_OK || done) return rc;
+    }
     if (v4)
         B200SP_CUDA(launch_pdl(k_bn_reduce<4, 1>, dim3(G), dim3(BN_THREADS), smem, st, x, dy, M, C, nullptr, nullptr, mean, invstd, relu, partial, fin));
     else
@@ -523,3 +541,241 @@ extern "C" int b200sp_scatter_add_rows(const float* src, const void* idx, int id
     B200SP_LAUNCH_CHECK();
     return B200SP_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm(+ReLU) for SMALL layers in ONE launch: the rows are dealt to the CTAs of one thread-block cluster, every
+// CTA keeps its slice in shared memory, the per-channel partial sums meet through distributed shared memory (added in
+// rank order: deterministic), and the normalised rows are written from shared memory -- x (and dy) cross L2 once
+// instead of twice and the deep U-Net levels (45 .. 6 k rows: a 7-12 us floor per launch in the two-kernel form) pay
+// one launch instead of two.
+// ---------------------------------------------------------------------------------------------
+namespace b200sp {
+
+constexpr int BNC_THREADS = 256;
+constexpr int BNC_MAX_CLUSTER = 16;  // > 8 is the opt-in (non-portable) cluster size; a B200 GPC holds it
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem(const float* local_smem_ptr, int rank) {
+    uint32_t laddr = (uint32_t)__cvta_generic_to_shared(local_smem_ptr), raddr;
+    float v;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(laddr), "r"(rank));
+    asm volatile("ld.shared::cluster.f32 %0, [%1];\n" : "=f"(v) : "r"(raddr) : "memory");
+    return v;
+}
+
+// MODE 0: forward (statistics + apply);  MODE 1: backward (sum g, sum g*xhat, dx)
+// smem: xs [rows_cta][C] (| gs [rows_cta][C] for MODE 1) | part [2][C] | coef [4][C]
+template <int MODE>
+__global__ void __launch_bounds__(BNC_THREADS) k_bn_cluster(const float* __restrict__ x, const float* __restrict__ dy,
+                                                            int64_t M, int C, int rows_cta, int relu, float* __restrict__ out,
+                                                            BNFinal fin, const float* __restrict__ mean_in,
+                                                            const float* __restrict__ invstd_in) {
+    extern __shared__ __align__(16) float s_bnc[];
+    pdl_trigger();
+    pdl_wait();
+    unsigned rank, nranks;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(rank));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;\n" : "=r"(nranks));
+    const int tid = threadIdx.x;
+    const int C4 = C >> 2;
+    const int64_t r0 = (int64_t)rank * rows_cta;
+    const int rows = (int)max((int64_t)0, min((int64_t)rows_cta, M - r0));
+    float* xs = s_bnc;
+    float* gs = xs + (size_t)rows_cta * C;
+    float* part = (MODE == 1 ? gs + (size_t)rows_cta * C : gs);
+    float* coef = part + 2 * C;
+    // ---- load the slice (coalesced float4) ----
+    const int n4 = rows * C4;
+#pragma unroll 4
+    for (int i = tid; i < n4; i += BNC_THREADS) {
+        reinterpret_cast<float4*>(xs)[i] = __ldg(reinterpret_cast<const float4*>(x + r0 * C) + i);
+        if (MODE == 1) reinterpret_cast<float4*>(gs)[i] = __ldg(reinterpret_cast<const float4*>(dy + r0 * C) + i);
+    }
+    __syncthreads();
+    // ---- per-channel partial sums over this CTA's rows: thread (rl, c) with c the channel; rows strided ----
+    const int rpb = BNC_THREADS / C > 0 ? BNC_THREADS / C : 1;  // row lanes per channel (C <= 256)
+    const int c = tid % C, rl = tid / C;
+    float a0 = 0.f, a1 = 0.f;
+    float shift = 0.f, mu = 0.f, is = 0.f, sc = 0.f, sh = 0.f;
+    if (rl < rpb && tid < rpb * C) {
+        if (MODE == 0) {
+            shift = __ldg(x + c);  // row 0 of the whole layer: the same shift in every CTA
+            for (int r = rl; r < rows; r += rpb) {
+                const float d = xs[r * C + c] - shift;
+                a0 += d;
+                a1 = fmaf(d, d, a1);
+            }
+        } else {
+            mu = mean_in[c];
+            is = invstd_in[c];
+            sc = (fin.w ? fin.w[c] : 1.f) * is;
+            sh = bn_shift(fin.b ? fin.b[c] : 0.f, mu, sc);
+            for (int r = rl; r < rows; r += rpb) {
+                const float xv = xs[r * C + c];
+                float g = gs[r * C + c];
+                if (relu && fmaf(xv, sc, sh) <= 0.f) g = 0.f;
+                gs[r * C + c] = g;  // masked gradient, reused by the apply pass
+                a0 += g;
+                a1 = fmaf(g, (xv - mu) * is, a1);
+            }
+        }
+    }
+    // the row lanes of one channel meet in shared memory
+    __shared__ float s_red[2 * BNC_THREADS];
+    s_red[tid] = a0;
+    s_red[BNC_THREADS + tid] = a1;
+    __syncthreads();
+    if (tid < C) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int l = 0; l < rpb; ++l) {
+            s0 += s_red[l * C + tid];
+            s1 += s_red[BNC_THREADS + l * C + tid];
+        }
+        part[tid] = s0;
+        part[C + tid] = s1;
+    }
+    cluster_sync_all();
+    // ---- every CTA adds the partials of all ranks in rank order (fp64) and derives the coefficients ----
+    if (tid < C) {
+        double s0 = 0.0, s1 = 0.0;
+        for (unsigned rk = 0; rk < nranks; ++rk) {
+            s0 += (double)ld_dsmem(part + tid, (int)rk);
+            s1 += (double)ld_dsmem(part + C + tid, (int)rk);
+        }
+        if (MODE == 0) {
+            const double dm = s0 / (double)M;
+            const double mud = (double)__ldg(x + tid) + dm;
+            double var = s1 / (double)M - dm * dm;
+            if (var < 0.0) var = 0.0;
+            const float isv = (float)(1.0 / sqrt(var + (double)fin.eps));
+            const float wv = fin.w ? fin.w[tid] : 1.f, bv = fin.b ? fin.b[tid] : 0.f;
+            const float scv = wv * isv;
+            coef[tid] = scv;
+            coef[C + tid] = bn_shift(bv, (float)mud, scv);
+            if (rank == 0) {
+                if (fin.scale) fin.scale[tid] = scv;
+                if (fin.shift) fin.shift[tid] = coef[C + tid];
+                fin.mean[tid] = (float)mud;
+                fin.invstd[tid] = isv;
+                if (fin.running_mean) fin.running_mean[tid] = (1.f - fin.momentum) * fin.running_mean[tid] + fin.momentum * (float)mud;
+                if (fin.running_var) {
+                    const float vu = (float)(M > 1 ? var * (double)M / (double)(M - 1) : var);
+                    fin.running_var[tid] = (1.f - fin.momentum) * fin.running_var[tid] + fin.momentum * vu;
+                }
+            }
+        } else {
+            const float wv = fin.w ? fin.w[tid] : 1.f;
+            const float isv = invstd_in[tid];
+            coef[tid] = wv * isv;                       // c_g
+            coef[C + tid] = (float)(s0 / (double)M);    // mean g
+            coef[2 * C + tid] = (float)(s1 / (double)M);  // mean g*xhat
+            coef[3 * C + tid] = mean_in[tid];
+            if (rank == 0) {
+                if (fin.dw) fin.dw[tid] = (float)s1;
+                if (fin.db) fin.db[tid] = (float)s0;
+            }
+        }
+    }
+    if (MODE == 0 && rank == 0 && tid == 0 && fin.num_batches_tracked) *fin.num_batches_tracked += 1;
+    __syncthreads();
+    // ---- apply from shared memory ----
+    for (int i = tid; i < n4; i += BNC_THREADS) {
+        const int c4 = (i % C4) * 4;
+        const float4 xv = reinterpret_cast<const float4*>(xs)[i];
+        float4 o;
+        if (MODE == 0) {
+            o.x = fmaf(xv.x, coef[c4], coef[C + c4]);
+            o.y = fmaf(xv.y, coef[c4 + 1], coef[C + c4 + 1]);
+            o.z = fmaf(xv.z, coef[c4 + 2], coef[C + c4 + 2]);
+            o.w = fmaf(xv.w, coef[c4 + 3], coef[C + c4 + 3]);
+            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        } else {
+            const float4 g = reinterpret_cast<const float4*>(gs)[i];
+            const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ga[4] = {g.x, g.y, g.z, g.w};
+            float r[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int cc = c4 + e;
+                const float xhat = (xa[e] - coef[3 * C + cc]) * invstd_in[cc];
+                r[e] = coef[cc] * (ga[e] - coef[C + cc] - xhat * coef[2 * C + cc]);
+            }
+            o = make_float4(r[0], r[1], r[2], r[3]);
+        }
+        reinterpret_cast<float4*>(out + r0 * C)[i] = o;
+    }
+    cluster_sync_all();  // nobody exits while a peer may still read its partial sums
+}
+
+// cluster size and rows per CTA for a small layer, or 0 when the layer does not fit / is not worth it
+static int bn_cluster_plan(int64_t M, int C, int mode, int* rows_cta, size_t* smem) {
+    B200SP_ENV_INT(env_max, "B200SP_BN_CLUSTER", 0);        // largest cluster (0 = never; 16 = opt-in non-portable size)
+    B200SP_ENV_INT(env_kb, "B200SP_BN_CLUSTER_KB", 64);     // largest slice per CTA
+    if (env_max <= 0 || C % 4 != 0 || C > BNC_THREADS || M < 1) return 0;
+    const size_t per_row = (size_t)C * 4u * (mode == 1 ? 2u : 1u);
+    const size_t fixed = (size_t)6 * C * 4u + 64u;
+    // one SM streams its slice at ~0.15 TB/s: past ~64 KB per CTA the two-kernel form (whole-GPU grids) is faster
+    // (measured: 6149 x 64 in 8 slices of 196 KB, 16.6 us against 13.4 us)
+    const size_t cap = (size_t)(env_kb > 200 ? 200 : env_kb) * 1024u;
+    const int nmax = env_max > BNC_MAX_CLUSTER ? BNC_MAX_CLUSTER : env_max;
+    for (int n = 1; n <= nmax; n <<= 1) {
+        const int64_t rc = (M + n - 1) / n;
+        const size_t need = (size_t)rc * per_row + fixed;
+        if (need <= cap && (need <= 32u * 1024u || n * 2 > nmax)) {
+            *rows_cta = (int)rc;
+            *smem = need;
+            return n;
+        }
+    }
+    return 0;
+}
+
+template <int MODE>
+static int bn_cluster_launch(int nclu, int rows_cta, size_t smem, const float* x, const float* dy, int64_t M, int C, int relu,
+                             float* out, const BNFinal& fin, const float* mean, const float* invstd, cudaStream_t st) {
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        B200SP_CUDA(cudaFuncSetAttribute(k_bn_cluster<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        B200SP_CUDA(cudaFuncSetAttribute(k_bn_cluster<MODE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        attr_smem = 200 * 1024;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)nclu);
+    cfg.blockDim = dim3(BNC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)nclu;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    B200SP_CUDA(cudaLaunchKernelEx(&cfg, k_bn_cluster<MODE>, x, dy, M, C, rows_cta, relu, out, fin, mean, invstd));
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}
+
+int bn_cluster_fwd(const float* x, int64_t M, int C, int relu, float* y, const BNFinal& fin, cudaStream_t st, bool* done) {
+    int rows_cta = 0;
+    size_t smem = 0;
+    const int n = bn_cluster_plan(M, C, 0, &rows_cta, &smem);
+    *done = n > 0;
+    if (!n) return B200SP_OK;
+    return bn_cluster_launch<0>(n, rows_cta, smem, x, nullptr, M, C, relu, y, fin, nullptr, nullptr, st);
+}
+int bn_cluster_bwd(const float* x, const float* dy, int64_t M, int C, int relu, float* dx, const BNFinal& fin, const float* mean,
+                   const float* invstd, cudaStream_t st, bool* done) {
+    int rows_cta = 0;
+    size_t smem = 0;
+    const int n = bn_cluster_plan(M, C, 1, &rows_cta, &smem);
+    *done = n > 0;
+    if (!n) return B200SP_OK;
+    return bn_cluster_launch<1>(n, rows_cta, smem, x, dy, M, C, relu, dx, fin, mean, invstd, st);
+}
+
+}  // namespace b200sp

@@ -345,6 +345,25 @@ int b200sp_cross_entropy_bwd(const float* logits_dev, const int64_t* labels_dev,
 int b200sp_intersection_union(const int64_t* pred_dev, const int64_t* label_dev, int64_t N, int K,
                               int64_t ignore_index, float* out3k_dev, void* ws_dev, int64_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Augmentation hot spots, replacing the numpy / scipy bodies of
+ * dataset/augmentor/augmentor_utils.py on the data-loading side.  Arithmetic as the reference: float32 noise grids
+ * blurred with double accumulation per pass, double interpolation, double coordinates out.
+ * ------------------------------------------------------------------------------------------ */
+/* elastic, augmentor_utils.py:62-73: six 3-tap box passes (axes 0,1,2,0,1,2; zero outside the grid) over the three
+ * noise grids noise_dev float[3][nx][ny][nz] in place; scratch_dev: same size. */
+int b200sp_elastic_blur(float* noise_dev, float* scratch_dev, int nx, int ny, int nz, void* stream);
+/* elastic, augmentor_utils.py:74-80: out = x + mag * trilinear(noise, x) on the axes linspace(-(n-1)*gran, (n-1)*gran, n);
+ * points outside the grid get 0 (bounds_error=0, fill_value=0).  xyz_dev: float or double [N,3]; out_dev: double [N,3]. */
+int b200sp_elastic_apply(const void* xyz_dev, int xyz_is_f64, int64_t N, const float* noise_dev, int nx, int ny, int nz,
+                         double gran, double mag, double* out_dev, void* stream);
+/* crop, augmentor_utils.py:459-470: xyz_offset = xyz + offset; valid &= (xyz_offset.min(1) >= 0) & all(xyz_offset <
+ * full_scale); *count_dev = valid.sum().  valid_u8_dev: uint8 [N] in/out; xyz_offset_dev: double [N,3] or NULL. */
+int b200sp_crop_mask(const double* xyz_dev, int64_t N, const double* offset3_host, const double* full_scale3_host,
+                     void* valid_u8_dev, double* xyz_offset_dev, int32_t* count_dev, void* stream);
+/* scene_aug, augmentor_utils.py:103: out = xyz @ m (m9_host row-major 3x3: jitter / flip / rotation) */
+int b200sp_affine3(const void* xyz_dev, int xyz_is_f64, int64_t N, const double* m9_host, double* out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

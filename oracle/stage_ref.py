@@ -33,6 +33,7 @@ FILES = [
     "util/config.py", "util/pseudo_labels_util.py",
     "cfgs/da_front3d_scannet/spconv.yaml", "cfgs/dataset_cfgs/scannet/scannet_cfg.yaml",
     "cfgs/dataset_cfgs/front3d/front3d_cfg.yaml",
+    "dataset/augmentor/augmentor_utils.py",   # elastic / crop / scene_aug: the f3 row's parity target
 ]
 
 
@@ -156,6 +157,27 @@ def make_cfg(mid_channel=16, n_classes=11, block_residual=True, voxel_mode=4, us
                         "DATA_PROCESSOR": {"voxel_mode": voxel_mode}},
         "OPTIMIZATION": {"loss": loss},
     })
+
+
+def load_augmentor_utils():
+    """the staged dataset/augmentor/augmentor_utils.py as a module, loaded from its file (the `dataset` package's own
+    __init__ pulls the whole data pipeline in); None when nothing is staged.  cv2 / open3d are stubbed when absent."""
+    import importlib.util
+    root = activate()
+    if root is None:
+        return None
+    path = os.path.join(root, "dataset", "augmentor", "augmentor_utils.py")
+    if not os.path.exists(path):
+        return None
+    if "cv2" not in sys.modules:
+        try:
+            import cv2  # noqa: F401
+        except ImportError:
+            sys.modules["cv2"] = types.ModuleType("cv2")
+    spec = importlib.util.spec_from_file_location("_ref_augmentor_utils", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
 if __name__ == "__main__":

@@ -233,3 +233,52 @@ def test_encoder_decoder_oracle_restores_the_active_set_and_is_linear_without_bn
     y = f(2 * x1 - 3 * x2)
     assert y.shape == x1.shape
     assert float((y - (2 * f(x1) - 3 * f(x2))).abs().max()) <= 1e-9 * float(y.abs().max())
+
+
+# ---------------------------------------------------------------------------------------------
+# augmentation row: numpy restatement vs the reference's own outputs
+# ---------------------------------------------------------------------------------------------
+def _aug_golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "augment_golden.npz"))
+
+
+def test_augment_oracle_matches_reference_golden():
+    """oracle/augment.py against tests/golden/augment_golden.npz (made by the reference's elastic / crop with seeded
+    np.random, tests/golden/make_augment_golden.py): bit-exact, the restatement consumes the random stream identically"""
+    from oracle import augment
+    g = _aug_golden()
+    x = g["elastic_x"]
+    for i in range(2):
+        gran, mag, seed = g["elastic_arg%d" % i]
+        np.random.seed(int(seed))
+        out = augment.elastic_ref(x, int(gran), float(mag))
+        assert out.dtype == np.float64 and np.array_equal(out, g["elastic_out%d" % i])
+    xyz = g["crop_xyz"]
+    for i in range(3):
+        f0, f1, pr, mx, seed = g["crop_arg%d" % i]
+        np.random.seed(int(seed))
+        xo, valid = augment.crop_ref(xyz, [int(f0), int(f1)], float(pr), int(mx))
+        assert np.array_equal(valid, g["crop_valid%d" % i]) and np.array_equal(xo, g["crop_off%d" % i])
+        assert valid.sum() <= mx
+
+
+def test_augment_oracle_matches_staged_reference():
+    """the same on fresh inputs against the staged, unmodified augmentor_utils.py when it is present"""
+    import warnings
+    from oracle import augment, stage_ref
+    au = stage_ref.load_augmentor_utils()
+    if au is None:
+        pytest.skip("reference not staged")
+    warnings.simplefilter("ignore")
+    rng = np.random.RandomState(4)
+    x = (rng.rand(4000, 3) * np.array([300, 500, 120]) - np.array([150, 250, 0])).astype(np.float32)
+    for gran, mag in ((6, 40), (20, 160)):
+        np.random.seed(9); ref = au.elastic(x, gran, mag)
+        np.random.seed(9); mine = augment.elastic_ref(x, gran, mag)
+        assert np.array_equal(ref, mine)
+    xyz = (rng.rand(50000, 3) * np.array([900, 700, 150])).astype(np.float64)
+    for fs, pr, mx in (([128, 512], 2e9, 20000), ([128, 512], 2e7, 40000)):
+        np.random.seed(5); r0, r1 = au.crop(xyz, fs, pr, mx)
+        np.random.seed(5); m0, m1 = augment.crop_ref(xyz, fs, pr, mx)
+        assert np.array_equal(r1, m1) and np.array_equal(r0, m0)

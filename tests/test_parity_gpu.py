@@ -347,7 +347,10 @@ def test_conv1x1_fwd_bwd(cuda_dev):
 
 
 @pytest.mark.parametrize("M,C", [(5000, 16), (777, 48), (20000, 32), (64, 112), (3, 224), (1000, 10),
-                                 (3000, 320), (900, 384), (500, 1024)])  # 320 / 384: the concat BN of the m=32 net
+                                 (3000, 320), (900, 384), (500, 1024),  # 320 / 384: the concat BN of the m=32 net
+                                 # the deep U-Net levels: one-launch cluster form up to 16 x 64 KB (3000 x 64 forward
+                                 # fits, its backward with x and dy does not: a mixed pair of forms)
+                                 (6149, 64), (3000, 64), (1381, 80), (1381, 160), (223, 96), (45, 112), (5, 16)])
 @pytest.mark.parametrize("relu", [True, False])
 def test_bn_relu_fwd_bwd(cuda_dev, M, C, relu):
     from doda_b200 import ops
