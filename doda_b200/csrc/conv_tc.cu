@@ -23,6 +23,8 @@
 // strided dgrad use the pair-grouped mode (one offset per CTA, rows scattered through the pair list).
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <map>
+#include <mutex>
 #include <cuda.h>  // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <algorithm>
 #include <vector>
@@ -146,23 +148,23 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const TCParams p, con
 
     const int ntiles = p.total_tiles > (int)blockIdx.x ? (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
-    if (tid == 0) {
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&full[s], TC_XFORM_THREADS / 32);
-            mbar_init(&empty[s], 1);
-            mbar_init(&raw[s], p.use_tma ? 1 : TC_LOADERS);
-        }
-        for (int s = 0; s < SB; ++s) {
-            mbar_init(&fullb[s], 1);
-            mbar_init(&emptyb[s], 1);
-        }
-        for (int b = 0; b < TC_NBUF; ++b) {
-            mbar_init(&tready[b], 1);
-            mbar_init(&tfree[b], (p.use_tma ? 1 : TC_LOADERS) + 4 /*xform warps*/ + 4 /*epilogue warps*/ + ni + 1 /*weights*/);
-            mbar_init(&accf[b], ni);
-            mbar_init(&acce[b], 4);
-            mbar_init(&tload[b], 1);
-        }
+    // barrier init spread over threads of three different warps (one thread doing all ~40 inits was ~1 us of every launch)
+    if (tid < S) {
+        mbar_init(&full[tid], TC_XFORM_THREADS / 32);
+        mbar_init(&empty[tid], 1);
+        mbar_init(&raw[tid], p.use_tma ? 1 : TC_LOADERS);
+        mbar_fence_init();
+    } else if (tid >= 32 && tid < 32 + SB) {
+        mbar_init(&fullb[tid - 32], 1);
+        mbar_init(&emptyb[tid - 32], 1);
+        mbar_fence_init();
+    } else if (tid >= 64 && tid < 64 + TC_NBUF) {
+        const int b = tid - 64;
+        mbar_init(&tready[b], 1);
+        mbar_init(&tfree[b], (p.use_tma ? 1 : TC_LOADERS) + 4 /*xform warps*/ + 4 /*epilogue warps*/ + ni + 1 /*weights*/);
+        mbar_init(&accf[b], ni);
+        mbar_init(&acce[b], 4);
+        mbar_init(&tload[b], 1);
         mbar_fence_init();
     }
     if (warp == TC_W_MMA) tmem_alloc(s_tmem, p.tmem_cols);
@@ -213,6 +215,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const TCParams p, con
                 const int64_t row0 = (int64_t)rt * TC_BM;
                 const int rows = (int)min((int64_t)TC_BM, p.n_rows - row0);
                 unsigned mask = 0, mrow = 0;
+                // the table rows first (one bulk copy in flight), the tile's output rows / row masks behind it: a CTA with
+                // a single tile pays these global round trips back to back before its first gather can start
+                const int* t = p.tab ? p.tab + row0 * K : nullptr;
+                const int tot = rows * K;
+                const uint32_t bytes = (uint32_t)tot * 4u;
+                const bool bulk = p.tab && !(p.dbg & 16) && rows == TC_BM && (bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(t) & 15) == 0);
+                if (bulk && lane == 0) {
+                    mbar_arrive_expect_tx(&tload[b], bytes);
+                    bulk_g2s(idx, t, bytes, &tload[b]);
+                }
                 {
                     int ov[TC_BM / 32];
 #pragma unroll
@@ -225,18 +237,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const TCParams p, con
                     for (int q = 0; q < TC_BM / 32; ++q) orow[lane + 32 * q] = ov[q];
                 }
                 if (p.tab) {
-                    const int* t = p.tab + row0 * K;
-                    const int tot = rows * K;
-                    const uint32_t bytes = (uint32_t)tot * 4u;
                     if (p.dbg & 16) {
                         if (lane == 0) mbar_arrive(&tload[b]);
                         __syncwarp();
-                    } else if (rows == TC_BM && (bytes & 15u) == 0 && ((reinterpret_cast<uintptr_t>(t) & 15) == 0)) {
-                        // full tile: one bulk copy of the 128 x K table rows, then the offset mask from shared memory
-                        if (lane == 0) {
-                            mbar_arrive_expect_tx(&tload[b], bytes);
-                            bulk_g2s(idx, t, bytes, &tload[b]);
-                        }
+                    } else if (bulk) {
                         mbar_wait(&tload[b], ph);
                     } else {
                         for (int e = lane; e < TC_BM * K; e += 32) idx[e] = e < tot ? __ldg(t + e) : -1;
@@ -615,16 +619,24 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const TCParams p, con
             for (int e = split * per + et; e < e_end; e += 128) {
                 const int row = e / cp4, c4 = e - row * cp4;
                 const uint32_t laddr = base + (uint32_t)(row * pstr4 + c4) * 16u;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                for (int sp = 0; sp < nact; ++sp) {
-                    uint32_t raddr;
-                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(laddr), "r"(sp));
-                    float4 t;
-                    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];\n"
-                                 : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
-                                 : "r"(raddr)
-                                 : "memory");
-                    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+                // all peer loads in flight first (distributed shared memory is a ~200-cycle round trip), then the adds in
+                // split order
+                float4 tp[8];
+#pragma unroll
+                for (int sp = 0; sp < 8; ++sp) {
+                    tp[sp] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (sp < nact) {
+                        uint32_t raddr;
+                        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(raddr) : "r"(laddr), "r"(sp));
+                        asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];\n"
+                                     : "=f"(tp[sp].x), "=f"(tp[sp].y), "=f"(tp[sp].z), "=f"(tp[sp].w)
+                                     : "r"(raddr));
+                    }
+                }
+                float4 acc = tp[0];
+#pragma unroll
+                for (int sp = 1; sp < 8; ++sp) {
+                    if (sp < nact) { acc.x += tp[sp].x; acc.y += tp[sp].y; acc.z += tp[sp].z; acc.w += tp[sp].w; }
                 }
                 if (c4 * 4 >= Cout) continue;
                 const int orw = orow_s[row];
@@ -875,6 +887,43 @@ static int launch_tc(const TCParams& p0, int KT, int64_t n_in, cudaStream_t st) 
         // split mode: p.nsplit is the WISH.  One tile per CTA, the nsplit CTAs of a row tile are one cluster (co-scheduled
         // by the hardware, so they may wait for each other); their partial tiles must fit into the idle stage rings
         p.nsplit = std::min(std::min(p.nsplit, 8), num_sms() * occ / p.row_tiles);
+        // ... and ALL clusters must be resident at once: a cluster lives inside one GPC, so e.g. 49 clusters of 3 CTAs do
+        // not fit a machine whose GPCs hold 6 such clusters each (2 SMs per GPC stay empty) and the stragglers run as a
+        // second wave (measured 6 148 rows x 64 ch: 3-way 39.1 us, 2-way 31.6 us).  Ask the driver, per (smem, n), once.
+        {
+            static std::map<uint64_t, int> s_fit;
+            static std::mutex s_fit_mu;
+            std::lock_guard<std::mutex> lk(s_fit_mu);
+            B200SP_ENV_INT(env_fit, "B200SP_TC_FITCHECK", 1);  // dev knob: 0 = the pre-check behaviour
+            while (env_fit && p.nsplit > 1) {
+                const uint64_t key = ((uint64_t)smem << 8) | (uint64_t)p.nsplit;
+                auto it = s_fit.find(key);
+                int fit = 0;
+                if (it == s_fit.end()) {
+                    cudaLaunchConfig_t q{};
+                    q.gridDim = dim3((unsigned)(p.nsplit * 64));
+                    q.blockDim = dim3(TC_THREADS);
+                    q.dynamicSmemBytes = smem;
+                    cudaLaunchAttribute qa[1];
+                    qa[0].id = cudaLaunchAttributeClusterDimension;
+                    qa[0].val.clusterDim.x = (unsigned)p.nsplit;
+                    qa[0].val.clusterDim.y = 1;
+                    qa[0].val.clusterDim.z = 1;
+                    q.attrs = qa;
+                    q.numAttrs = 1;
+                    if (cudaOccupancyMaxActiveClusters(&fit, k_conv_tc<KC>, &q) != cudaSuccess) {
+                        (void)cudaGetLastError();
+                        fit = num_sms() * occ / p.nsplit;
+                    }
+                    if (occ == 1) fit = std::min(fit, num_sms() / p.nsplit);  // TMEM (unknown to the driver) allows one CTA per SM
+                    s_fit[key] = fit;
+                } else {
+                    fit = it->second;
+                }
+                if (fit >= p.row_tiles) break;
+                --p.nsplit;
+            }
+        }
         const uint32_t part_bytes = (uint32_t)TC_BM * (uint32_t)(p.Cout_pad + 4) * 4u;
         if (part_bytes > L::offMeta(p.nslots, p.nslots_b, p.stageB_bytes)) p.nsplit = 1;
         if (p.nsplit < 2) p.nsplit = 1;
