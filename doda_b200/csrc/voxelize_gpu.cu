@@ -5,7 +5,10 @@
 //   * input_map[p] = voxel of point p;  out_coords[v] = coordinates of the voxel (of its first point);
 //   * output_map[v] = [count, points of v in ascending order ..., -1 padding] for modes 3/4 (maxActive = largest count),
 //     [1, first point] for modes 0/1, [1, last point] for mode 2.
-// How: hash the packed coordinate (batch 4 bits, < 15 | 3 x 20 bits) with atomicMin of the point index -> every voxel knows
+// How: hash the packed coordinate with atomicMin of the point index -> every voxel knows
+// [packing: a range pass finds the largest coordinate; x, y, z take cb = bits(max) each (<= 20) and the batch index the
+//  remaining 64 - 3 cb bits, so a 1024^3 grid leaves 34 bits for the batch index and only a 2^20-wide grid is held to
+//  batch < 15; the all-ones key is the table's empty marker and stays unreachable]
 // its first point; an exclusive scan over the "I am a first point" flags numbers the voxels in first-touch order; a
 // stable radix sort of (voxel id, point) groups each voxel's points in ascending order.  Two calls (the host has to
 // size out_coords / output_map from M and maxActive): _begin ... sync ... _finish, like the strided rulebook.
@@ -81,20 +84,52 @@ int carve(VoxWs& w, int64_t N, void* ws, int64_t ws_bytes) {
     return B200SP_OK;
 }
 
-__device__ __forceinline__ bool pack_key(const long long* c, int ncol, unsigned long long& key) {
+// info[4] = largest coordinate, info[5] = largest batch index (k_vox_range); -> bits per coordinate, or -1 when the
+// batch does not fit into what the coordinates leave of the 64-bit key
+__device__ __forceinline__ int key_layout(const int* info) {
+    const int cmax = info[4], bmax = info[5];
+    const int cb = 32 - __clz(cmax);  // 0 for an all-zero grid
+    if (cb > 20) return -1;
+    const int bb = 64 - 3 * cb;
+    if (bb < 32 && (long long)bmax >= (1ll << bb) - 1) return -1;
+    return cb;
+}
+
+__device__ __forceinline__ bool pack_key(const long long* c, int ncol, int cb, unsigned long long& key) {
     const long long b = ncol == 4 ? c[0] : 0;
     const long long x = c[ncol - 3], y = c[ncol - 2], z = c[ncol - 1];
-    const long long lim = 1ll << 20;
-    if (b < 0 || b >= 15 || x < 0 || x >= lim || y < 0 || y >= lim || z < 0 || z >= lim) return false;
-    key = ((unsigned long long)b << 60) | ((unsigned long long)x << 40) | ((unsigned long long)y << 20) | (unsigned long long)z;
+    if (cb < 0 || b < 0 || x < 0 || y < 0 || z < 0) return false;
+    key = ((unsigned long long)b << (3 * cb)) | ((unsigned long long)x << (2 * cb)) | ((unsigned long long)y << cb) | (unsigned long long)z;
     return true;
+}
+
+// largest coordinate / batch index of the call; negative or >= 2^31 values raise the bad-coordinate flag
+__global__ void k_vox_range(const long long* __restrict__ coords, long long N, int ncol, int* info) {
+    const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int cm = 0, bm = 0, bad = 0;
+    if (p < N) {
+        const long long* c = coords + p * ncol;
+        const long long b = ncol == 4 ? c[0] : 0;
+        const long long x = c[ncol - 3], y = c[ncol - 2], z = c[ncol - 1];
+        const long long hi = max(x, max(y, z)), lo = min(min(x, y), min(z, b));
+        if (lo < 0 || hi >= (1ll << 31) || b >= (1ll << 31)) bad = 1;
+        else { cm = (int)hi; bm = (int)b; }
+    }
+    cm = __reduce_max_sync(0xffffffffu, cm);
+    bm = __reduce_max_sync(0xffffffffu, bm);
+    bad = __reduce_max_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (cm > info[4]) atomicMax(&info[4], cm);
+        if (bm > info[5]) atomicMax(&info[5], bm);
+        if (bad) info[2] = 1;
+    }
 }
 
 __global__ void k_vox_insert(const long long* __restrict__ coords, long long N, int ncol, HashTab t, int* info) {
     const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p >= N) return;
     unsigned long long key;
-    if (!pack_key(coords + p * ncol, ncol, key)) {
+    if (!pack_key(coords + p * ncol, ncol, key_layout(info), key)) {
         info[2] = 1;
         return;
     }
@@ -102,12 +137,12 @@ __global__ void k_vox_insert(const long long* __restrict__ coords, long long N, 
 }
 
 __global__ void k_vox_first(const long long* __restrict__ coords, long long N, int ncol, HashTab t, int* __restrict__ first,
-                            int* __restrict__ flag, int* __restrict__ iota) {
+                            int* __restrict__ flag, int* __restrict__ iota, const int* __restrict__ info) {
     const long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (p >= N) return;
     unsigned long long key;
     int f = (int)p;
-    if (pack_key(coords + p * ncol, ncol, key)) {
+    if (pack_key(coords + p * ncol, ncol, key_layout(info), key)) {
         const int v = hash_lookup(t, key);
         if (v >= 0) f = v;
     }
@@ -181,15 +216,16 @@ extern "C" int b200sp_voxelize_idx_gpu_begin(const int64_t* coords, int64_t N, i
     B200SP_CUDA(cudaMemsetAsync(w.t.keys, 0xFF, cap * 8, st));
     B200SP_CUDA(cudaMemsetAsync(w.t.vals, 0x7F, cap * 4, st));
     B200SP_CUDA(cudaMemsetAsync(w.cnt, 0, N * 4, st));
-    B200SP_CUDA(cudaMemsetAsync(w.info, 0, 16, st));
+    B200SP_CUDA(cudaMemsetAsync(w.info, 0, 32, st));
     const unsigned grid = (unsigned)cdiv(N, 256);
+    k_vox_range<<<grid, 256, 0, st>>>((const long long*)coords, N, ncol, w.info);
     k_vox_insert<<<grid, 256, 0, st>>>((const long long*)coords, N, ncol, w.t, w.info);
-    k_vox_first<<<grid, 256, 0, st>>>((const long long*)coords, N, ncol, w.t, w.first, w.flag, w.iota);
+    k_vox_first<<<grid, 256, 0, st>>>((const long long*)coords, N, ncol, w.t, w.first, w.flag, w.iota, w.info);
     B200SP_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_ws, w.cub_bytes, w.flag, w.scan, (int)N, st));
     k_vox_ids<<<grid, 256, 0, st>>>(N, w.first, w.flag, w.scan, w.vid, w.cnt, w.info);
     // maxActive = max count (modes 3/4 only; 1 otherwise, as the reference sizes output_map)
     B200SP_CUDA(cub::DeviceReduce::Max(w.cub_ws, w.cub_bytes, w.cnt, w.info + 1, (int)N, st));
-    B200SP_LAUNCH_CHECK_N(3 + 2);
+    B200SP_LAUNCH_CHECK_N(4 + 2);
     B200SP_CUDA(cudaMemcpyAsync(input_map, w.vid, N * 4, cudaMemcpyDeviceToDevice, st));
     B200SP_CUDA(cudaMemcpyAsync(info_host, w.info, 16, cudaMemcpyDeviceToHost, st));
     return B200SP_OK;

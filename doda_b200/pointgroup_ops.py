@@ -50,7 +50,8 @@ def voxelization_idx_gpu(coords, batchsize, mode=4):
     torch.cuda.current_stream(dev).synchronize()
     M, A, bad, dup = [int(v) for v in info.tolist()]
     if bad:
-        raise RuntimeError("voxelization_idx_gpu: coordinates must satisfy 0 <= batch < 15 and 0 <= x, y, z < 2^20")
+        raise RuntimeError("voxelization_idx_gpu: coordinates must be non-negative, x, y, z < 2^20, and the batch index must fit "
+                           "into the 64 - 3 * bits(max coordinate) key bits the grid leaves (any batch for grids up to 2^17 wide)")
     if int(mode) == 0 and dup:
         raise RuntimeError("libb200sparse voxelize_idx failed: mode 0 requires unique coordinates")
     A = A if int(mode) in (3, 4) else 1

@@ -270,8 +270,9 @@ int b200sp_voxelize_idx_cpu_fill(const int64_t* coords_host, int64_t N, int ncol
                                  const int32_t* input_map_host /*[N], from the first call*/, int64_t M,
                                  int32_t max_active, int64_t* out_coords_host, int32_t* output_map_host);
 /* The same on the device (batch assembly without the serial CPU hash map), bit-identical results
- * (first-touch voxel order, ascending points per voxel).  coords: int64 [N, ncol] on the device, 0 <= batch < 15,
- * 0 <= x, y, z < 2^20.  Two calls: _begin writes input_map [N] and starts an async copy of
+ * (first-touch voxel order, ascending points per voxel).  coords: int64 [N, ncol] on the device, non-negative,
+ * x, y, z < 2^20, batch index < 2^(64 - 3 * bits(largest coordinate)) - 1 (any batch up to a 2^17-wide grid; a
+ * 2^20-wide grid leaves 4 bits).  Two calls: _begin writes input_map [N] and starts an async copy of
  * info[4] = {M, maxActive (modes 3/4), bad-coordinate flag, duplicate flag} to pinned host memory; after a stream
  * sync the caller sizes out_coords [M, ncol] / output_map [M, 1 + maxActive] (maxActive = 1 for modes 0-2) and calls
  * _finish with the SAME workspace (b200sp_voxelize_idx_gpu_ws_bytes(N) bytes). */

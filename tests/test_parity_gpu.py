@@ -584,6 +584,20 @@ def test_voxelize_idx_gpu_full_size_and_errors(cuda_dev):
     assert e[0].shape == (0, 4) and e[1].numel() == 0 and e[2].shape[0] == 0
     with pytest.raises(RuntimeError):
         pointgroup_ops.voxelization_idx_gpu(torch.tensor([[0, -1, 0, 0]], device=cuda_dev), 1, 4)
+    # batch indices past 15 (round-1 limit): the key gives the batch whatever bits the grid leaves -- 64 scenes on a
+    # 1024-wide grid, and batch 40000 on a small one; only a 2^20-wide grid still holds the batch below 15
+    rng = np.random.RandomState(3)
+    for nb, side in ((64, 1024), (40000, 30), (14, (1 << 20) - 1)):
+        c = np.concatenate([np.sort(rng.randint(0, nb, size=(6000, 1)), 0), rng.randint(0, 8, size=(6000, 3)) * (side // 8)], 1)
+        c[0, 0], c[-1, 0], c[5, 1:] = 0, nb - 1, side - 1 if side < (1 << 20) - 1 else side
+        c = torch.from_numpy(np.ascontiguousarray(c.astype(np.int64)))
+        oc, im, om = pointgroup_ops.voxelization_idx(c, nb, 4)
+        goc, gim, gom = pointgroup_ops.voxelization_idx_gpu(c.to(cuda_dev), nb, 4)
+        assert torch.equal(goc.cpu(), oc) and torch.equal(gim.cpu(), im) and torch.equal(gom.cpu(), om), (nb, side)
+    with pytest.raises(RuntimeError):
+        pointgroup_ops.voxelization_idx_gpu(torch.tensor([[15, (1 << 20) - 1, 0, 0]], device=cuda_dev), 16, 4)
+    with pytest.raises(RuntimeError):
+        pointgroup_ops.voxelization_idx_gpu(torch.tensor([[0, 1 << 20, 0, 0]], device=cuda_dev), 1, 4)
     with pytest.raises(RuntimeError):
         pointgroup_ops.voxelization_idx_gpu(torch.tensor([[0, 1, 1, 1], [0, 1, 1, 1]], device=cuda_dev), 1, 0)
 
