@@ -237,17 +237,21 @@ def measure(state_dict, batch, device, steps=5, warmup=2, graph=True):
            "loss": float(loss.detach()), "scores": scores.detach()}
     if graph:
         try:
+            # fresh leaves whose first use (and so their AccumulateGrad nodes) is on the capture stream itself, warm-up and
+            # capture on that one stream: a gradient accumulation that has to hop to another stream breaks the capture
             g = torch.cuda.CUDAGraph()
+            net_g = NativeUNet(state_dict, device)
+            net_g.rb = net.rb
             side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                net.step(vf, p2v, labels)
-            torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            for p in net.params():
+            with torch.cuda.stream(side):
+                net_g.step(vf, p2v, labels)
+            torch.cuda.synchronize()
+            for p in net_g.params():
                 p.grad = None
-            with torch.cuda.graph(g):
-                l2, _ = net.forward(vf, p2v, labels)
+            # relaxed: other threads of the process (clock sampler, copy stream) may call the CUDA API during the capture
+            with torch.cuda.graph(g, stream=side, capture_error_mode="relaxed"):
+                l2, _ = net_g.forward(vf, p2v, labels)
                 l2.backward()
             for _ in range(max(1, warmup)):
                 g.replay()

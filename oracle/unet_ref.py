@@ -122,17 +122,27 @@ def model_step_ref(sd, batch, training=True, relu_masks=None):
     return loss, scores
 
 
-def encoder_decoder_ref(weights_down, weights_up, bn_down, bn_up, x, coords, spatial_shape, batch_size, training=True):
+def encoder_decoder_ref(weights_down, weights_up, bn_down, bn_up, x, coords, spatial_shape, batch_size, training=True,
+                        relu_masks=None):
     """BASELINE configs[3]: the stride-2 SparseConv3d / SparseInverseConv3d encoder-decoder of UBlock
     (model/unet_block.py:67-79) without the SubM blocks.  weights_down[l] / weights_up[l]: [2,2,2,Cin,Cout] filters of
     level l's down conv / inverse conv; bn_down[l] / bn_up[l]: (weight, bias) of the BatchNorm in front of each (None =
-    no BN/ReLU).  -> features on the input's own active set [M, C0]."""
+    no BN/ReLU).  -> features on the input's own active set [M, C0].
+    relu_masks: optional list of 0/1 masks, one per BN+ReLU in execution order, that replace the ReLU gates (the
+    pinned-gate comparison of oracle/gates.py)."""
+    masks = list(relu_masks) if relu_masks is not None else None
+
+    def act(y):
+        if masks is None:
+            return F.relu(y)
+        return y * masks.pop(0).to(y.dtype)
+
     idx = np.asarray(coords, dtype=np.int64)
     shape = [int(s) for s in spatial_shape]
     stack, f = [], x
     for l, W in enumerate(weights_down):
         if bn_down is not None:
-            f = F.relu(F.batch_norm(f, None, None, bn_down[l][0], bn_down[l][1], True, 0.1, 1e-4))
+            f = act(F.batch_norm(f, None, None, bn_down[l][0], bn_down[l][1], True, 0.1, 1e-4))
         outids, pairs, pairnum, oshape = get_indice_pairs_ref(idx, batch_size, shape, 2, 2, 0, 1, subm=False)
         stack.append((pairs, pairnum, f.shape[0]))
         f = indice_conv_ref(f, W, pairs, pairnum, outids.shape[0])
@@ -140,6 +150,6 @@ def encoder_decoder_ref(weights_down, weights_up, bn_down, bn_up, x, coords, spa
     for l in reversed(range(len(weights_up))):
         pairs, pairnum, n_fine = stack[l]
         if bn_up is not None:
-            f = F.relu(F.batch_norm(f, None, None, bn_up[l][0], bn_up[l][1], True, 0.1, 1e-4))
+            f = act(F.batch_norm(f, None, None, bn_up[l][0], bn_up[l][1], True, 0.1, 1e-4))
         f = indice_conv_ref(f, weights_up[l], pairs, pairnum, n_fine, inverse=True)
     return f

@@ -33,32 +33,7 @@ def surface_coords(seed, target, batch):
     return c, shape
 
 
-def capture_relu_masks(model):
-    """Instrument a SparseConvNet (the mirror or the reference's own class) built on the engine's spconv surface so
-    that its next forward records, per BatchNorm key (state_dict prefix), which BN+ReLU outputs were > 0.
-    -> dict filled during the forward.  Test infrastructure: wraps the fused-triplet entry point per conv instance."""
-    from doda_b200 import spconv
-    from doda_b200.spconv.modules import is_sparse_conv, _is_bn_like
-    masks = {}
-    for name, seq in model.named_modules():
-        if not isinstance(seq, spconv.SparseSequential):
-            continue
-        mods = list(seq._modules.items())
-        for i, (k, m) in enumerate(mods):
-            if not _is_bn_like(m):
-                continue
-            key = "%s.%s" % (name, k)
-            if i + 2 < len(mods) and is_sparse_conv(mods[i + 2][1]):
-                conv = mods[i + 2][1]
-
-                def wrapped(input, bn, stats_args, _orig=conv.forward_after_bn_relu, _key=key):
-                    out = _orig(input, bn, stats_args)
-                    masks[_key] = (input.features.detach() > 0).cpu()
-                    return out
-                conv.forward_after_bn_relu = wrapped
-            else:  # BN + ReLU at the end of a sequential (output_layer): the sequential's output holds the activation
-                seq.register_forward_hook(lambda mod, inp, out, _key=key: masks.__setitem__(_key, (out.features.detach() > 0).cpu()))
-    return masks
+from oracle.gates import capture_relu_masks  # noqa: E402,F401  (kept importable from helpers)
 
 
 def oracle_step(sd_f32, batch, dtype, relu_masks=None):
@@ -90,9 +65,7 @@ def grad_report(named_grads, sd64, sd32):
             "f32_max": float(np.max(e_f32)), "f32_l2": float((num32 / den) ** 0.5)}
 
 
-GRAD_FACTOR = 40.0  # UNPINNED gates: engine-vs-fp64 gradient error as a multiple of the fp32 oracle's own (measured 3-22;
-                    # a sanity bound only -- the fixed bars are the PINNED ones below)
-GRAD_CAP = 5e-2     # and never more than this, whatever the fp32 oracle does
+GRAD_CAP = 5e-2     # UNPINNED gates: absolute cap only (see assert_grad_parity); the fixed bars are the PINNED ones below
 
 
 def pinned_grad_report(named_grads, sd64p):
@@ -119,15 +92,15 @@ def assert_pinned_grad_parity(rep, what=""):
 
 
 def assert_grad_parity(rep, what=""):
-    """Whole-net GRADIENTS of a 71-conv / 65-BN ReLU net cannot be held to a per-op bar: two fp32 evaluations whose
-    forward activations agree to ~1e-6 disagree on the sign of a ~1e-6 fraction of the ReLU pre-activations, and every
-    flipped gate changes its gradient contribution by 100 % -- an L2 gradient difference of ~sqrt(1e-6) = 1e-3 per layer,
-    ~1e-2 over the net.  The fp32 CPU oracle (the reference algorithm in plain torch fp32) shows exactly that against
-    its own fp64 evaluation: L2 5.7e-3 at 2 x 150 k voxels, 1.4e-3 at 2 x 8 k.  The engine is
-    therefore held (a) to FIXED tight bars against the fp64 oracle evaluated with the gates pinned to the engine's own
-    (assert_pinned_grad_parity: the smooth part of the computation), and (b) with free gates only to a multiple of the
-    fp32 reference's own distance from fp64 (the engine's 3xTF32 products round at 2^-21 instead of 2^-24, so it flips
-    several times more gates than plain fp32), with an absolute cap."""
+    """Whole-net GRADIENTS of a 71-conv / 65-BN ReLU net cannot be held to a per-op bar with FREE gates: two fp32
+    evaluations whose forward activations agree to ~1e-6 disagree on the sign of a ~1e-6 fraction of the ReLU
+    pre-activations, and every flipped gate changes its gradient contribution by 100 % -- an L2 gradient difference
+    of ~1e-3 per flip-carrying layer, up to ~1e-2 over the net.  Whether a given evaluation flips a gate is chance:
+    the fp32 CPU oracle sits 5.7e-3 from its own fp64 evaluation at 2 x 150 k voxels and 1.4e-3 at 2 x 8 k, but
+    7e-6 on a run where none of its gates happened to flip -- so a bound expressed as a multiple
+    of the fp32 oracle's distance is a coin toss and is not used.  The engine is held (a) to FIXED tight bars against
+    the fp64 oracle evaluated with the gates pinned to the engine's own (assert_pinned_grad_parity: the smooth part
+    of the computation, i.e. the arithmetic), and (b) with free gates to an absolute cap that only a wrong kernel
+    exceeds; the fp32 oracle's own numbers are printed next to the engine's for the record."""
     for k in ("median", "p90", "l2"):
-        g, f = rep["gpu_" + k], rep["f32_" + k]
-        assert g <= max(GRAD_FACTOR * f, 1e-4) and g <= GRAD_CAP, (what, k, rep)
+        assert rep["gpu_" + k] <= GRAD_CAP, (what, k, rep)

@@ -81,6 +81,8 @@ def test_cfg4_encoder_decoder_matches_oracle_400k(cuda_dev):
                                 x32, coords, shape, 1)
     ref32.backward(g)
     net = net.to(cuda_dev).train()
+    from helpers import capture_relu_masks
+    gates = capture_relu_masks(net)
     xd = x.to(cuda_dev).requires_grad_(True)
     y = net(spconv.SparseConvTensor(xd, torch.from_numpy(coords).to(cuda_dev), shape, 1))
     y.features.backward(g.to(cuda_dev))
@@ -90,13 +92,28 @@ def test_cfg4_encoder_decoder_matches_oracle_400k(cuda_dev):
     print("cfg4 400k encoder-decoder: out rel err %.3e (fp32 oracle %.3e), dx rel err %.3e (fp32 oracle %.3e)"
           % (e, rel_err(ref32, ref), ex, ex32))
     assert e <= 1e-4, e
-    assert ex <= max(4.0 * ex32, 1e-4) and ex <= 5e-2, (ex, ex32)  # ReLU gate flips: see helpers.assert_grad_parity
     ew = [rel_err(c.weight.grad, w.grad) for c, w in zip(convs[:L], wd)] + \
          [rel_err(c.weight.grad, w.grad) for c, w in zip(convs[L:], wu_rev)]
     ew32 = [rel_err(a.grad, b.grad) for a, b in zip(wd32, wd)] + \
            [rel_err(a.grad, b.grad) for a, b in zip(list(reversed(wu32)), wu_rev)]
-    print("cfg4 dW rel errs:", ["%.1e" % v for v in ew], "fp32 oracle:", ["%.1e" % v for v in ew32])
-    assert float(np.median(ew)) <= max(4.0 * float(np.median(ew32)), 1e-4) and max(ew) <= 5e-2, (ew, ew32)
+    print("cfg4 dW rel errs, free gates:", ["%.1e" % v for v in ew], "fp32 oracle:", ["%.1e" % v for v in ew32])
+    # free gates: an absolute cap only (whether an fp32 evaluation flips a ReLU gate is chance, helpers.assert_grad_parity)
+    assert ex <= 5e-2 and max(ew) <= 5e-2, (ex, ew)
+    # the fixed bar: the fp64 oracle with the ReLU gates pinned to the engine's own, in execution order
+    assert len(gates) == 2 * L
+    order = [gates[k] for k in sorted(gates, key=lambda s: int(s.split(".")[-1]))]
+    wdp = [w.detach().clone().requires_grad_(True) for w in wd]
+    wup = [w.detach().clone().requires_grad_(True) for w in wu]
+    x64p = x.double().requires_grad_(True)
+    refp = encoder_decoder_ref(wdp, wup, bd, bu, x64p, coords, shape, 1, relu_masks=order)
+    refp.backward(g.double())
+    wup_rev = list(reversed(wup))
+    ep = rel_err(y.features, refp)
+    exp_ = rel_err(xd.grad, x64p.grad)
+    ewp = [rel_err(c.weight.grad, w.grad) for c, w in zip(convs[:L], wdp)] + \
+          [rel_err(c.weight.grad, w.grad) for c, w in zip(convs[L:], wup_rev)]
+    print("cfg4 pinned gates: out %.3e dx %.3e dW" % (ep, exp_), ["%.1e" % v for v in ewp])
+    assert ep <= 1e-4 and exp_ <= 1e-4 and max(ewp) <= 2e-4, (ep, exp_, ewp)
 
 
 def test_step_is_bit_reproducible_where_claimed(cuda_dev):
