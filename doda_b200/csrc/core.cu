@@ -29,10 +29,11 @@ long long get_launches() { return g_launches.load(std::memory_order_relaxed); }
 bool pdl_enabled() {
     static int on = -1;
     if (on < 0) {
-        // opt-in: measured on the full step (bench.py, 2 x 150 k voxels) PDL = 1 gave 12.95-13.45 ms against 12.80 ms
-        // without -- the GPU is ~94 % busy inside kernels, the gaps PDL can close are not where the time is
+        // ON by default (B200SP_PDL=0 turns it off).  While the step was host-bound it measured as nothing or a loss
+        // (12.95-13.45 ms against 12.80 ms); with the taped U-Net (doda_b200/tape.py) the step is GPU-bound and the
+        // ~1.5 us between dependent kernels is worth 12.01 -> 11.76 ms per step over ~610 launches
         const char* e = getenv("B200SP_PDL");
-        on = (e && e[0] == '1') ? 1 : 0;
+        on = (e && e[0] == '0') ? 0 : 1;
     }
     return on != 0;
 }

@@ -931,7 +931,10 @@ def conv_forward_raw(kind, features, filters, rb, prep):
 # bound (deep levels: a few CTAs) -- the backward node forks a side stream for the wgrad kernel and joins it before it
 # returns, so everything autograd / DDP does with dW afterwards is ordered as before.
 async_wgrad = os.environ.get("B200SP_ASYNC_WGRAD", "1") != "0"
-async_wgrad_max_rows = 65536  # above this both kernels fill the machine and the fork/join only costs host time
+# rows above which the weight gradient stays on the compute stream.  Round 2 started with 65536 ("both kernels fill the
+# machine, the fork / join only costs host time") -- true while the step was host-bound; with the taped U-Net the step
+# is GPU-bound and the latency-bound level-1/2 kernels overlap well: 12.53 -> 12.10 ms per step with no limit
+async_wgrad_max_rows = int(os.environ.get("B200SP_ASYNC_WGRAD_MAX_ROWS", str(1 << 40)))
 _wg_side = {}        # device index -> (torch side stream, its raw handle, fork event, join event)
 _pending_join = None
 

@@ -13,6 +13,7 @@ from torch import nn
 from . import spconv
 from . import ops as _ops
 from . import pointgroup_ops
+from . import tape as _tape
 
 
 class ResidualBlock(spconv.SparseModule):
@@ -69,7 +70,13 @@ class UBlock(nn.Module):
             self.blocks_tail = spconv.SparseSequential(OrderedDict(
                 ("block%d" % i, block(c0 * (2 - i), c0, norm_fn, indice_key=sub_key)) for i in range(block_reps)))
 
+    tape = True  # run this sub-tree as ONE autograd node when it qualifies (doda_b200/tape.py); False: module by module
+
     def forward(self, x):
+        if self.tape and _tape.enabled and self.training:
+            p = _tape.cached_plan(self)
+            if _tape.usable(self, p, x):
+                return _tape.run(self, p, x)
         out = self.blocks(x)
         skip = spconv.SparseConvTensor(out.features, out.indices, out.spatial_shape, out.batch_size)
         if len(self.nPlanes) > 1:

@@ -14,6 +14,9 @@ def capture_relu_masks(model):
     from doda_b200 import spconv
     from doda_b200.spconv.modules import is_sparse_conv, _is_bn_like
     masks = {}
+    # a U-Net sub-tree that runs as one taped autograd node (doda_b200/tape.py) records its gates itself
+    from doda_b200 import tape as _tape
+    _tape.capture = (masks, {id(m): name for name, m in model.named_modules() if _is_bn_like(m)})
     for name, seq in model.named_modules():
         if not isinstance(seq, spconv.SparseSequential):
             continue

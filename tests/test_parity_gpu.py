@@ -799,3 +799,64 @@ def test_spconv_surface_sequential_semantics(cuda_dev):
     assert z.features.shape == (500, 4)
     d = z.dense()
     assert d.shape == (1, 4, 16, 16, 16)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("residual", [True, False])
+def test_taped_ublock_matches_module_path(cuda_dev, residual):
+    """doda_b200/tape.py runs the U-Net sub-tree as ONE autograd node (host cost); it must be the same computation as
+    the module-by-module path: identical loss, scores, BatchNorm running statistics and BatchNorm / activation
+    gradients bit for bit; conv weight gradients (float atomics in both paths) to 1e-5"""
+    from doda_b200 import scenes, tape
+    from doda_b200.unet import SparseConvNet, model_step
+    torch.manual_seed(0)
+    batch = scenes.collate([scenes.scene_with_voxels(0, 6000), scenes.scene_with_voxels(1, 5000)], dup_max=2)
+    model = SparseConvNet(mid_channel=16, block_residual=residual).to(cuda_dev).train()
+    sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    res = {}
+    try:
+        for on in (False, True):
+            tape.enabled = on
+            model.load_state_dict(sd0)
+            for p in model.parameters():
+                p.grad = None
+            runs0 = tape.runs
+            loss, scores = model_step(model, batch, device=cuda_dev)
+            loss.backward()
+            assert (tape.runs - runs0 == 1) == on
+            res[on] = (loss.detach().clone(), scores.detach().clone(),
+                       {n: p.grad.detach().clone() for n, p in model.named_parameters()},
+                       {n: b.detach().clone() for n, b in model.named_buffers()})
+    finally:
+        tape.enabled = True
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
+    for n, b in res[False][3].items():
+        assert torch.equal(b, res[True][3][n]), n
+    for n, g in res[False][2].items():
+        if g.dim() >= 3:  # conv filters
+            assert rel_err(res[True][2][n], g) <= 1e-5, n
+        else:
+            assert torch.equal(res[True][2][n], g), n
+
+
+@pytest.mark.gpu
+def test_taped_ublock_falls_back_and_frees(cuda_dev):
+    """eval mode / no_grad / a second backward: module path or a clear error, never a wrong result"""
+    from doda_b200 import scenes, tape
+    from doda_b200.unet import SparseConvNet, model_step
+    torch.manual_seed(1)
+    batch = scenes.collate([scenes.scene_with_voxels(0, 3000)], dup_max=2)
+    model = SparseConvNet(mid_channel=16).to(cuda_dev).train()
+    loss, _ = model_step(model, batch, device=cuda_dev)
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="ONE backward"):
+        loss.backward()
+    runs0 = tape.runs
+    model.eval()
+    with torch.no_grad():
+        _, s_eval = model_step(model, batch, device=cuda_dev)
+    assert tape.runs == runs0 and torch.isfinite(s_eval).all()
+    model.train()
+    model.unet.u.blocks.block0.conv_branch[0].eval()  # one BatchNorm of level 2 frozen: levels 1 and 2 run module by
+    _, s1 = model_step(model, batch, device=cuda_dev)  # module, the level-3 sub-tree still qualifies and is taped
+    assert tape.runs == runs0 + 1 and torch.isfinite(s1).all()

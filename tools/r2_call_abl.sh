@@ -1,2 +1,3 @@
 #!/bin/bash
-timeout 300 python tools/cpu_profile_step.py 2>&1 | grep -v Warning | head -75 | cut -c1-190
+B200SP_PDL=1 timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -4
+B200SP_PDL=1 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
