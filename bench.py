@@ -51,6 +51,7 @@ def parse():
     ap.add_argument("--ddp", action="store_true", help="N>1: torch DistributedDataParallel instead of parallel.allreduce_grads")
     ap.add_argument("--model", default="mirror", choices=["mirror", "reference"],
                     help="mirror: doda_b200/unet.py; reference: the reference's own model/unet.py, unchanged, via compat/")
+    ap.add_argument("--attach-tape", action="store_true", help="--model reference: doda_b200.tape.attach(model) (taped U-Net sub-trees)")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one gradient mean AFTER backward instead of the overlapped reducer")
     ap.add_argument("--no-allreduce", action="store_true", help="N>1 diagnosis: skip the collective (load imbalance only)")
     ap.add_argument("--no-gpu-native", action="store_true")
@@ -393,6 +394,9 @@ def main():
         cfg = stage_ref.make_cfg(mid_channel=args.mid)
         model = RefNet(cfg).to(dev).train()
         ref_model_fn = model_fn_decorator(cfg, args.bs)
+        if args.attach_tape:  # optional one-liner of INTEGRATION.md: the reference's UBlocks as one autograd node each
+            from doda_b200 import tape as _tape
+            _tape.attach(model)
     else:
         model = SparseConvNet(mid_channel=args.mid).to(dev).train()
     net = model
@@ -429,6 +433,9 @@ def main():
             # the gradient mean starts as soon as backward leaves the sub-network below level 1 (97 % of the parameters)
             reducer = parallel.OverlappedGradReducer(params, world)
             reducer.attach(model.unet.u)
+            # the hook fires when `unet.u`'s module forward is entered: level 1 runs module by module, levels 2-7 are
+            # the taped sub-tree (one autograd node: all its gradients exist when the hook's tensor gets its gradient)
+            model.unet.tape = False
 
     def step(b):
         for p in params:  # what optimizer.zero_grad(set_to_none=True) does

@@ -323,3 +323,27 @@ def run(ub, p, x):
     res.indice_dict = x.indice_dict
     res.grid = x.grid
     return res
+
+
+def attach(model):
+    """Opt a model built from the REFERENCE's own classes (model/unet_block.py UBlock / ResidualBlock / VGGBlock on the
+    engine's spconv surface) into taped execution: every sub-module whose structure `plan` recognises gets an
+    instance-level `forward` that runs the sub-tree as one autograd node when it qualifies and the class's own forward
+    otherwise.  The engine's mirror (doda_b200/unet.py) does this by itself.  Returns the number of sub-trees wrapped
+    (nested ones included: an outer taped run never reaches the inner wrappers)."""
+    n = 0
+    for m in model.modules():
+        if "forward" in m.__dict__ or plan(m) is None:
+            continue
+        cls_forward = m.forward
+
+        def fwd(x, _m=m, _orig=cls_forward):
+            if enabled and _m.training and getattr(_m, "tape", True):
+                p = cached_plan(_m)
+                if usable(_m, p, x):
+                    return run(_m, p, x)
+            return _orig(x)
+
+        m.forward = fwd
+        n += 1
+    return n

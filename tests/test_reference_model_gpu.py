@@ -305,3 +305,39 @@ def test_reference_update_meter_matches_engine_metrics(ref, cuda_dev):
     assert np.array_equal(im.sum, im2.sum) and np.array_equal(um.sum, um2.sum) and np.array_equal(tm.sum, tm2.sum)
     m1, m2 = cu.calc_metrics(im, um, tm), cu.calc_metrics(im2, um2, tm2)
     assert abs(m1[0] - m2[0]) <= 1e-12 and abs(m1[2] - m2[2]) <= 1e-12
+
+
+def test_reference_model_with_attached_tape_is_the_same_computation(ref, cuda_dev):
+    """doda_b200.tape.attach(model) on the reference's OWN classes (optional one-liner of INTEGRATION.md): the U-Net
+    runs as one autograd node, and loss / scores / BatchNorm running statistics / BatchNorm gradients are bit-identical
+    to the unchanged module-by-module execution, conv weight gradients (float atomics on both sides) within 1e-5"""
+    from model.unet import SparseConvNet as RefNet, model_fn_decorator
+    from doda_b200 import tape
+    cfg = ref.make_cfg(mid_channel=16)
+    batch = _batch(8000)
+    torch.manual_seed(3)
+    net = RefNet(cfg).to(cuda_dev).train()
+    sd0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    model_fn = model_fn_decorator(cfg, 2)
+    out = {}
+    for attached in (False, True):
+        net.load_state_dict(sd0)
+        for p in net.parameters():
+            p.grad = None
+        if attached:
+            assert tape.attach(net) >= 1
+        runs0 = tape.runs
+        ret = model_fn(batch, net, 0)
+        ret["loss"].backward()
+        assert (tape.runs - runs0 == 1) == attached
+        out[attached] = (ret["loss"].detach().clone(), ret["output"].detach().clone(),
+                         {n: p.grad.detach().clone() for n, p in net.named_parameters()},
+                         {n: b.detach().clone() for n, b in net.named_buffers()})
+    assert torch.equal(out[True][0], out[False][0]) and torch.equal(out[True][1], out[False][1])
+    for n, b in out[False][3].items():
+        assert torch.equal(b, out[True][3][n]), n
+    for n, g in out[False][2].items():
+        if g.dim() >= 3:
+            assert rel_err(out[True][2][n], g) <= 1e-5, n
+        else:
+            assert torch.equal(out[True][2][n], g), n
