@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--model", default="mirror", choices=["mirror", "reference"],
                     help="mirror: doda_b200/unet.py; reference: the reference's own model/unet.py, unchanged, via compat/")
     ap.add_argument("--attach-tape", action="store_true", help="--model reference: doda_b200.tape.attach(model) (taped U-Net sub-trees)")
+    ap.add_argument("--no-top-tape", action="store_true", help="diagnosis: level 1 module by module, levels 2-7 taped (what N>1 runs)")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one gradient mean AFTER backward instead of the overlapped reducer")
     ap.add_argument("--no-allreduce", action="store_true", help="N>1 diagnosis: skip the collective (load imbalance only)")
     ap.add_argument("--no-gpu-native", action="store_true")
@@ -424,6 +425,8 @@ def main():
     del grow
 
     params = [p for p in model.parameters()]
+    if args.no_top_tape and hasattr(model, "unet"):
+        model.unet.tape = False
     from doda_b200 import ops as _engine_ops
     from doda_b200 import parallel
     reducer = None
