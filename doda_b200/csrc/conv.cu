@@ -405,12 +405,14 @@ namespace b200sp {
 int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, int wflags, const int* tab, const int* orow,
                 const int* rowmask, const int* pin,
                 const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out, int Cout,
-                int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st, int64_t n_in);
+                int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st, int64_t n_in,
+                const float* res = nullptr);
 int64_t conv_tc_ws_bytes(int K, int Cin, int Cout);
 bool conv_direct_covers(int K, int Cin, int Cout);
 void conv_direct_set(int on);
 int conv_direct_run(const float* in, int Cin, const float* W, int wflags, const int* tab, const int* orow,
-                    const int* rowmask, long long n_rows, int K, float* out, int Cout, int accumulate, cudaStream_t st);
+                    const int* rowmask, long long n_rows, int K, float* out, int Cout, int accumulate, cudaStream_t st,
+                    const float* res = nullptr);
 int conv_tc_prep_batch(const int64_t* desc_host, int n, void* desc_dev, int64_t desc_dev_bytes, cudaStream_t st);
 bool wgrad_direct_covers(int K, int Ca, int Cb);
 int wgrad_direct_run(const float* a, int Ca, const float* g, int Cb, const int* tab, const int* orow, const int* rowmask,
@@ -493,20 +495,29 @@ extern "C" int64_t b200sp_conv_ws_bytes(int K, int Cin, int Cout) {
     return align_up(a > b ? a : b, 256);
 }
 
-extern "C" int b200sp_gather_gemm(const float* in, int64_t n_in, int Cin, const float* W, int wflags, const int32_t* tab,
-                                  const int32_t* orow, const int32_t* rowmask, int K, float* out, int64_t n_out, int Cout,
-                                  int accumulate, void* ws, int64_t ws_bytes, void* stream) {
+namespace b200sp {
+namespace {
+__global__ void __launch_bounds__(256) k_add_rows(float* __restrict__ a, const float* __restrict__ b, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) a[i] += __ldg(b + i);
+}
+}  // namespace
+
+// res != NULL: out = conv + res (res [n_out][Cout], may not alias out); accumulate: out += conv
+int gather_gemm_impl(const float* in, int64_t n_in, int Cin, const float* W, int wflags, const int32_t* tab,
+                     const int32_t* orow, const int32_t* rowmask, int K, float* out, int64_t n_out, int Cout,
+                     int accumulate, const float* res, void* ws, int64_t ws_bytes, void* stream) {
     B200SP_CHECK_ARG(Cin >= 1 && Cout >= 1 && K >= 1, "gather_gemm: bad Cin/Cout/K");
     B200SP_CHECK_ARG(K <= GG_MAXK, "gather_gemm: K=%d > %d not supported by this build", K, GG_MAXK);
     B200SP_CHECK_ARG(tab || K == 1, "gather_gemm: tab==NULL requires K==1");
+    B200SP_CHECK_ARG(!(res && accumulate), "gather_gemm: a residual and accumulate exclude each other");
     if (n_out == 0) return B200SP_OK;
     cudaStream_t st = (cudaStream_t)stream;
     if (conv_impl() == 0) {
         const int Ci_w = (wflags & 1) ? Cout : Cin, Co_w = (wflags & 1) ? Cin : Cout;
-        int rc = conv_direct_run(in, Cin, W, wflags, tab, orow, rowmask, n_out, K, out, Cout, accumulate, st);
+        int rc = conv_direct_run(in, Cin, W, wflags, tab, orow, rowmask, n_out, K, out, Cout, accumulate, st, res);
         if (rc != B200SP_EUNSUP) return rc;
         rc = conv_tc_run(in, Cin, W, Ci_w, Co_w, wflags, tab, orow, rowmask, nullptr, nullptr, nullptr, n_out, 0, K, out, Cout,
-                             accumulate, 0, ws, ws_bytes, st, tab ? n_in : n_out);
+                             accumulate, 0, ws, ws_bytes, st, tab ? n_in : n_out, res);
         if (rc != B200SP_EUNSUP) return rc;
     }
     B200SP_CHECK_ARG(!(wflags & 4), "gather_gemm: a prepared weight image needs the tensor path");
@@ -518,7 +529,26 @@ extern "C" int b200sp_gather_gemm(const float* in, int64_t n_in, int Cin, const 
     p.n_rows = n_out; p.Cin = Cin; p.Cout = Cout; p.K = K;
     p.accumulate = accumulate; p.pairs_mode = 0;
     note_kernel("k_gather_gemm");
-    return dispatch_gg(p, n_out, 1, st);
+    rc = dispatch_gg(p, n_out, 1, st);
+    if (rc || !res) return rc;
+    const int64_t n = n_out * Cout;  // the CUDA-core fallback adds the residual in a second pass
+    k_add_rows<<<(unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 8), 256, 0, st>>>(out, res, n);
+    B200SP_LAUNCH_CHECK();
+    return B200SP_OK;
+}
+}  // namespace b200sp
+
+extern "C" int b200sp_gather_gemm(const float* in, int64_t n_in, int Cin, const float* W, int wflags, const int32_t* tab,
+                                  const int32_t* orow, const int32_t* rowmask, int K, float* out, int64_t n_out, int Cout,
+                                  int accumulate, void* ws, int64_t ws_bytes, void* stream) {
+    return gather_gemm_impl(in, n_in, Cin, W, wflags, tab, orow, rowmask, K, out, n_out, Cout, accumulate, nullptr, ws, ws_bytes,
+                            stream);
+}
+
+extern "C" int b200sp_gather_gemm_res(const float* in, int64_t n_in, int Cin, const float* W, int wflags, const int32_t* tab,
+                                      const int32_t* orow, const int32_t* rowmask, int K, float* out, int64_t n_out, int Cout,
+                                      const float* res, void* ws, int64_t ws_bytes, void* stream) {
+    return gather_gemm_impl(in, n_in, Cin, W, wflags, tab, orow, rowmask, K, out, n_out, Cout, 0, res, ws, ws_bytes, stream);
 }
 
 extern "C" int b200sp_gather_gemm_pairs(const float* in, int Cin, const float* W, int wflags, const int32_t* pin,

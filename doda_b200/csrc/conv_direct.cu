@@ -31,6 +31,7 @@ struct DirectParams {
     int transposed;       // Weff[k][ci][co] = W[k'][co][ci]
     int mirror;           // k' = K-1-k
     int accumulate;
+    const float* res;     // added to the result: out itself when accumulating, a residual branch, or nullptr
     int total_warps;
 };
 
@@ -176,13 +177,13 @@ __global__ void __launch_bounds__(256) k_conv_direct(const DirectParams p) {
                 if (va_ok) {
                     float4 v = make_float4(acc[m][G][0][0], acc[m][G][1][0], acc[m][G][0][1], acc[m][G][1][1]);
                     float4* dst = (float4*)(p.out + (size_t)oa * Cout + c);
-                    if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                    if (p.res) { const float4 o = *(const float4*)(p.res + (size_t)oa * Cout + c); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
                     *dst = v;
                 }
                 if (vb_ok) {
                     float4 v = make_float4(acc[m][G][0][2], acc[m][G][1][2], acc[m][G][0][3], acc[m][G][1][3]);
                     float4* dst = (float4*)(p.out + (size_t)ob * Cout + c);
-                    if (p.accumulate) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                    if (p.res) { const float4 o = *(const float4*)(p.res + (size_t)ob * Cout + c); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
                     *dst = v;
                 }
             }
@@ -237,7 +238,7 @@ bool conv_direct_covers(int K, int Cin, int Cout) {
 
 // table mode only (tab [n_rows][K] or identity); B200SP_EUNSUP when the shape is not covered
 int conv_direct_run(const float* in, int Cin, const float* W, int wflags, const int* tab, const int* orow,
-                    const int* rowmask, long long n_rows, int K, float* out, int Cout, int accumulate, cudaStream_t st) {
+                    const int* rowmask, long long n_rows, int K, float* out, int Cout, int accumulate, cudaStream_t st, const float* res) {
     if (!conv_direct_covers(K, Cin, Cout) || (wflags & 4)) return B200SP_EUNSUP;
     if (!tab && K != 1) return B200SP_EUNSUP;
     B200SP_CHECK_ARG((((uintptr_t)in | (uintptr_t)out | (uintptr_t)W) & 15) == 0, "conv_direct: pointers must be 16-byte aligned");
@@ -246,6 +247,8 @@ int conv_direct_run(const float* in, int Cin, const float* W, int wflags, const 
     p.in = in; p.W = W; p.tab = tab; p.orow = orow; p.rowmask = rowmask; p.out = out;
     p.n_rows = n_rows; p.K = K; p.Cin = Cin; p.Cout = Cout;
     p.transposed = wflags & 1; p.mirror = (wflags >> 1) & 1; p.accumulate = accumulate;
+    p.res = res ? res : (accumulate ? out : nullptr);
+    B200SP_CHECK_ARG(((uintptr_t)p.res & 15) == 0, "conv_direct: residual pointer must be 16-byte aligned");
     const int groups = Cout / 16;
     const int ng = groups == 4 ? 2 : groups;  // 64 columns = two warps of 32
     const int ysplit = groups / ng;

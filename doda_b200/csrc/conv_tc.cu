@@ -66,6 +66,8 @@ struct TCParams {
     int Cin, Cout, K;
     int nchunks, Cout_pad;
     int accumulate, pairs_mode;
+    const float* res;       // added to the result (same [row][Cout] layout as out): out itself when accumulating, a residual
+                            // branch for out = conv + res (model/unet_block.py:37), or nullptr
     int nslots;             // A ring (gathered rows, hi + lo tiles)
     int nslots_b;           // B ring (weight blocks): deeper, so weight copies run far ahead of the A slots
     uint32_t stageB_bytes;  // 2 * Cout_pad * KC * 4
@@ -471,14 +473,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const TCParams p, con
                 }
                 if (orow < 0) continue;
                 float* o = p.out + (int64_t)orow * Cout + ch * 16;
+                const float* rs = p.res ? p.res + (int64_t)orow * Cout + ch * 16 : nullptr;
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
                     const int col = ch * 16 + g4 * 4;
                     if (col >= Cout) break;
                     if (vecO) {
                         float4 wv = make_float4(v[g4 * 4 + 0], v[g4 * 4 + 1], v[g4 * 4 + 2], v[g4 * 4 + 3]);
-                        if (p.accumulate) {
-                            const float4 old = *reinterpret_cast<const float4*>(o + g4 * 4);
+                        if (rs) {
+                            const float4 old = *reinterpret_cast<const float4*>(rs + g4 * 4);
                             wv.x += old.x; wv.y += old.y; wv.z += old.z; wv.w += old.w;
                         }
                         *reinterpret_cast<float4*>(o + g4 * 4) = wv;
@@ -487,7 +490,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const TCParams p, con
                         for (int e = 0; e < 4; ++e) {
                             if (col + e < Cout) {
                                 float wv = v[g4 * 4 + e];
-                                if (p.accumulate) wv += o[g4 * 4 + e];
+                                if (rs) wv += rs[g4 * 4 + e];
                                 o[g4 * 4 + e] = wv;
                             }
                         }
@@ -642,18 +645,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const TCParams p, con
                 const int orw = orow_s[row];
                 if (orw < 0) continue;
                 float* o = p.out + (int64_t)orw * Cout + c4 * 4;
+                const float* rs = p.res ? p.res + (int64_t)orw * Cout + c4 * 4 : nullptr;
                 const float av[4] = {acc.x, acc.y, acc.z, acc.w};
                 if (vecO) {
                     float4 wv = acc;
-                    if (p.accumulate) {
-                        const float4 old = *reinterpret_cast<const float4*>(o);
+                    if (rs) {
+                        const float4 old = *reinterpret_cast<const float4*>(rs);
                         wv.x += old.x; wv.y += old.y; wv.z += old.z; wv.w += old.w;
                     }
                     *reinterpret_cast<float4*>(o) = wv;
                 } else {
 #pragma unroll
                     for (int e2 = 0; e2 < 4; ++e2)
-                        if (c4 * 4 + e2 < Cout) o[e2] = p.accumulate ? o[e2] + av[e2] : av[e2];
+                        if (c4 * 4 + e2 < Cout) o[e2] = rs ? rs[e2] + av[e2] : av[e2];
                 }
             }
         }
@@ -957,7 +961,7 @@ static int launch_tc(const TCParams& p0, int KT, int64_t n_in, cudaStream_t st) 
 // returns B200SP_EUNSUP when the shape is outside what the tensor path covers (caller falls back to the fp32 kernel)
 int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, int wflags, const int* tab, const int* orow,
                 const int* rowmask, const int* pin, const int* pout, const int* pairnum, int64_t n_rows, int64_t pstride, int K, float* out,
-                int Cout, int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st, int64_t n_in) {
+                int Cout, int accumulate, int pairs_mode, void* ws, int64_t ws_bytes, cudaStream_t st, int64_t n_in, const float* res) {
     TCPlan pl;
     const int KT = pairs_mode ? 1 : K;
     if (!tc_plan(K, Cin, Cout, KT, pl, cdiv(n_rows, TC_BM) * (pairs_mode ? K : 1))) return B200SP_EUNSUP;
@@ -981,6 +985,8 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
     p.in = in; p.Wp = Wp; p.tab = tab; p.orow = orow; p.rowmask = rowmask; p.pin = pin; p.pout = pout; p.pairnum = pairnum; p.out = out;
     p.n_rows = n_rows; p.pstride = pstride; p.Cin = Cin; p.Cout = Cout; p.K = K;
     p.nchunks = pl.nchunks; p.Cout_pad = pl.Cout_pad; p.accumulate = accumulate; p.pairs_mode = pairs_mode;
+    p.res = res ? res : (accumulate ? out : nullptr);
+    if (((uintptr_t)p.res & 15) != 0) return B200SP_EUNSUP;  // the epilogue reads it as float4
     p.nslots = pl.nslots; p.nslots_b = pl.nslots_b; p.stageB_bytes = pl.stageB; p.tmem_cols = pl.tmem_cols; p.ni = pl.ni;
     {
         B200SP_ENV_INT(env_dbg, "B200SP_TC_DEBUG", 0);

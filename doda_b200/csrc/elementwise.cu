@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
                                                       const float* __restrict__ c_g,
                                                       const float* __restrict__ c_mean_g,
                                                       const float* __restrict__ c_mean_gx, int relu,
-                                                      float* __restrict__ dx) {
+                                                      float* __restrict__ dx, const float* __restrict__ add) {
     pdl_trigger();
     pdl_wait();
     const int CG = C / VEC;
@@ -289,7 +289,16 @@ __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ 
             float g = gv[v];
             if (relu && fmaf(xv[v], scale[c], shift[c]) <= 0.f) g = 0.f;
             float xhat = (xv[v] - mean[c]) * invstd[c];
-            o[v] = c_g[c] * (g - c_mean_g[c] - xhat * c_mean_gx[c]);
+            o[v] = __fmul_rn(c_g[c], g - c_mean_g[c] - xhat * c_mean_gx[c]);
+        }
+        if (add) {  // gradient of a second consumer of x (residual skip, U-Net skip): a separate rounded add, as if the
+                    // sum were formed by a following kernel (no contraction with the product above)
+            if (VEC == 4) {
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(add) + i);
+                o[0] = __fadd_rn(o[0], a4.x); o[1] = __fadd_rn(o[1], a4.y); o[2] = __fadd_rn(o[2], a4.z); o[3] = __fadd_rn(o[3], a4.w);
+            } else {
+                o[0] = __fadd_rn(o[0], __ldg(add + i));
+            }
         }
         if (VEC == 4) reinterpret_cast<float4*>(dx)[i] = make_float4(o[0], o[1], o[2], o[3]);
         else dx[i] = o[0];
@@ -447,11 +456,12 @@ extern "C" int b200sp_affine_relu(const float* x, int64_t M, int C, const float*
     return B200SP_OK;
 }
 
-extern "C" int b200sp_bn_bwd(const float* x, const float* dy, int64_t M, int C, const float* w, const float* b,
-                             const float* mean, const float* invstd, int relu, float* dx, float* dw, float* db,
-                             void* ws, int64_t ws_bytes, void* stream) {
+extern "C" int b200sp_bn_bwd_add(const float* x, const float* dy, int64_t M, int C, const float* w, const float* b,
+                                 const float* mean, const float* invstd, int relu, float* dx, float* dw, float* db,
+                                 const float* add, void* ws, int64_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     B200SP_CHECK_ARG(M >= 1 && C >= 1, "bn_bwd: need M>=1, C>=1");
+    B200SP_CHECK_ARG(!add || ((uintptr_t)add & 15) == 0 || !(vec4_ok(C, x, dy, dx) && C / 4 <= BN_THREADS), "bn_bwd: the added gradient must be 16-byte aligned");
     B200SP_CHECK_ARG(ws_bytes >= b200sp_bn_ws_bytes(M, C), "bn_bwd: workspace too small");
     const bool v4 = vec4_ok(C, x, dy, dx) && C / 4 <= BN_THREADS;
     B200SP_CHECK_ARG(v4 || C <= BN_THREADS, "bn_bwd: C=%d unsupported", C);
@@ -469,7 +479,7 @@ extern "C" int b200sp_bn_bwd(const float* x, const float* dy, int64_t M, int C, 
     fin.ticket = reinterpret_cast<unsigned*>(ws);
     fin.M = M; fin.w = w; fin.b = b; fin.scale = scale; fin.shift = shift; fin.dw = dw; fin.db = db;
     fin.c_g = c_g; fin.c_mean_g = c_mg; fin.c_mean_gx = c_mgx;
-    if (v4) {
+    if (v4 && !add) {
         bool done = false;
         int rc = bn_cluster_bwd(x, dy, M, C, relu, dx, fin, mean, invstd, st, &done);
         if (rc != B200SP_OK || done) return rc;
@@ -480,12 +490,18 @@ extern "C" int b200sp_bn_bwd(const float* x, const float* dy, int64_t M, int C, 
         B200SP_CUDA(launch_pdl(k_bn_reduce<1, 1>, dim3(G), dim3(BN_THREADS), smem, st, x, dy, M, C, nullptr, nullptr, mean, invstd, relu, partial, fin));
     if (v4)
         B200SP_CUDA(launch_pdl(k_bn_bwd_apply<4>, dim3(stream_grid(M * (C / 4), 256)), dim3(256), 0, st, x, dy, M, C, scale, shift,
-                               mean, invstd, c_g, c_mg, c_mgx, relu, dx));
+                               mean, invstd, c_g, c_mg, c_mgx, relu, dx, v4 ? add : nullptr));
     else
         B200SP_CUDA(launch_pdl(k_bn_bwd_apply<1>, dim3(stream_grid(M * C, 256)), dim3(256), 0, st, x, dy, M, C, scale, shift, mean,
-                               invstd, c_g, c_mg, c_mgx, relu, dx));
+                               invstd, c_g, c_mg, c_mgx, relu, dx, v4 ? nullptr : add));
     B200SP_LAUNCH_CHECK_N(2);
     return B200SP_OK;
+}
+
+extern "C" int b200sp_bn_bwd(const float* x, const float* dy, int64_t M, int C, const float* w, const float* b,
+                             const float* mean, const float* invstd, int relu, float* dx, float* dw, float* db,
+                             void* ws, int64_t ws_bytes, void* stream) {
+    return b200sp_bn_bwd_add(x, dy, M, C, w, b, mean, invstd, relu, dx, dw, db, nullptr, ws, ws_bytes, stream);
 }
 
 extern "C" int b200sp_voxelize_fp(const float* feats, float* out, const int32_t* map, int average, int64_t M, int A,

@@ -71,8 +71,14 @@ struct Weights {
     int64_t ws_bytes;
 };
 
+// res != nullptr: out = conv + res (the residual / skip branch that meets this layer's output, or, in a dgrad, the
+// gradient of a second consumer of this layer's input)
 int gg(const float* in, int64_t n_in, int Cin, const Weights& w, int wflags, const int32_t* tab, const int32_t* orow,
-       const int32_t* rowmask, int K, float* out, int64_t n_out, int Cout, void* st) {
+       const int32_t* rowmask, int K, float* out, int64_t n_out, int Cout, void* st, const float* res = nullptr) {
+    if (res) {
+        if (w.img) return b200sp_gather_gemm_res(in, n_in, Cin, w.img, wflags | W_PREP, tab, orow, rowmask, K, out, n_out, Cout, res, nullptr, 0, st);
+        return b200sp_gather_gemm_res(in, n_in, Cin, w.raw, wflags, tab, orow, rowmask, K, out, n_out, Cout, res, w.ws, w.ws_bytes, st);
+    }
     if (w.img) return b200sp_gather_gemm(in, n_in, Cin, w.img, wflags | W_PREP, tab, orow, rowmask, K, out, n_out, Cout, 0, nullptr, 0, st);
     return b200sp_gather_gemm(in, n_in, Cin, w.raw, wflags, tab, orow, rowmask, K, out, n_out, Cout, 0, w.ws, w.ws_bytes, st);
 }
@@ -86,13 +92,14 @@ int gg_pairs(const float* in, int Cin, const Weights& w, int wflags, const RB& r
 
 // forward of one sparse conv: out [n_out, Cout] from feat [M, Cin]
 int conv_forward(int kind, const RB& rb, const float* feat, int64_t M, int Cin, const Weights& w, int Kw, float* out,
-                 int Cout, void* st) {
+                 int Cout, void* st, const float* res = nullptr) {
+    B200SP_CHECK_ARG(!res || kind == KIND_SUBM || kind == KIND_DENSE, "conv_layer_fwd: a residual needs a conv that keeps the sites");
     switch (kind) {
         case KIND_SUBM:
-            if (rb.nbr_perm) return gg(feat, M, Cin, w, 0, rb.nbr_perm, rb.order, rb.rowmask, Kw, out, M, Cout, st);
-            return gg(feat, M, Cin, w, 0, rb.nbr, nullptr, nullptr, Kw, out, M, Cout, st);
+            if (rb.nbr_perm) return gg(feat, M, Cin, w, 0, rb.nbr_perm, rb.order, rb.rowmask, Kw, out, M, Cout, st, res);
+            return gg(feat, M, Cin, w, 0, rb.nbr, nullptr, nullptr, Kw, out, M, Cout, st, res);
         case KIND_DENSE:
-            return gg(feat, M, Cin, w, 0, nullptr, nullptr, nullptr, 1, out, M, Cout, st);
+            return gg(feat, M, Cin, w, 0, nullptr, nullptr, nullptr, 1, out, M, Cout, st, res);
         case KIND_CONV:
             return gg(feat, M, Cin, w, 0, rb.bwd, nullptr, nullptr, Kw, out, rb.n_coarse, Cout, st);
         default:  // inverse: coarse -> fine through the strided conv's rulebook with the roles swapped
@@ -104,13 +111,14 @@ int conv_forward(int kind, const RB& rb, const float* feat, int64_t M, int Cin, 
 
 // dgrad: din [M, Cin] from g [n_g, Cout] (the conv maps Cin -> Cout; wflags transpose the weights)
 int conv_dgrad(int kind, const RB& rb, const float* g, int64_t n_g, int Cin, const Weights& w, int Kw, float* din, int64_t M,
-               int Cout, void* st) {
+               int Cout, void* st, const float* res = nullptr) {
+    B200SP_CHECK_ARG(!res || kind == KIND_SUBM || kind == KIND_DENSE, "conv_layer_bwd: dx_add without BatchNorm needs a conv that keeps the sites");
     switch (kind) {
         case KIND_SUBM:
-            if (rb.nbr_perm) return gg(g, n_g, Cout, w, W_T_MIRROR, rb.nbr_perm, rb.order, rb.rowmask, Kw, din, M, Cin, st);
-            return gg(g, n_g, Cout, w, W_T_MIRROR, rb.nbr, nullptr, nullptr, Kw, din, M, Cin, st);
+            if (rb.nbr_perm) return gg(g, n_g, Cout, w, W_T_MIRROR, rb.nbr_perm, rb.order, rb.rowmask, Kw, din, M, Cin, st, res);
+            return gg(g, n_g, Cout, w, W_T_MIRROR, rb.nbr, nullptr, nullptr, Kw, din, M, Cin, st, res);
         case KIND_DENSE:
-            return gg(g, n_g, Cout, w, W_T, nullptr, nullptr, nullptr, 1, din, M, Cin, st);
+            return gg(g, n_g, Cout, w, W_T, nullptr, nullptr, nullptr, 1, din, M, Cin, st, res);
         case KIND_CONV:
             if (rb.nonoverlap && !b200sp_conv_direct_covers(Kw, Cout, Cin) && rb.pairs_in)
                 return gg_pairs(g, Cout, w, W_T, rb, rb.pairs_out, rb.pairs_in, M, din, M, Cin, st);
@@ -162,6 +170,7 @@ __global__ void __launch_bounds__(256) k_add_inplace(float* __restrict__ a, cons
 //  0 kind  1 rb desc (host ptr, 0 for 1x1)  2 x  3 M  4 Cin  5 W  6 W image (fwd) or 0  7 Kw  8 Cout  9 out  10 n_out
 //  11 has_bn  12 bn_w  13 bn_b  14 eps (f64 bits)  15 momentum (f64 bits)  16 running_mean  17 running_var
 //  18 num_batches_tracked  19 y  20 stats [2][Cin]  21 bn_ws  22 bn_ws_bytes  23 conv_ws  24 conv_ws_bytes  25 stream
+//  26 (optional) residual [n_out][Cout]: out = conv + residual (SubM / 1x1 only)
 extern "C" int b200sp_conv_layer_fwd(const int64_t* a, int n) {
     B200SP_CHECK_ARG(a && n >= 26, "conv_layer_fwd: expected 26 arguments, got %d", n);
     const int kind = (int)a[0];
@@ -184,7 +193,7 @@ extern "C" int b200sp_conv_layer_fwd(const int64_t* a, int n) {
         if (rc) return rc;
         feat = y;
     }
-    return conv_forward(kind, rb, feat, M, Cin, w, Kw, out, Cout, st);
+    return conv_forward(kind, rb, feat, M, Cin, w, Kw, out, Cout, st, n >= 27 ? as_ptr<const float>(a[26]) : nullptr);
 }
 
 // args (see doda_b200/ops.py:_layer_bwd_args):
@@ -194,6 +203,8 @@ extern "C" int b200sp_conv_layer_fwd(const int64_t* a, int n) {
 //  23 dy [M][Cin] (gradient of the conv input)  24 dx [M][Cin] (gradient of the BN input)  25 dwb [2][Cin]
 //  26 main stream  27 side stream (0: everything on main)  28 fork event  29 join event
 //  30 grad_y (extra gradient of the exposed BN+ReLU activation, or 0)  31 defer_join (caller joins later)
+//  32 (optional) dx_add [M][Cin]: added to this layer's input gradient (dx with BN, dy without) -- the gradient of a
+//     second consumer of the layer's input (residual skip, U-Net skip connection)
 extern "C" int b200sp_conv_layer_bwd(const int64_t* a, int n) {
     B200SP_CHECK_ARG(a && n >= 32, "conv_layer_bwd: expected 32 arguments, got %d", n);
     const int kind = (int)a[0];
@@ -222,7 +233,8 @@ extern "C" int b200sp_conv_layer_bwd(const int64_t* a, int n) {
     }
     if (need_din) {
         float* dy = as_ptr<float>(a[23]);
-        rc = conv_dgrad(kind, rb, g, n_g, Cin, w, Kw, dy, M, Cout, main_st);
+        const float* dx_add = n >= 33 ? as_ptr<const float>(a[32]) : nullptr;
+        rc = conv_dgrad(kind, rb, g, n_g, Cin, w, Kw, dy, M, Cout, main_st, has_bn ? nullptr : dx_add);
         if (rc) return rc;
         if (a[30]) {
             const int64_t n4 = M * Cin / 4;
@@ -234,8 +246,9 @@ extern "C" int b200sp_conv_layer_bwd(const int64_t* a, int n) {
         if (has_bn) {
             const float* stats = as_ptr<const float>(a[14]);
             float* dwb = as_ptr<float>(a[25]);
-            rc = b200sp_bn_bwd(as_ptr<const float>(a[2]), dy, M, Cin, as_ptr<const float>(a[12]), as_ptr<const float>(a[13]),
-                               stats, stats + Cin, 1, as_ptr<float>(a[24]), dwb, dwb + Cin, as_ptr<void>(a[16]), a[17], main_st);
+            rc = b200sp_bn_bwd_add(as_ptr<const float>(a[2]), dy, M, Cin, as_ptr<const float>(a[12]), as_ptr<const float>(a[13]),
+                                   stats, stats + Cin, 1, as_ptr<float>(a[24]), dwb, dwb + Cin, dx_add, as_ptr<void>(a[16]), a[17],
+                                   main_st);
             if (rc) return rc;
         }
     }

@@ -740,9 +740,9 @@ def _side_state(dev):
     return st
 
 
-def _layer_fwd(kind, x, filters, rb, prep, bn=None):
+def _layer_fwd(kind, x, filters, rb, prep, bn=None, res=None):
     """-> (out, y, stats): one C call for [BN + ReLU +] conv.  bn = (weight, bias, running_mean, running_var,
-    num_batches_tracked, momentum, eps) or None"""
+    num_batches_tracked, momentum, eps) or None; res: [n_out, Cout] added in the conv's epilogue (SubM / 1x1 only)"""
     M, Cin = x.shape
     dev = x.device
     K, Ci_w, Cout = _kcc(filters)
@@ -756,7 +756,8 @@ def _layer_fwd(kind, x, filters, rb, prep, bn=None):
     rbp = rb.descriptor() if rb is not None else None
     if bn is None:
         rc = _fast.layer_fwd(_KIND_ID[kind], rbp, x.data_ptr(), M, Cin, filters.data_ptr(), wimg, K, Cout, out.data_ptr(),
-                             n_out, 0, None, None, 0.0, 0.0, None, None, None, None, None, None, 0, cws, cwn, _stream())
+                             n_out, 0, None, None, 0.0, 0.0, None, None, None, None, None, None, 0, cws, cwn, _stream(),
+                             res.data_ptr() if res is not None else None)
         if rc:
             check(rc, "conv_layer_fwd")
         return out, None, None
@@ -768,14 +769,16 @@ def _layer_fwd(kind, x, filters, rb, prep, bn=None):
                          1, bw.data_ptr() if bw is not None else None, bb.data_ptr() if bb is not None else None,
                          float(eps), float(momentum), rm.data_ptr() if rm is not None else None,
                          rv.data_ptr() if rv is not None else None, nbt.data_ptr() if nbt is not None else None,
-                         y.data_ptr(), stats.data_ptr(), bws.data_ptr(), bws.numel(), cws, cwn, _stream())
+                         y.data_ptr(), stats.data_ptr(), bws.data_ptr(), bws.numel(), cws, cwn, _stream(),
+                         res.data_ptr() if res is not None else None)
     if rc:
         check(rc, "conv_layer_fwd")
     return out, y, stats
 
 
-def _layer_bwd(kind, x, act, filters, grad_out, rb, prep, need_din, need_dw, bn=None, stats=None, grad_y=None):
-    """-> (din or dx, dW, dwb): one C call for wgrad (side stream) + dgrad [+ grad_y] [+ BN backward]"""
+def _layer_bwd(kind, x, act, filters, grad_out, rb, prep, need_din, need_dw, bn=None, stats=None, grad_y=None, dx_add=None):
+    """-> (din or dx, dW, dwb): one C call for wgrad (side stream) + dgrad [+ grad_y] [+ BN backward]; dx_add [M, Cin]:
+    added to the returned input gradient inside the last kernel (the gradient of a second consumer of the input)"""
     M, Cin = act.shape
     dev = act.device
     K, Ci_w, Cout = _kcc(filters)
@@ -808,7 +811,8 @@ def _layer_bwd(kind, x, act, filters, grad_out, rb, prep, need_din, need_dw, bn=
                          dy.data_ptr() if dy is not None else None, dx.data_ptr() if dx is not None else None,
                          dwb.data_ptr() if dwb is not None else None, _stream(), side[1] if side else None,
                          side[2] if side else None, side[3] if side else None,
-                         grad_y.data_ptr() if grad_y is not None else None, 0)
+                         grad_y.data_ptr() if grad_y is not None else None, 0,
+                         dx_add.data_ptr() if dx_add is not None else None)
     if rc:
         check(rc, "conv_layer_bwd")
     return (dx if has_bn else dy), dW, dwb

@@ -174,12 +174,14 @@ def usable(ub, p, x):
 # (contiguous fp32) and the dict {id(parameter): gradient} it adds its parameter gradients to; it returns the gradient
 # of its input and drops its saved activations.
 # ---------------------------------------------------------------------------------------------------
-def _triplet(bn, conv, x, t):
+def _triplet(bn, conv, x, t, res=None):
+    """res: [rows, Cout] added to the conv output in its epilogue; the closure's `add`: added to the returned input
+    gradient inside the BatchNorm backward (both replace a separate elementwise kernel, same fp32 adds)"""
     kind, rb, outids, oshape = conv._resolve(t)
     rm, rv, nbt, momentum = _ops.bn_batch_stats_args(bn)
     prep = _ops.prepared_weights(conv)
     W = conv.weight
-    out, y, stats = _ops._layer_fwd(kind, x, W, rb, prep, (bn.weight, bn.bias, rm, rv, nbt, momentum, bn.eps))
+    out, y, stats = _ops._layer_fwd(kind, x, W, rb, prep, (bn.weight, bn.bias, rm, rv, nbt, momentum, bn.eps), res=res)
     if capture is not None:
         key = capture[1].get(id(bn))
         if key is not None:
@@ -187,10 +189,11 @@ def _triplet(bn, conv, x, t):
     t.indices, t.spatial_shape = outids, oshape
     saved = [x, y, stats]
 
-    def bw(g, grads):
+    def bw(g, grads, add=None):
         x_, y_, stats_ = saved
         saved[:] = (None, None, None)
-        dx, dW, dwb = _ops._layer_bwd(kind, x_, y_, W, g, rb, prep, True, W.requires_grad, bn=(bn.weight, bn.bias), stats=stats_)
+        dx, dW, dwb = _ops._layer_bwd(kind, x_, y_, W, g, rb, prep, True, W.requires_grad, bn=(bn.weight, bn.bias), stats=stats_,
+                                      dx_add=add)
         if dW is not None:
             grads[id(W)] = dW
         if bn.weight is not None and bn.weight.requires_grad:
@@ -225,22 +228,20 @@ def _block(bp, x, t):
     if kind == "vgg":
         return _triplet(trips[0][0], trips[0][1], x, t)
     h1, bw1 = _triplet(trips[0][0], trips[0][1], x, t)
-    h2, bw2 = _triplet(trips[1][0], trips[1][1], h1, t)
     if skip is None:
-        h2.add_(x)  # out.features += identity.features (model/unet_block.py:37)
+        # out.features += identity.features (model/unet_block.py:37): folded into the second conv's epilogue, and the
+        # identity's gradient into the first BatchNorm's backward
+        h2, bw2 = _triplet(trips[1][0], trips[1][1], h1, t, res=x)
 
         def bw(g, grads):
-            dx = bw1(bw2(g, grads), grads)
-            dx.add_(g)
-            return dx
+            return bw1(bw2(g, grads), grads, add=g)
     else:
         s, bws = _plain_conv(skip, x, t)
-        h2.add_(s)
+        h2, bw2 = _triplet(trips[1][0], trips[1][1], h1, t, res=s)
 
         def bw(g, grads):
-            dx = bw1(bw2(g, grads), grads)
-            dx.add_(bws(g, grads))
-            return dx
+            ds = bws(g, grads)
+            return bw1(bw2(g, grads), grads, add=ds)
     return h2, bw
 
 
@@ -273,8 +274,7 @@ def _ublock(p, x, t):
             g = b(g, grads)
         g_skip = g[:, :c0].contiguous()
         g_up = g[:, c0:].contiguous()
-        g = bw_down(bw_child(bw_up(g_up, grads), grads), grads)
-        g.add_(g_skip)
+        g = bw_down(bw_child(bw_up(g_up, grads), grads), grads, add=g_skip)  # + the skip connection's gradient
         for b in reversed(bws):
             g = b(g, grads)
         return g

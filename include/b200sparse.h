@@ -120,6 +120,12 @@ int b200sp_gather_gemm(const float* in_dev, int64_t n_in, int Cin, const float* 
                        const int32_t* tab_dev, const int32_t* orow_dev, const int32_t* rowmask_dev /*or NULL*/, int K,
                        float* out_dev, int64_t n_out, int Cout, int accumulate, void* ws_dev, int64_t ws_bytes,
                        void* stream);
+/* the same with a residual: out = conv + res_dev ([n_out][Cout], must not alias out_dev) -- the `output.features +=
+ * identity.features` of model/unet_block.py:37 folded into the conv's epilogue (same fp32 add, one launch less) */
+int b200sp_gather_gemm_res(const float* in_dev, int64_t n_in, int Cin, const float* W_dev, int wflags,
+                           const int32_t* tab_dev, const int32_t* orow_dev, const int32_t* rowmask_dev /*or NULL*/, int K,
+                           float* out_dev, int64_t n_out, int Cout, const float* res_dev, void* ws_dev, int64_t ws_bytes,
+                           void* stream);
 
 /* pair-grouped variant (each output row written by exactly one pair; used for the non-overlapping
  * inverse conv forward and the strided conv dgrad):  out[po[k][i],:] = in[pi[k][i],:] @ W[k].
@@ -226,6 +232,10 @@ int b200sp_affine_relu(const float* x_dev, int64_t M, int C, const float* scale_
 int b200sp_bn_bwd(const float* x_dev, const float* dy_dev, int64_t M, int C, const float* w_dev, const float* b_dev,
                   const float* mean_dev, const float* invstd_dev, int relu, float* dx_dev, float* dw_dev,
                   float* db_dev, void* ws_dev, int64_t ws_bytes, void* stream);
+/* the same, dx = BN backward + add_dev ([M][C] or NULL): the gradient of a second consumer of x (skip connection) */
+int b200sp_bn_bwd_add(const float* x_dev, const float* dy_dev, int64_t M, int C, const float* w_dev, const float* b_dev,
+                      const float* mean_dev, const float* invstd_dev, int relu, float* dx_dev, float* dw_dev,
+                      float* db_dev, const float* add_dev, void* ws_dev, int64_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Point <-> voxel.  Replaces PG_OP.voxelize_idx (CPU, lib/pointgroup_ops/src/voxelize/voxelize.cpp:11-155),

@@ -47,6 +47,16 @@ busy += cur_e - cur_s
 wall = ivs[-1][1] - ivs[0][0]
 print("steps %d: wall %.2f ms/step, GPU busy (union of kernels) %.2f ms/step, sum of kernel durations %.2f ms/step, kernels/step %d"
       % (NS, wall / NS / 1e3, busy / NS / 1e3, sum(tot.values()) / NS / 1e3, len(evs) // NS))
+try:  # busy time per CUDA stream (compute stream, weight-gradient side stream, index stream)
+    kev = prof.profiler.kineto_results.events()
+    bys = collections.defaultdict(list)
+    for e in kev:
+        if e.device_type() == torch.autograd.DeviceType.CUDA:
+            bys[e.device_resource_id()].append((e.start_ns(), e.start_ns() + e.duration_ns()))
+    for sid, iv in sorted(bys.items(), key=lambda kv: -sum(b - a for a, b in kv[1])):
+        print("  stream %s: %5d kernels/step, busy %.2f ms/step" % (sid, len(iv) // NS, sum(b - a for a, b in iv) / NS / 1e6))
+except Exception as ex:
+    print("per-stream breakdown unavailable:", repr(ex)[:120])
 for name, t in sorted(tot.items(), key=lambda kv: -kv[1])[:28]:
     print("%9.1f us/step %5d  %s" % (t / NS, cnt[name] // NS, name))
 
