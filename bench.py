@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--model", default="mirror", choices=["mirror", "reference"],
                     help="mirror: doda_b200/unet.py; reference: the reference's own model/unet.py, unchanged, via compat/")
     ap.add_argument("--attach-tape", action="store_true", help="--model reference: doda_b200.tape.attach(model) (taped U-Net sub-trees)")
+    ap.add_argument("--as-rank", type=int, default=-1, help="diagnosis at N=1: run the scenes rank R holds in a multi-GPU run")
     ap.add_argument("--no-top-tape", action="store_true", help="diagnosis: level 1 module by module, levels 2-7 taped (what N>1 runs)")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one gradient mean AFTER backward instead of the overlapped reducer")
     ap.add_argument("--no-allreduce", action="store_true", help="N>1 diagnosis: skip the collective (load imbalance only)")
@@ -384,7 +385,7 @@ def main():
     lib.load()  # fail loudly if the extension is missing
 
     torch.manual_seed(0)
-    batch = make_batch(rank, args.bs, args.voxels)
+    batch = make_batch(args.as_rank if (args.as_rank >= 0 and world == 1) else rank, args.bs, args.voxels)
     ref_model_fn = None
     if args.model == "reference":
         # the reference's own files, unchanged (oracle/_ref/src staged by oracle/stage_ref.py), on compat/
