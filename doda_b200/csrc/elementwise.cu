@@ -504,6 +504,17 @@ extern "C" int b200sp_bn_bwd(const float* x, const float* dy, int64_t M, int C, 
     return b200sp_bn_bwd_add(x, dy, M, C, w, b, mean, invstd, relu, dx, dw, db, nullptr, ws, ws_bytes, stream);
 }
 
+extern "C" int b200sp_copy_cols(const float* src, int64_t rows, int src_stride, int src_col0, int ncols, float* dst,
+                                int dst_stride, int dst_col0, void* stream) {
+    B200SP_CHECK_ARG(rows >= 0 && ncols >= 1 && src_col0 >= 0 && dst_col0 >= 0 && src_col0 + ncols <= src_stride &&
+                         dst_col0 + ncols <= dst_stride,
+                     "copy_cols: column range outside the row");
+    if (rows == 0) return B200SP_OK;
+    B200SP_CUDA(cudaMemcpy2DAsync(dst + dst_col0, (size_t)dst_stride * sizeof(float), src + src_col0, (size_t)src_stride * sizeof(float),
+                                  (size_t)ncols * sizeof(float), (size_t)rows, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return B200SP_OK;
+}
+
 extern "C" int b200sp_voxelize_fp(const float* feats, float* out, const int32_t* map, int average, int64_t M, int A,
                                   int C, void* stream) {
     B200SP_CHECK_ARG(M >= 0 && A >= 0 && C >= 1, "voxelize_fp: bad sizes");

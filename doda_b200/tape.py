@@ -20,6 +20,7 @@ from torch import nn
 from torch.autograd import Function
 
 from . import ops as _ops
+from ._lib import lib as _lib
 from .spconv.modules import SparseSequential, is_sparse_conv, _is_bn_like
 
 enabled = True          # module-level switch (A/B tests); `B200SP_TAPE=0` in the environment turns it off too
@@ -310,6 +311,267 @@ class UBlockTapeFunction(Function):
             grads.get(id(prm)) if need[3 + i] else None for i, prm in enumerate(ctx.params))
 
 
+# ---------------------------------------------------------------------------------------------------
+# Raw-buffer execution (default): inside a taped sub-tree no intermediate is a torch tensor.  Activations, gradients
+# and BatchNorm statistics live in a few large blocks taken from the caching allocator per step (`_Arena`) and travel
+# between the per-layer C calls as (device pointer, rows, channels); the skip connection's concat and the split of its
+# gradient are 2-D copies (`b200sp_copy_cols`).  What this removes from the host per layer and direction: three
+# `torch.empty`, the tensor bookkeeping around them and ~10 `data_ptr()` calls -- 24 -> ~9 us (forward) and 32 -> ~11
+# us (backward) of 71 layers.  Same C entry points, same arguments, same kernels as the tensor form below it
+# (`raw = False`), which stays as the A/B reference (`test_taped_ublock_*` runs both against the module path).
+# ---------------------------------------------------------------------------------------------------
+raw = _os.environ.get("B200SP_TAPE_RAW", "1") != "0"
+
+
+class _Arena(object):
+    """bump allocator over blocks from torch's caching allocator; everything handed out lives until the arena is dropped
+    (end of the sub-tree's backward).  256-byte aligned."""
+    __slots__ = ("dev", "blocks", "base", "off", "cap", "next_size")
+
+    def __init__(self, dev, first=8 << 20):
+        self.dev, self.blocks, self.base, self.off, self.cap, self.next_size = dev, [], 0, 0, 0, first
+
+    def take(self, nfloats):
+        n = (nfloats + 63) & ~63
+        if self.off + n > self.cap:
+            size = max(self.next_size, n)
+            self.next_size = min(self.next_size * 2, 64 << 20)  # floats: blocks grow 32 MB .. 256 MB
+            t = torch.empty(size, dtype=torch.float32, device=self.dev)
+            self.blocks.append(t)
+            self.base, self.off, self.cap = t.data_ptr(), 0, size
+        p = self.base + 4 * self.off
+        self.off += n
+        return p
+
+    def tensor(self, ptr, rows, C):
+        """a torch view of a buffer handed out earlier (gate capture, the sub-tree's output)"""
+        for t in self.blocks:
+            b = t.data_ptr()
+            if b <= ptr < b + 4 * t.numel():
+                o = (ptr - b) // 4
+                return t[o:o + rows * C].view(rows, C)
+        raise RuntimeError("tape arena: foreign pointer")
+
+
+def _r_triplet(bn, conv, x, t, ar, res=None):
+    """x, res, result: (ptr, rows, C)"""
+    kind, rb, outids, oshape = conv._resolve(t)
+    rm, rv, nbt, momentum = _ops.bn_batch_stats_args(bn)
+    prep = _ops.prepared_weights(conv)
+    W = conv.weight
+    xp, M, Cin = x
+    K, _ciw, Cout = _ops._kcc(W)
+    n_out = _ops._conv_out_rows(kind, rb, M)
+    kid = _ops._KIND_ID[kind]
+    rbp = rb.descriptor() if rb is not None else None
+    Wp = W.data_ptr()
+    if prep:
+        wf, wb, cws, cwn = prep[0].data_ptr(), prep[1].data_ptr(), None, 0
+    else:
+        ws = _ops._workspace(_ops._conv_ws_bytes(K, Cin, Cout), ar.dev, "conv")
+        wf, wb, cws, cwn = None, None, ws.data_ptr(), ws.numel()
+    bw_, bb_ = bn.weight, bn.bias
+    bwp = bw_.data_ptr() if bw_ is not None else None
+    bbp = bb_.data_ptr() if bb_ is not None else None
+    bws = _ops._workspace(_ops._bn_ws_bytes(Cin), ar.dev, "bn")
+    bwsp, bwsn = bws.data_ptr(), bws.numel()
+    out = ar.take(n_out * Cout)
+    y = ar.take(M * Cin)
+    stats = ar.take(2 * Cin)
+    rc = _ops._fast.layer_fwd(kid, rbp, xp, M, Cin, Wp, wf, K, Cout, out, n_out, 1, bwp, bbp, float(bn.eps), float(momentum),
+                              rm.data_ptr() if rm is not None else None, rv.data_ptr() if rv is not None else None,
+                              nbt.data_ptr() if nbt is not None else None, y, stats, bwsp, bwsn, cws, cwn, _ops._stream(),
+                              res[0] if res is not None else None)
+    if rc:
+        _ops.check(rc, "conv_layer_fwd")
+    if capture is not None:
+        key = capture[1].get(id(bn))
+        if key is not None:
+            capture[0][key] = (ar.tensor(y, M, Cin) > 0).cpu()
+    t.indices, t.spatial_shape = outids, oshape
+    need_dw = W.requires_grad
+
+    def bw(g, grads, add=None, _keep=(rb, prep)):  # _keep: the rulebook's tables and the weight images stay alive
+        # g: (ptr, rows, Cout) -> (ptr, M, Cin).  Scratch buffers are looked up again here: they are grow-only and a
+        # pointer taken during the forward may be stale by now
+        dW = _ops._dw_arena.take(W.shape, ar.dev) if need_dw else None
+        dy = ar.take(M * Cin)
+        dx = ar.take(M * Cin)
+        dwb = grads["__dwb"].take(2 * Cin)
+        bws = _ops._workspace(_ops._bn_ws_bytes(Cin), ar.dev, "bn")
+        bwsp, bwsn = bws.data_ptr(), bws.numel()
+        cws_b, cwn_b = None, 0
+        if wb is None:
+            ws2 = _ops._workspace(_ops._conv_ws_bytes(K, Cout, Cin), ar.dev, "conv")
+            cws_b, cwn_b = ws2.data_ptr(), ws2.numel()
+        side = _ops._side_state(ar.dev) if (need_dw and _ops.async_wgrad and M <= _ops.async_wgrad_max_rows) else None
+        rc = _ops._fast.layer_bwd(kid, rbp, xp, M, Cin, Wp, wb, K, Cout, g[0], g[1], 1, bwp, bbp, stats, y, bwsp, bwsn,
+                                  cws_b, cwn_b, 1, 1 if need_dw else 0, dW.data_ptr() if dW is not None else None, dy, dx, dwb,
+                                  _ops._stream(), side[1] if side else None, side[2] if side else None,
+                                  side[3] if side else None, None, 0, add[0] if add is not None else None)
+        if rc:
+            _ops.check(rc, "conv_layer_bwd")
+        if dW is not None:
+            grads[id(W)] = dW
+        if bw_ is not None and bw_.requires_grad:
+            grads[id(bw_)] = (dwb, Cin)
+        if bb_ is not None and bb_.requires_grad:
+            grads[id(bb_)] = (dwb + 4 * Cin, Cin)
+        return (dx, M, Cin)
+
+    return (out, n_out, Cout), bw
+
+
+def _r_plain_conv(conv, x, t, ar):
+    kind, rb, outids, oshape = conv._resolve(t)
+    prep = _ops.prepared_weights(conv)
+    W = conv.weight
+    xp, M, Cin = x
+    K, _ciw, Cout = _ops._kcc(W)
+    n_out = _ops._conv_out_rows(kind, rb, M)
+    kid = _ops._KIND_ID[kind]
+    rbp = rb.descriptor() if rb is not None else None
+    Wp = W.data_ptr()
+    if prep:
+        wf, wb, cws, cwn = prep[0].data_ptr(), prep[1].data_ptr(), None, 0
+    else:
+        ws = _ops._workspace(_ops._conv_ws_bytes(K, Cin, Cout), ar.dev, "conv")
+        wf, wb, cws, cwn = None, None, ws.data_ptr(), ws.numel()
+    out = ar.take(n_out * Cout)
+    rc = _ops._fast.layer_fwd(kid, rbp, xp, M, Cin, Wp, wf, K, Cout, out, n_out, 0, None, None, 0.0, 0.0, None, None, None,
+                              None, None, None, 0, cws, cwn, _ops._stream(), None)
+    if rc:
+        _ops.check(rc, "conv_layer_fwd")
+    need_dw = W.requires_grad
+
+    def bw(g, grads, _keep=(rb, prep)):
+        dW = _ops._dw_arena.take(W.shape, ar.dev) if need_dw else None
+        dy = ar.take(M * Cin)
+        cws_b, cwn_b = None, 0
+        if wb is None:
+            ws2 = _ops._workspace(_ops._conv_ws_bytes(K, Cout, Cin), ar.dev, "conv")
+            cws_b, cwn_b = ws2.data_ptr(), ws2.numel()
+        side = _ops._side_state(ar.dev) if (need_dw and _ops.async_wgrad and M <= _ops.async_wgrad_max_rows) else None
+        rc = _ops._fast.layer_bwd(kid, rbp, None, M, Cin, Wp, wb, K, Cout, g[0], g[1], 0, None, None, None, xp, None, 0,
+                                  cws_b, cwn_b, 1, 1 if need_dw else 0, dW.data_ptr() if dW is not None else None, dy, None,
+                                  None, _ops._stream(), side[1] if side else None, side[2] if side else None,
+                                  side[3] if side else None, None, 0, None)
+        if rc:
+            _ops.check(rc, "conv_layer_bwd")
+        if dW is not None:
+            grads[id(W)] = dW
+        return (dy, M, Cin)
+
+    return (out, n_out, Cout), bw
+
+
+def _r_block(bp, x, t, ar):
+    kind, trips, skip = bp
+    if kind == "vgg":
+        return _r_triplet(trips[0][0], trips[0][1], x, t, ar)
+    h1, bw1 = _r_triplet(trips[0][0], trips[0][1], x, t, ar)
+    if skip is None:
+        h2, bw2 = _r_triplet(trips[1][0], trips[1][1], h1, t, ar, res=x)
+
+        def bw(g, grads):
+            return bw1(bw2(g, grads), grads, add=g)
+    else:
+        s, bws = _r_plain_conv(skip, x, t, ar)
+        h2, bw2 = _r_triplet(trips[1][0], trips[1][1], h1, t, ar, res=s)
+
+        def bw(g, grads):
+            ds = bws(g, grads)
+            return bw1(bw2(g, grads), grads, add=ds)
+    return h2, bw
+
+
+def _copy_cols(src, src_col0, ncols, dst, dst_col0):
+    rc = _lib.b200sp_copy_cols(src[0], src[1], src[2], src_col0, ncols, dst[0], dst[2], dst_col0, _ops._stream())
+    if rc:
+        _ops.check(rc, "copy_cols")
+
+
+def _r_ublock(p, x, t, ar):
+    bws = []
+    h = x
+    for bp in p["blocks"]:
+        h, b = _r_block(bp, h, t, ar)
+        bws.append(b)
+    if p["tail"] is None:
+        def bw(g, grads):
+            for b in reversed(bws):
+                g = b(g, grads)
+            return g
+        return h, bw
+    rows, c0 = h[1], h[2]
+    fine_rows = t.indices.shape[0]
+    d, bw_down = _r_triplet(p["down"][0], p["down"][1], h, t, ar)
+    u, bw_child = _r_ublock(p["child"], d, t, ar)
+    up, bw_up = _r_triplet(p["up"][0], p["up"][1], u, t, ar)
+    assert t.indices.shape[0] == fine_rows and up[1] == rows
+    c1 = up[2]
+    cat = (ar.take(rows * (c0 + c1)), rows, c0 + c1)  # torch.cat((identity, decoder), dim=1), model/unet_block.py:95
+    _copy_cols(h, 0, c0, cat, 0)
+    _copy_cols(up, 0, c1, cat, c0)
+    h = cat
+    tails = []
+    for bp in p["tail"]:
+        h, b = _r_block(bp, h, t, ar)
+        tails.append(b)
+
+    def bw(g, grads):
+        for b in reversed(tails):
+            g = b(g, grads)
+        g_skip = (ar.take(rows * c0), rows, c0)
+        g_up = (ar.take(rows * c1), rows, c1)
+        _copy_cols(g, 0, c0, g_skip, 0)
+        _copy_cols(g, c0, c1, g_up, 0)
+        g = bw_down(bw_child(bw_up(g_up, grads), grads), grads, add=g_skip)
+        for b in reversed(bws):
+            g = b(g, grads)
+        return g
+
+    return h, bw
+
+
+class UBlockRawTapeFunction(Function):
+    """the same node on raw buffers: forward(features, plan, metadata tensor, *parameters)"""
+
+    @staticmethod
+    def forward(ctx, feats, p, t, *params):
+        feats = _ops._f32c(feats)
+        ar = _Arena(feats.device)
+        out, bw = _r_ublock(p, (feats.data_ptr(), feats.shape[0], feats.shape[1]), t, ar)
+        ctx.bw, ctx.ar, ctx.params, ctx.x = bw, ar, params, feats  # feats: the first layer reads it again in backward
+        # the output leaves the arena as a tensor of its own block-view; the arena stays alive through ctx until backward
+        return ar.tensor(out[0], out[1], out[2])
+
+    @staticmethod
+    def backward(ctx, g):
+        bw, ar = ctx.bw, ctx.ar
+        ctx.bw = ctx.ar = None
+        if bw is None:
+            raise RuntimeError("doda_b200.tape: a taped U-Net sub-tree supports ONE backward pass (its activations are "
+                               "released as the gradient passes; retain_graph / double backward need B200SP_TAPE=0)")
+        g = _ops._f32c(g)
+        small = _Arena(g.device, first=1 << 16)  # BatchNorm gradients: blocks of their own, they outlive this node
+        grads = {"__dwb": small}
+        try:
+            dx = bw((g.data_ptr(), g.shape[0], g.shape[1]), grads)
+        except BaseException:
+            _ops._drop_pending_join()
+            raise
+        need = ctx.needs_input_grad
+        out = []
+        for i, prm in enumerate(ctx.params):
+            v = grads.get(id(prm)) if need[3 + i] else None
+            if type(v) is tuple:  # BatchNorm gradients: (pointer, C) inside the small arena
+                v = small.tensor(v[0], 1, v[1]).view(v[1])
+            out.append(v)
+        dxt = ar.tensor(dx[0], dx[1], dx[2]) if need[0] else None
+        return (dxt, None, None) + tuple(out)
+
+
 def run(ub, p, x):
     """x: SparseConvTensor entering the UBlock `ub` (plan p) -> SparseConvTensor leaving it"""
     from .spconv import SparseConvTensor
@@ -318,7 +580,7 @@ def run(ub, p, x):
     t = SparseConvTensor(None, x.indices, x.spatial_shape, x.batch_size)
     t.indice_dict = x.indice_dict
     t.grid = x.grid
-    out = UBlockTapeFunction.apply(x.features, p, t, *p["_params"])
+    out = (UBlockRawTapeFunction if raw else UBlockTapeFunction).apply(x.features, p, t, *p["_params"])
     res = SparseConvTensor(out, t.indices, t.spatial_shape, x.batch_size)
     res.indice_dict = x.indice_dict
     res.grid = x.grid

@@ -253,6 +253,10 @@ int b200sp_voxelize_fp(const float* feats_dev, float* out_dev, const int32_t* ma
 /* d_feats[map[v,1+i],:] += mult * d_out[v,:] */
 int b200sp_voxelize_bp(const float* dout_dev, float* dfeats_dev, const int32_t* map_dev, int average, int64_t M,
                        int max_active, int C, void* stream);
+/* dst[r, dst_col0 : dst_col0 + ncols] = src[r, src_col0 : src_col0 + ncols] for r < rows (row strides in floats): the
+ * channel concat of the U-Net skip connection (model/unet_block.py:95) and the split of its gradient, one 2-D copy */
+int b200sp_copy_cols(const float* src_dev, int64_t rows, int src_stride, int src_col0, int ncols, float* dst_dev,
+                     int dst_stride, int dst_col0, void* stream);
 /* out[i,:] = src[idx[i],:]   (idx int32 or int64) */
 int b200sp_gather_rows(const float* src_dev, const void* idx_dev, int idx_is_i64, int64_t n, int C, float* out_dev,
                        void* stream);

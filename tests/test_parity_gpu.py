@@ -802,8 +802,9 @@ def test_spconv_surface_sequential_semantics(cuda_dev):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("raw", [True, False])
 @pytest.mark.parametrize("residual", [True, False])
-def test_taped_ublock_matches_module_path(cuda_dev, residual):
+def test_taped_ublock_matches_module_path(cuda_dev, residual, raw):
     """doda_b200/tape.py runs the U-Net sub-tree as ONE autograd node (host cost); it must be the same computation as
     the module-by-module path: identical loss, scores, BatchNorm running statistics and BatchNorm / activation
     gradients bit for bit; conv weight gradients (float atomics in both paths) to 1e-5"""
@@ -814,7 +815,9 @@ def test_taped_ublock_matches_module_path(cuda_dev, residual):
     model = SparseConvNet(mid_channel=16, block_residual=residual).to(cuda_dev).train()
     sd0 = {k: v.detach().clone() for k, v in model.state_dict().items()}
     res = {}
+    raw0 = tape.raw
     try:
+        tape.raw = raw  # raw device buffers from a per-step arena (default) / torch tensors per layer
         for on in (False, True):
             tape.enabled = on
             model.load_state_dict(sd0)
@@ -829,6 +832,7 @@ def test_taped_ublock_matches_module_path(cuda_dev, residual):
                        {n: b.detach().clone() for n, b in model.named_buffers()})
     finally:
         tape.enabled = True
+        tape.raw = raw0
     assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
     for n, b in res[False][3].items():
         assert torch.equal(b, res[True][3][n]), n
