@@ -864,3 +864,56 @@ def test_taped_ublock_falls_back_and_frees(cuda_dev):
     model.unet.u.blocks.block0.conv_branch[0].eval()  # one BatchNorm of level 2 frozen: levels 1 and 2 run module by
     _, s1 = model_step(model, batch, device=cuda_dev)  # module, the level-3 sub-tree still qualifies and is taped
     assert tape.runs == runs0 + 1 and torch.isfinite(s1).all()
+
+
+@pytest.mark.gpu
+def test_fused_residual_and_gradient_adds_match_separate_adds(cuda_dev):
+    """b200sp_gather_gemm_res (out = conv + res in the epilogue), b200sp_bn_bwd_add (dx = BN backward + add) and
+    b200sp_copy_cols against the unfused sequences: bit-identical (the same fp32 adds, just not as a kernel of their own)"""
+    from doda_b200 import ops
+    from doda_b200._lib import lib, check
+    torch.manual_seed(0)
+    st = ops._stream()
+    for M, C, Co in ((20000, 16, 16), (9000, 32, 32), (3000, 48, 48), (300, 96, 96), (2000, 32, 16)):
+        coords, shape = surface_coords(1, M // 2, 2)
+        c = torch.from_numpy(coords).to(cuda_dev)
+        rb = ops.build_rulebook(c, 2, shape, 3, 1, 1, 1, subm=True)
+        n = c.shape[0]
+        x = torch.randn(n, C, device=cuda_dev)
+        W3 = torch.randn(27, C, Co, device=cuda_dev) * 0.2
+        res = torch.randn(n, Co, device=cuda_dev)
+        ref = ops.gather_gemm(x, W3, rb.nbr_perm, n, orow=rb.order, rowmask=rb.rowmask) + res
+        out = torch.empty(n, Co, device=cuda_dev)
+        ws = torch.zeros(int(lib.b200sp_conv_ws_bytes(27, C, Co)), dtype=torch.uint8, device=cuda_dev)
+        check(lib.b200sp_gather_gemm_res(x.data_ptr(), n, C, W3.data_ptr(), 0, rb.nbr_perm.data_ptr(), rb.order.data_ptr(),
+                                         rb.rowmask.data_ptr(), 27, out.data_ptr(), n, Co, res.data_ptr(), ws.data_ptr(),
+                                         ws.numel(), st), "gather_gemm_res")
+        assert torch.equal(out, ref), (M, C, Co)
+    for M, C in ((30000, 16), (777, 48), (45, 112), (1000, 10)):
+        x = torch.randn(M, C, device=cuda_dev) * 2 + 0.3
+        dy = torch.randn(M, C, device=cuda_dev)
+        add = torch.randn(M, C, device=cuda_dev)
+        w = torch.rand(C, device=cuda_dev) + 0.5
+        b = torch.randn(C, device=cuda_dev) * 0.1
+        mean, var = x.mean(0), x.var(0, unbiased=False)
+        inv = torch.rsqrt(var + 1e-4)
+        ws = torch.zeros(int(lib.b200sp_bn_ws_bytes(M, C)), dtype=torch.uint8, device=cuda_dev)
+        dx0, dx1 = torch.empty_like(x), torch.empty_like(x)
+        g0, g1 = torch.empty(2, C, device=cuda_dev), torch.empty(2, C, device=cuda_dev)
+        check(lib.b200sp_bn_bwd(x.data_ptr(), dy.data_ptr(), M, C, w.data_ptr(), b.data_ptr(), mean.data_ptr(), inv.data_ptr(), 1,
+                                dx0.data_ptr(), g0.data_ptr(), g0.data_ptr() + 4 * C, ws.data_ptr(), ws.numel(), st), "bn_bwd")
+        check(lib.b200sp_bn_bwd_add(x.data_ptr(), dy.data_ptr(), M, C, w.data_ptr(), b.data_ptr(), mean.data_ptr(), inv.data_ptr(),
+                                    1, dx1.data_ptr(), g1.data_ptr(), g1.data_ptr() + 4 * C, add.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), st), "bn_bwd_add")
+        assert torch.equal(dx1, dx0 + add) and torch.equal(g0, g1), (M, C)
+    a = torch.randn(5000, 48, device=cuda_dev)
+    bsrc = torch.randn(5000, 32, device=cuda_dev)
+    cat = torch.empty(5000, 80, device=cuda_dev)
+    check(lib.b200sp_copy_cols(a.data_ptr(), 5000, 48, 0, 48, cat.data_ptr(), 80, 0, st), "copy_cols")
+    check(lib.b200sp_copy_cols(bsrc.data_ptr(), 5000, 32, 0, 32, cat.data_ptr(), 80, 48, st), "copy_cols")
+    assert torch.equal(cat, torch.cat((a, bsrc), 1))
+    back = torch.empty(5000, 32, device=cuda_dev)
+    check(lib.b200sp_copy_cols(cat.data_ptr(), 5000, 80, 48, 32, back.data_ptr(), 32, 0, st), "copy_cols")
+    assert torch.equal(back, bsrc)
+    with pytest.raises(RuntimeError):
+        check(lib.b200sp_copy_cols(a.data_ptr(), 10, 48, 40, 16, cat.data_ptr(), 80, 0, st), "copy_cols")
