@@ -78,6 +78,8 @@ struct TCParams {
     int nsplit;             // table mode, few row tiles: the active offsets of a row tile are dealt to the nsplit CTAs of
                             // one thread-block CLUSTER; their partial tiles meet through distributed shared memory and
                             // are added in split order 0, 1, ... (deterministic: no float atomics on the output)
+    int meta_bufs;          // tile-metadata buffers in shared memory: 2 (one tile prefetched ahead), or 1 when no CTA gets more
+                            // than one tile -- the 14 KB that frees buy a fourth stage slot at two CTAs per SM
     int use_tma;            // gathers by cp.async.bulk.tensor tile::gather4 (tensor map = kernel parameter) instead of LDGSTS
     int dbg;                // dev only: 1 no MMAs, 2 no gathers, 4 no transform, 8 no epilogue data, 16 no table copy/mask, 32 no weight copies
 };
@@ -96,12 +98,12 @@ struct TCLayout {
     __host__ __device__ static uint32_t offMeta(int nslots, int nslots_b, uint32_t stageB) {
         return offB(nslots) + (uint32_t)nslots_b * stageB;
     }
-    __host__ __device__ static uint32_t offBars(int nslots, int nslots_b, uint32_t stageB, int KT) {
-        uint32_t o = offMeta(nslots, nslots_b, stageB) + TC_NBUF * meta_ints(KT) * 4u;
+    __host__ __device__ static uint32_t offBars(int nslots, int nslots_b, uint32_t stageB, int KT, int mbufs) {
+        uint32_t o = offMeta(nslots, nslots_b, stageB) + (uint32_t)mbufs * meta_ints(KT) * 4u;
         return (o + 15u) & ~15u;
     }
-    __host__ __device__ static uint32_t total(int nslots, int nslots_b, uint32_t stageB, int KT) {
-        return offBars(nslots, nslots_b, stageB, KT) + (uint32_t)(3 * nslots + 2 * nslots_b + 5 * TC_NBUF) * 8u + 16u;
+    __host__ __device__ static uint32_t total(int nslots, int nslots_b, uint32_t stageB, int KT, int mbufs) {
+        return offBars(nslots, nslots_b, stageB, KT, mbufs) + (uint32_t)(3 * nslots + 2 * nslots_b + 5 * TC_NBUF) * 8u + 16u;
     }
 };
 
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(const TCParams p, con
     int* s_meta = reinterpret_cast<int*>(smem + L::offMeta(S, SB, p.stageB_bytes));
     const int meta_ints = (int)L::meta_ints(KT);
     // per buffer: idx[128*KT] | orow[128] | klist[32] | nk | kfixed | pad
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::offBars(S, SB, p.stageB_bytes, KT));  // hi+lo tiles ready -> MMA
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::offBars(S, SB, p.stageB_bytes, KT, p.meta_bufs));  // hi+lo tiles ready -> MMA
     uint64_t* empty = full + S;                                                                // MMA done -> A slot reusable
     uint64_t* raw = empty + S;                                                                 // gathered rows landed -> transform
     uint64_t* fullb = raw + S;            // [SB] weight block landed -> MMA
@@ -745,12 +747,15 @@ __global__ void k_prep_weights_batch(const PrepItem* __restrict__ items) {
 }
 
 struct TCPlan {
-    int KC, nchunks, Cout_pad, nslots, nslots_b, ni;
+    int KC, nchunks, Cout_pad, nslots, nslots_b, ni, meta_bufs;
     uint32_t stageB, tmem_cols, smem;
     int64_t wp_bytes;
 };
 
-static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl, int64_t n_tiles = 0) {
+// two CTAs per SM: 228 KB of shared memory per SM, 1 KB reserved per resident CTA
+constexpr uint32_t TC_TWO_CTA_SMEM = (233472u - 2u * 1024u) / 2u - 256u;
+
+static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl, int64_t n_tiles = 0, int force_meta_bufs = 0) {
     if (K < 1 || K > TC_MAXK || Cin < 1 || Cout < 1) return false;
     const int Cin_pad = (Cin + 7) / 8 * 8;
     pl.KC = (Cin_pad % 32 == 0) ? 32 : (Cin_pad % 16 == 0) ? 16 : 8;
@@ -761,11 +766,16 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl, int64_t n_tile
     pl.wp_bytes = (int64_t)K * pl.nchunks * pl.stageB;
     const uint32_t cpr = (uint32_t)pl.KC / 4u;
     const uint32_t a_bytes = 2u * ((cpr * (TC_BM * 16u + 128u / cpr) + 1023u) & ~1023u);
-    const uint32_t fixed = TC_NBUF * (uint32_t)(TC_BM * KT + TC_BM + TC_MAXK + 4) * 4u + 1536u;
+    // one metadata buffer is enough when no CTA can get a second tile (n_tiles <= resident CTAs, checked again below and
+    // in launch_tc); the double buffer only exists to prefetch the NEXT tile's table rows
+    B200SP_ENV_INT(env_mb, "B200SP_TC_META_BUFS", 0);  // dev knob: 2 = always double-buffered (round-2 behaviour before)
+    const int want_bufs = force_meta_bufs ? force_meta_bufs : (env_mb ? env_mb : ((n_tiles > 0 && n_tiles <= 2 * (int64_t)num_sms()) ? 1 : 2));
+    pl.meta_bufs = want_bufs;
+    const uint32_t fixed = (uint32_t)want_bufs * (uint32_t)(TC_BM * KT + TC_BM + TC_MAXK + 4) * 4u + 1536u;
     // slots: 4 under ~110 KB lets two CTAs share an SM; big stages fall back to fewer slots / one CTA per SM
     int best = 0;
     int smax = 4;
-    uint32_t two_cta_budget = 110u * 1024u;
+    uint32_t two_cta_budget = TC_TWO_CTA_SMEM;
     {
         B200SP_ENV_INT(env_slots, "B200SP_TC_SLOTS", 0);  // dev knob: > 4 trades the second CTA per SM for a deeper ring
         if (env_slots >= 2) {
@@ -818,6 +828,12 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl, int64_t n_tile
     uint32_t cols = 32;
     while (cols < (uint32_t)(TC_NBUF * pl.ni * pl.Cout_pad)) cols <<= 1;
     pl.tmem_cols = cols;
+    if (pl.meta_bufs == 1 && !force_meta_bufs) {
+        // residency this plan will get (launch_tc computes the same): a CTA must never see a second tile
+        int occ = budget == two_cta_budget && two_cta_budget > 0 ? 2 : 1;
+        while (occ > 1 && (uint32_t)occ * cols > 512u) --occ;
+        if (n_tiles > (int64_t)num_sms() * occ) return tc_plan(K, Cin, Cout, KT, pl, n_tiles, 2);
+    }
     return true;
 }
 
@@ -878,14 +894,16 @@ static int launch_tc(const TCParams& p0, int KT, int64_t n_in, cudaStream_t st) 
         if (env_tma && p.Cin % 4 == 0 && (reinterpret_cast<uintptr_t>(p.in) & 15) == 0 && p.Cin >= KC / 2)
             p.use_tma = make_gather_map(p.in, n_in > 0 ? n_in : ((int64_t)1 << 31) - 1, p.Cin, KC, &tmap) ? 1 : 0;
     }
-    const uint32_t smem = L::total(p.nslots, p.nslots_b, p.stageB_bytes, KT);
+    const uint32_t smem = L::total(p.nslots, p.nslots_b, p.stageB_bytes, KT, p.meta_bufs);
     static uint32_t attr_smem = 0;
     if (smem > attr_smem) {
         B200SP_CUDA(cudaFuncSetAttribute(k_conv_tc<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // two CTAs of up to 113 KB each only fit with the whole 228 KB carved out as shared memory
+        B200SP_CUDA(cudaFuncSetAttribute(k_conv_tc<KC>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
         attr_smem = smem;
     }
     // persistent grid: as many CTAs as fit on the machine (TMEM: 512 columns per SM), never more than tiles
-    int occ = smem <= 110u * 1024u ? 2 : 1;
+    int occ = smem <= TC_TWO_CTA_SMEM ? 2 : 1;
     while (occ > 1 && (uint32_t)occ * p.tmem_cols > 512u) --occ;
     if (p.nsplit > 1) {
         // split mode: p.nsplit is the WISH.  One tile per CTA, the nsplit CTAs of a row tile are one cluster (co-scheduled
@@ -953,6 +971,7 @@ static int launch_tc(const TCParams& p0, int KT, int64_t n_in, cudaStream_t st) 
         }
     }
     const int grid = std::min(p.total_tiles, num_sms() * occ);
+    B200SP_CHECK_ARG(p.meta_bufs == 2 || p.total_tiles <= grid, "conv_tc: single metadata buffer with %d tiles on %d CTAs", p.total_tiles, grid);
     B200SP_CUDA(launch_pdl(k_conv_tc<KC>, dim3((unsigned)grid), dim3(TC_THREADS), smem, st, p, tmap));
     B200SP_LAUNCH_CHECK();
     return B200SP_OK;
@@ -988,6 +1007,7 @@ int conv_tc_run(const float* in, int Cin, const float* W, int Ci_w, int Co_w, in
     p.res = res ? res : (accumulate ? out : nullptr);
     if (((uintptr_t)p.res & 15) != 0) return B200SP_EUNSUP;  // the epilogue reads it as float4
     p.nslots = pl.nslots; p.nslots_b = pl.nslots_b; p.stageB_bytes = pl.stageB; p.tmem_cols = pl.tmem_cols; p.ni = pl.ni;
+    p.meta_bufs = pl.meta_bufs;
     {
         B200SP_ENV_INT(env_dbg, "B200SP_TC_DEBUG", 0);
         p.dbg = env_dbg;
