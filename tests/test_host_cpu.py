@@ -250,3 +250,47 @@ def test_staged_reference_files_match_their_manifest():
             src = os.path.join("/root/reference", rel)
             if os.path.exists(src):
                 assert filecmp.cmp(src, os.path.join(stage_ref.DST, rel), shallow=False), rel
+
+
+def test_tape_plan_recognises_only_the_reference_shapes():
+    """doda_b200/tape.py: the structural match that decides whether a U-Net sub-tree may run as one autograd node
+    (host logic, no GPU): residual and VGG nets qualify with every parameter of the sub-tree accounted for; a sub-tree
+    with a foreign module, a conv bias or a missing ReLU does not, and a replaced module invalidates the cached plan"""
+    import torch
+    from torch import nn
+    from doda_b200 import tape, spconv
+    from doda_b200.unet import SparseConvNet
+    for residual in (True, False):
+        m = SparseConvNet(mid_channel=16, block_residual=residual)
+        p = tape.cached_plan(m.unet)
+        assert p is not None and p["tail"] is not None and p["child"] is not None
+        assert len(p["_params"]) == len(list(m.unet.parameters()))
+        assert {id(x) for x in p["_params"]} == {id(x) for x in m.unet.parameters()}
+        depth, q = 1, p
+        while q["tail"] is not None:
+            q, depth = q["child"], depth + 1
+        assert depth == 7
+        assert tape.cached_plan(m.unet) is p  # cached
+    m = SparseConvNet(mid_channel=16)
+    blk = m.unet.u.blocks.block0
+    old = blk.conv_branch._modules["1"]
+    blk.conv_branch._modules["1"] = nn.LeakyReLU()      # not the [BN, ReLU, conv] triplet any more
+    assert tape.plan(m.unet) is None and tape.plan(m.unet.u) is None and tape.plan(m.unet.u.u) is not None
+    blk.conv_branch._modules["1"] = old
+    assert tape.plan(m.unet) is not None
+    p0 = tape.cached_plan(m.unet)
+    blk.conv_branch._modules["0"] = nn.BatchNorm1d(32, eps=1e-4)   # what convert_dsnorm does: swap the norm modules
+    p1 = tape.cached_plan(m.unet)
+    assert p1 is not p0 and any(b is blk.conv_branch._modules["0"] for b in p1["_bns"])
+    m2 = SparseConvNet(mid_channel=16)
+    m2.unet.conv._modules["2"] = spconv.SparseConv3d(16, 32, kernel_size=2, stride=2, bias=True, indice_key="spconv1")
+    assert tape.plan(m2.unet) is None                     # a conv bias is outside what the per-layer executor fuses
+    # the arena: 256-byte aligned, grows by blocks, finds its own pointers again
+    ar = tape._Arena(torch.device("cpu"), first=1 << 10)
+    a, b = ar.take(100), ar.take(5000)
+    # (offsets inside a block are multiples of 256 bytes; CUDA blocks themselves start 512-byte aligned)
+    assert (a - ar.blocks[0].data_ptr()) % 256 == 0 and (b - ar.blocks[1].data_ptr()) % 256 == 0 and len(ar.blocks) == 2
+    t = ar.tensor(b, 50, 100)
+    assert t.shape == (50, 100) and t.data_ptr() == b
+    with pytest.raises(RuntimeError):
+        ar.tensor(12345, 1, 1)
