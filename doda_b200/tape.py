@@ -321,6 +321,11 @@ class UBlockTapeFunction(Function):
 # (`raw = False`), which stays as the A/B reference (`test_taped_ublock_*` runs both against the module path).
 # ---------------------------------------------------------------------------------------------------
 raw = _os.environ.get("B200SP_TAPE_RAW", "1") != "0"
+# raw form only: the compute stream does not wait for a layer's weight gradient (side stream) before it goes on with
+# the next layer -- every buffer a weight-gradient kernel reads lives in the arena until the sub-tree's backward ends,
+# where ONE join replaces the per-layer ones (the tensor form has to join per layer: its activations are freed as the
+# gradient passes)
+defer_join = _os.environ.get("B200SP_TAPE_DEFER_JOIN", "1") != "0"
 
 
 class _Arena(object):
@@ -405,12 +410,16 @@ def _r_triplet(bn, conv, x, t, ar, res=None):
             ws2 = _ops._workspace(_ops._conv_ws_bytes(K, Cout, Cin), ar.dev, "conv")
             cws_b, cwn_b = ws2.data_ptr(), ws2.numel()
         side = _ops._side_state(ar.dev) if (need_dw and _ops.async_wgrad and M <= _ops.async_wgrad_max_rows) else None
+        main = _ops._stream()
         rc = _ops._fast.layer_bwd(kid, rbp, xp, M, Cin, Wp, wb, K, Cout, g[0], g[1], 1, bwp, bbp, stats, y, bwsp, bwsn,
                                   cws_b, cwn_b, 1, 1 if need_dw else 0, dW.data_ptr() if dW is not None else None, dy, dx, dwb,
-                                  _ops._stream(), side[1] if side else None, side[2] if side else None,
-                                  side[3] if side else None, None, 0, add[0] if add is not None else None)
+                                  main, side[1] if side else None, side[2] if side else None,
+                                  side[3] if side else None, None, 1 if (side and defer_join) else 0,
+                                  add[0] if add is not None else None)
         if rc:
             _ops.check(rc, "conv_layer_bwd")
+        if side and defer_join:
+            grads["__join"] = (main, side[1], side[3])
         if dW is not None:
             grads[id(W)] = dW
         if bw_ is not None and bw_.requires_grad:
@@ -452,12 +461,15 @@ def _r_plain_conv(conv, x, t, ar):
             ws2 = _ops._workspace(_ops._conv_ws_bytes(K, Cout, Cin), ar.dev, "conv")
             cws_b, cwn_b = ws2.data_ptr(), ws2.numel()
         side = _ops._side_state(ar.dev) if (need_dw and _ops.async_wgrad and M <= _ops.async_wgrad_max_rows) else None
+        main = _ops._stream()
         rc = _ops._fast.layer_bwd(kid, rbp, None, M, Cin, Wp, wb, K, Cout, g[0], g[1], 0, None, None, None, xp, None, 0,
                                   cws_b, cwn_b, 1, 1 if need_dw else 0, dW.data_ptr() if dW is not None else None, dy, None,
-                                  None, _ops._stream(), side[1] if side else None, side[2] if side else None,
-                                  side[3] if side else None, None, 0, None)
+                                  None, main, side[1] if side else None, side[2] if side else None,
+                                  side[3] if side else None, None, 1 if (side and defer_join) else 0, None)
         if rc:
             _ops.check(rc, "conv_layer_bwd")
+        if side and defer_join:
+            grads["__join"] = (main, side[1], side[3])
         if dW is not None:
             grads[id(W)] = dW
         return (dy, M, Cin)
@@ -561,6 +573,12 @@ class UBlockRawTapeFunction(Function):
         except BaseException:
             _ops._drop_pending_join()
             raise
+        finally:
+            j = grads.get("__join")
+            if j is not None:  # the one join of the sub-tree: the compute stream waits for the last weight gradient
+                rc = _ops._fast.join(j[0], j[1], j[2])
+                if rc:
+                    _ops.check(rc, "stream_join")
         need = ctx.needs_input_grad
         out = []
         for i, prm in enumerate(ctx.params):
