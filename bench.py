@@ -36,7 +36,7 @@ UNIT = "scenes/s"
 
 
 WORKLOAD = "2x150k-voxel ScanNet-shape scenes, full SparseConvNet fwd+bwd, bs=%d, m=%d"
-SETTLE = 6  # extra untimed steps per timed loop (see main); reported in the JSON line's config
+SETTLE = 10  # extra untimed steps per timed loop (see main); reported in the JSON line's config
 
 
 def parse():
@@ -523,8 +523,9 @@ def main():
         step(resident)
     # untimed passes through the timing harness itself: with the host running ahead of the GPU the caching allocator
     # needs a few steps to reach its steady state (cudaMalloc inside a timed step is a 20-60 ms outlier)
+    # (each timed loop directly behind a settle loop of its OWN mode: switching between the resident and the host-fed
+    # loop changes the allocation sequence, and the first ~8 steps after a switch ran 0.5-1 ms slow on some boxes)
     timed(resident, SETTLE, False)
-    timed(host, SETTLE, True)
     if sampler:
         sampler.rows.clear()  # keep only samples taken during the timed regions
     calls0 = ops.launch_count()
@@ -532,6 +533,10 @@ def main():
     steps_ms = [round(v, 3) for v in timed.last_steps]
     mallocs = timed.last_mallocs
     launches = ops.launch_count() - calls0
+    rows_keep = list(sampler.rows) if sampler else []
+    timed(host, SETTLE, True)
+    if sampler:
+        sampler.rows[:] = rows_keep
     ms_e2e = timed(host, args.steps, True)
     scenes_per_step = args.bs * world
     value = scenes_per_step * args.steps / (ms_total / 1e3)
