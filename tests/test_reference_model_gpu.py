@@ -341,3 +341,47 @@ def test_reference_model_with_attached_tape_is_the_same_computation(ref, cuda_de
             assert rel_err(out[True][2][n], g) <= 1e-5, n
         else:
             assert torch.equal(out[True][2][n], g), n
+
+
+def test_attached_tape_follows_convert_dsnorm_and_domain_switches(ref, cuda_dev):
+    """tape.attach BEFORE convert_dsnorm: the cached plan must notice that every BatchNorm module was swapped for a
+    DSNorm (model/dsnorm.py:178-214) and the taped node must use the domain's own running statistics
+    (set_ds_source / set_ds_target, 335-344): bit-identical to the module-by-module execution of the same DSNorm net,
+    source and target passes"""
+    import copy
+    from model.dsnorm import DSNorm, set_ds_source, set_ds_target
+    from model.unet import SparseConvNet as RefNet, model_fn_decorator
+    from doda_b200 import tape
+    cfg = ref.make_cfg(mid_channel=16)
+    torch.manual_seed(4)
+    base = RefNet(cfg)
+    assert tape.attach(base) >= 1          # attached while the net still holds nn.BatchNorm1d modules
+    tape.cached_plan(base.unet)            # ... and a plan referring to them
+    net = DSNorm.convert_dsnorm(base).to(cuda_dev).train()
+    assert all(m.__class__.__name__ == "DSNorm" for m in tape.cached_plan(net.unet)["_bns"])
+    plain = copy.deepcopy(net)
+    for m in plain.modules():              # the twin runs module by module
+        m.__dict__.pop("forward", None)
+    model_fn = model_fn_decorator(cfg, 2)
+    b_src, b_tgt = _batch(4000, seeds=(20, 21)), _batch(4000, seeds=(22, 23))
+    outs = {}
+    for name, model, taped in (("taped", net, True), ("modules", plain, False)):
+        runs0 = tape.runs
+        model.apply(set_ds_source)
+        r_s = model_fn(b_src, model, 0)
+        r_s["loss"].backward()
+        model.apply(set_ds_target)
+        r_t = model_fn(b_tgt, model, 0)
+        r_t["loss"].backward()
+        assert (tape.runs - runs0 == 2) == taped
+        outs[name] = (r_s["output"].detach().clone(), r_t["output"].detach().clone(),
+                      {k: v.detach().clone() for k, v in model.state_dict().items()},
+                      {n: p.grad.detach().clone() for n, p in model.named_parameters()})
+    assert torch.equal(outs["taped"][0], outs["modules"][0]) and torch.equal(outs["taped"][1], outs["modules"][1])
+    for k, v in outs["modules"][2].items():
+        assert torch.equal(v, outs["taped"][2][k]), k
+    for n, g in outs["modules"][3].items():
+        if g.dim() >= 3:
+            assert rel_err(outs["taped"][3][n], g) <= 1e-5, n
+        else:
+            assert torch.equal(outs["taped"][3][n], g), n
