@@ -781,6 +781,11 @@ static bool tc_plan(int K, int Cin, int Cout, int KT, TCPlan& pl, int64_t n_tile
         if (env_slots >= 2) {
             smax = env_slots;
             if (smax > 4) two_cta_budget = 0;
+        } else if (n_tiles > 0 && n_tiles * 2 <= num_sms()) {
+            // few row tiles (split mode, levels 4-7 of DODA's net): even split 8 ways the layer has at most one CTA
+            // per SM, so the second CTA's shared memory buys a deeper ring instead (6 148 rows x 64: 28.4 -> 26.2 us)
+            smax = 6;
+            two_cta_budget = 0;
         }
     }
     uint32_t budget = 0;
